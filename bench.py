@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline metric on the B200-native tiled-diffusion hot path.
+
+Workload (config.workload): BASELINE configs[1] -- SD1.5 4096x4096 txt2img, MultiDiffusion,
+96x96 latent tiles, overlap 48 (the UI default), 50 sampler steps: latent [N=2, C=4, 512, 512]
+fp16, T = 100 tiles.  One bench "step" = one sampler step of the hot path:
+
+    td_scatter_tiles (latent -> [T*N,4,96,96] tile batch)  ->  [UNet: the host application's, stubbed]
+    ->  td_blend_multidiffusion (tile outputs -> blended fp32 latent)
+
+`value` = megapixels of final image per second = 16.777216 MP / (50 * seconds_per_step), inputs
+resident in HBM.  The UNet is NOT part of the path: its outputs are
+pre-generated synthetic tensors (25 batch tensors of 4 tiles), rotated over enough buffer sets that
+every launch reads cold (HBM-resident, not L2-resident) data.
+
+`e2e` = the same metric through the reference-facing class (MultiDiffusion.kdiff_forward, identity
+denoiser) with the step's latent copied from pinned host memory and the blended result copied back.
+
+`--impl reference` / `cpu_baseline` = the oracle port of the reference's PyTorch tile path
+(oracle/blend.py, bit-identical to the reference) on this box's host cores, identity denoiser.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+IMAGE_MP = 4096 * 4096 / 1e6
+SAMPLER_STEPS = 50
+CFG = dict(N=2, C=4, H=512, W=512, tile=96, overlap=48, tile_bs=4)
+METRIC = "megapixels/sec final image (SD1.5 4K MultiDiffusion)"
+
+
+def mp_per_s(sec_per_step: float) -> float:
+    return IMAGE_MP / (SAMPLER_STEPS * sec_per_step)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampler running while the GPU is under load (recipe in B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_reference_step_fn():
+    """The reference's PyTorch tile path (oracle port), identity denoiser, all host threads."""
+    from oracle import blend, synth, tiling
+    c = CFG
+    plan = tiling.GridPlan(c["W"], c["H"], c["tile"], c["tile"], c["overlap"], c["tile_bs"], False)
+    x = synth.latent(0, (c["N"], c["C"], c["H"], c["W"]), torch.float16)
+
+    def step():
+        return blend.multidiffusion_step(x, plan.batched_bboxes, plan.weights, lambda t, bb: t)
+    return step
+
+
+def run_cpu(steps: int, warmup: int, budget_s: float = None):
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    step = cpu_reference_step_fn()
+    for _ in range(max(warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps:
+        step()
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / done
+    return dt, done, threads
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    dt, done, threads = run_cpu(args.steps, args.warmup)
+    v = mp_per_s(dt)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "MP/s", "n_gpus": args.gpus, "steps": done,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(),
+        "cpu_baseline": {"value": v, "unit": "MP/s", "cores": threads, "kind": "port",
+                         "sample": f"{done} sampler steps of cfg2 (scatter+blend+normalise, identity denoiser), torch CPU"},
+        "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config():
+    c = CFG
+    return {"workload": "SD1.5 4096x4096 txt2img MultiDiffusion: latent [2,4,512,512] fp16, 96x96 tiles, overlap 48 "
+                        "(T=100, 25 batches of 4), 50 sampler steps; hot path = scatter + blend/normalise per step",
+            "denoiser": "stubbed (UNet belongs to the host application; tile outputs are pre-generated synthetic tensors)",
+            "l2": "inputs larger than L2: buffer sets rotate (see buffer_sets / set_mb)",
+            **{k: c[k] for k in ("N", "C", "H", "W", "tile", "overlap", "tile_bs")}}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+class Workload:
+    def __init__(self, device, rank, world, nsets):
+        from multidiffusion_upscaler_for_automatic1111_b200 import _cabi, engine
+        from oracle import synth
+        self.cabi, self.engine = _cabi, engine
+        c = CFG
+        self.dev, self.rank, self.world = device, rank, world
+        self.N, self.C = c["N"], c["C"]
+        self.g = engine.make_grid(c["W"], c["H"], c["tile"], c["tile"], c["overlap"], c["tile_bs"])
+        g = self.g
+        self.T = g.num_tiles
+        self.weights = torch.from_numpy(engine.grid_weights(g)).to(device)
+        # tile shard of this rank (contiguous chunk of the row-major tile list)
+        self.chunk = -(-self.T // world)
+        self.t0 = min(rank * self.chunk, self.T)
+        self.t1 = min(self.t0 + self.chunk, self.T)
+        self.nsets = nsets
+        base = synth.latent(0, (self.N, self.C, g.H, g.W), torch.float16).to(device)
+        tile_shape = (self.N, self.C, g.tile_h, g.tile_w)
+        self.x, self.tiles_in, self.outs, self.x_out, self.gathered = [], [], [], [], []
+        for s in range(nsets):
+            self.x.append(base.roll(s, 3).contiguous())
+            self.tiles_in.append(torch.empty(((self.t1 - self.t0) * self.N,) + tile_shape[1:], dtype=torch.float16, device=device))
+            if world == 1:
+                outs = []
+                for b in range(g.num_batches):
+                    nt = min(g.tile_bs, self.T - b * g.tile_bs)
+                    outs.append((torch.randn((nt * self.N,) + tile_shape[1:], device=device, dtype=torch.float32) * 0.8).half())
+                self.outs.append(outs)
+            else:
+                self.outs.append([(torch.randn((self.chunk * self.N,) + tile_shape[1:], device=device) * 0.8).half()])
+                self.gathered.append(torch.empty((world * self.chunk * self.N,) + tile_shape[1:], dtype=torch.float16, device=device))
+            self.x_out.append(torch.empty((self.N, self.C, g.H, g.W), dtype=torch.float32, device=device))
+        es = 2
+        self.bytes_scatter = (self.N * self.C * g.H * g.W + (self.t1 - self.t0) * self.N * self.C * g.tile_h * g.tile_w) * es
+        self.bytes_blend = self.T * self.N * self.C * g.tile_h * g.tile_w * es + self.N * self.C * g.H * g.W * 4 + g.H * g.W * 4
+        self.set_mb = (self.x[0].numel() * 2 + self.tiles_in[0].numel() * 2 + sum(o.numel() for o in self.outs[0]) * 2 +
+                       self.x_out[0].numel() * 4 + (self.gathered[0].numel() * 2 if self.gathered else 0)) / 1e6
+        self.stream = ctypes.c_void_p(0)
+        self._tables = []
+        for s in range(nsets):
+            if world == 1:
+                ts = self.outs[s]
+                self._tables.append(((ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts]), len(ts), g.tile_bs))
+            else:
+                stride = self.chunk * self.N * self.C * g.tile_h * g.tile_w * es
+                basep = self.gathered[s].data_ptr()
+                nb = -(-self.T // self.chunk)
+                self._tables.append(((ctypes.c_void_p * nb)(*[basep + b * stride for b in range(nb)]), nb, self.chunk))
+
+    def set_stream(self):
+        self.stream = self.cabi.current_stream_ptr(self.dev)
+
+    def scatter(self, s):
+        c = self.cabi
+        c.check(c.lib.td_scatter_tiles(ctypes.byref(self.g), self.x[s].data_ptr(), self.tiles_in[s].data_ptr(), self.N, self.C,
+                                       c.TD_F16, self.t0, self.t1, 0, self.stream))
+
+    def exchange(self, s):
+        if self.world > 1:
+            torch.distributed.all_gather_into_tensor(self.gathered[s], self.outs[s][0])
+
+    def blend(self, s):
+        c = self.cabi
+        ptrs, nb, tbs = self._tables[s]
+        c.check(c.lib.td_blend_multidiffusion(ctypes.byref(self.g), ptrs, nb, tbs, self.N, self.C, c.TD_F16, c.TD_F16,
+                                              self.weights.data_ptr(), self.x_out[s].data_ptr(), None, 0, self.stream))
+
+    def step(self, i):
+        s = i % self.nsets
+        self.scatter(s)
+        self.exchange(s)
+        self.blend(s)
+
+
+def timed_graph_loop(fn_step, steps, stream, chunk=1024):
+    """Capture `steps` hot-path steps into CUDA graphs (chunks of <= `chunk`) and return a replay closure."""
+    graphs = []
+    done = 0
+    while done < steps:
+        n = min(chunk, steps - done)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for i in range(done, done + n):
+                fn_step(i)
+        graphs.append(g)
+        done += n
+
+    def replay():
+        for g in graphs:
+            g.replay()
+    return replay
+
+
+def event_time_ms(fn, stream):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def gpu_arm(args, rank, world, local_rank):
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    peak, peak_src = load_peaks()
+    nsets = args.buffer_sets
+    wl = Workload(dev, rank, world, nsets)
+    stream = torch.cuda.Stream(dev)
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+
+    with torch.cuda.stream(stream):
+        wl.set_stream()
+        for i in range(max(args.warmup, 3)):          # eager warm-up steps
+            wl.step(i)
+        torch.cuda.synchronize()
+        use_graph = not args.no_graph
+        if use_graph:
+            replay = timed_graph_loop(wl.step, args.steps, stream)
+            replay()                                   # extra untimed warm-up of the instantiated graphs
+        else:
+            def replay():
+                for i in range(args.steps):
+                    wl.step(i)
+        torch.cuda.synchronize()
+        barrier()
+        ms = event_time_ms(replay, stream)             # EXACTLY args.steps steps
+        barrier()
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+        sec_per_step = ms / 1e3 / args.steps
+
+        # --- per-kernel duration for the roofline (same buffers, same stream, CUDA events) -------------
+        roof = None
+        if rank == 0:
+            reps = max(args.steps, 2000)
+            def only(fn):
+                r = timed_graph_loop(lambda i: fn(i % nsets), reps, stream)
+                r()
+                return event_time_ms(r, stream) / reps * 1e-3
+            t_blend = only(wl.blend)
+            t_scatter = only(wl.scatter)
+            roof = {
+                "bound": "hbm", "kernel": "blend_grid_vec_kernel<half, MODE_MD> (td_blend_multidiffusion)",
+                "achieved": wl.bytes_blend / t_blend / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": wl.bytes_blend / t_blend / 1e9 / peak, "traffic": load_traffic("blend"),
+                "peak_source": peak_src, "algorithmic_bytes": wl.bytes_blend, "avg_launch_us": t_blend * 1e6,
+                "scatter": {"kernel": "scatter_vec_kernel<half> (td_scatter_tiles)", "achieved": wl.bytes_scatter / t_scatter / 1e9,
+                            "frac": wl.bytes_scatter / t_scatter / 1e9 / peak, "algorithmic_bytes": wl.bytes_scatter,
+                            "avg_launch_us": t_scatter * 1e6, "traffic": load_traffic("scatter")},
+                "note": "back-to-back launches inside a CUDA graph; avg includes the inter-kernel dependency gap",
+            }
+
+        # --- e2e through the public class API with host buffers ----------------------------------------
+        e2e = e2e_arm(args, dev, stream, world, rank) if world == 1 else None
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        cpu_dt, cpu_done, cpu_threads = run_cpu(10 ** 9, 2, budget_s=args.cpu_budget)
+        line = {
+            "metric": METRIC, "value": mp_per_s(sec_per_step), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {**workload_config(), "buffer_sets": nsets, "set_mb": round(wl.set_mb, 1),
+                       "cuda_graph": use_graph,
+                       "parallelism": "single GPU" if world == 1 else f"tile-shard over {world} ranks, NCCL all-gather of tile outputs, replicated blend"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (2 if world == 1 else 2),
+            "roofline": roof,
+            "cpu_baseline": {"value": mp_per_s(cpu_dt), "unit": "MP/s", "cores": cpu_threads, "kind": "port",
+                             "ms_per_step": cpu_dt * 1e3,
+                             "sample": f"{cpu_done} sampler steps of the same workload (oracle port of the reference's "
+                                       f"PyTorch tile path, identity denoiser, torch CPU, {cpu_threads} threads)"},
+            "impl": "b200",
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def load_traffic(kernel: str):
+    """dram bytes per launch from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(kernel)
+    except Exception:
+        return None
+
+
+def e2e_arm(args, dev, stream, world, rank):
+    """Same metric through MultiDiffusion.kdiff_forward with pinned-host input and host read-back each step."""
+    import types
+
+    from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
+    from oracle import synth
+    c = CFG
+    inner = types.SimpleNamespace(forward=lambda x, sigma, cond=None: x)  # identity denoiser
+    sampler = types.SimpleNamespace(model_wrap_cfg=types.SimpleNamespace(inner_model=inner, image_cfg_scale=None))
+    p = types.SimpleNamespace(width=c["W"] * 8, height=c["H"] * 8, sampler_name="Euler a")
+    d = MultiDiffusion(p, sampler)
+    d.init_grid_bbox(c["tile"], c["tile"], c["overlap"], c["tile_bs"])
+    d.init_done()
+    d.hook()
+    fwd = sampler.model_wrap_cfg.inner_model.forward
+    x_host = synth.latent(0, (c["N"], c["C"], c["H"], c["W"]), torch.float16).pin_memory()
+    out_host = torch.empty((c["N"], c["C"], c["H"], c["W"]), dtype=torch.float32).pin_memory()
+    x_dev = torch.empty_like(x_host, device=dev)
+    sigma = torch.ones(c["N"], device=dev, dtype=torch.float16)
+    cond = {"c_crossattn": [torch.zeros(c["N"], 77, 768, device=dev, dtype=torch.float16)],
+            "c_concat": [torch.zeros(c["N"], 5, 1, 1, device=dev, dtype=torch.float16)]}
+
+    def step():
+        x_dev.copy_(x_host, non_blocking=True)
+        out = fwd(x_dev, sigma, cond=cond)
+        out_host.copy_(out, non_blocking=True)
+
+    n = max(20, min(args.steps, 200))
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ms = event_time_ms(lambda: [step() for _ in range(n)], stream)
+    wall = time.perf_counter() - t0
+    sec = max(ms / 1e3, wall) / n   # host-bound loops are charged wall time
+    return {"value": mp_per_s(sec), "unit": "MP/s", "h2d_bytes_per_step": x_host.numel() * 2,
+            "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": sec * 1e3, "steps": n,
+            "api": "MultiDiffusion.kdiff_forward (hooked inner_model.forward), identity denoiser, 25 tile batches"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--buffer-sets", type=int, default=8)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        sys.exit(f"--gpus {args.gpus} needs torchrun (WORLD_SIZE={world})")
+    gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

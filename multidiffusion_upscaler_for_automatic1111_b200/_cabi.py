@@ -1,0 +1,106 @@
+"""ctypes binding of libtd_b200.so (the C-ABI declared in include/td_b200.h).
+
+There is NO fallback: if the shared library is missing or does not export a
+symbol the header declares, importing this module raises.  The product path
+never routes through `oracle/` or a PyTorch re-implementation.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libtd_b200.so")
+
+TD_OK = 0
+TD_ERR_INVALID_ARG, TD_ERR_UNSUPPORTED, TD_ERR_CUDA, TD_ERR_CAPACITY = -1, -2, -3, -4
+TD_F16, TD_BF16, TD_F32 = 0, 1, 2
+TD_FLAG_FORCE_GENERIC = 1
+TD_MAX_GRID_DIM = 256
+TD_MAX_BATCH_PTRS = 128
+ABI_VERSION = 1
+
+DTYPE_CODE = {torch.float16: TD_F16, torch.bfloat16: TD_BF16, torch.float32: TD_F32}
+
+
+class TdError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"td_b200 error {status}: {message}")
+        self.status = status
+
+
+class TdGrid(ctypes.Structure):
+    """struct td_grid (include/td_b200.h)."""
+    _fields_ = [
+        ("H", c_int32), ("W", c_int32),
+        ("tile_h", c_int32), ("tile_w", c_int32),
+        ("overlap", c_int32),
+        ("rows", c_int32), ("cols", c_int32),
+        ("num_tiles", c_int32), ("num_batches", c_int32), ("tile_bs", c_int32),
+        ("ys", c_int32 * TD_MAX_GRID_DIM),
+        ("xs", c_int32 * TD_MAX_GRID_DIM),
+    ]
+
+
+# symbol -> (restype, argtypes); must list EVERY function td_b200.h declares
+_SIGNATURES = {
+    "td_last_error": (c_char_p, []),
+    "td_abi_version": (c_int, []),
+    "td_split_bboxes": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int), POINTER(c_int)]),
+    "td_splitable": (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    "td_gaussian_weights": (c_int, [c_int, c_int, POINTER(c_float)]),
+    "td_grid_init": (c_int, [POINTER(TdGrid), c_int, c_int, c_int, c_int, c_int, c_int]),
+    "td_grid_weights": (c_int, [POINTER(TdGrid), POINTER(c_float), POINTER(c_float)]),
+    "td_rescale_factor": (c_int, [POINTER(c_float), POINTER(c_float), c_int64]),
+    "td_scatter_tiles": (c_int, [POINTER(TdGrid), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_uint32, c_void_p]),
+    "td_blend_multidiffusion": (c_int, [POINTER(TdGrid), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
+    "td_blend_mixture": (c_int, [POINTER(TdGrid), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
+}
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found. Build it with `python -m multidiffusion_upscaler_for_automatic1111_b200.build` "
+            "(needs nvcc). There is no CPU / PyTorch fallback for this path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise ImportError(f"{LIB_PATH} does not export `{name}` declared in include/td_b200.h") from e
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.td_abi_version() != ABI_VERSION:
+        raise ImportError(f"ABI mismatch: library {lib.td_abi_version()} vs binding {ABI_VERSION}; rebuild")
+    return lib
+
+
+lib = _load()
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(status: int) -> int:
+    """Raise TdError for a negative td_status; pass non-negative results through."""
+    if status < 0:
+        raise TdError(status, lib.td_last_error().decode("utf-8", "replace"))
+    return status
+
+
+def current_stream_ptr(device=None) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    try:
+        return DTYPE_CODE[dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {dtype}; this path handles float16 / bfloat16 / float32") from None

@@ -1,0 +1,123 @@
+"""Tensor-level wrappers over the C-ABI kernels (device pointers + current stream).
+
+PyTorch is plumbing here: it owns the memory and the stream; every byte of the
+hot path moves through the hand-written sm_100a kernels in csrc/.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._cabi import TdGrid, check, current_stream_ptr, dtype_code, lib
+
+
+def make_grid(w: int, h: int, tile_w: int, tile_h: int, overlap: int, tile_bs: int) -> TdGrid:
+    """init_grid_bbox bookkeeping (abstractdiffusion.py:172-186) -> td_grid."""
+    g = TdGrid()
+    check(lib.td_grid_init(ctypes.byref(g), int(w), int(h), int(tile_w), int(tile_h), int(overlap), int(tile_bs)))
+    return g
+
+
+def grid_bboxes_xywh(g: TdGrid) -> np.ndarray:
+    """int32 [T,4] (x, y, w, h) in tile-list order (row outer, col inner)."""
+    xs = np.ctypeslib.as_array(g.xs)[:g.cols]
+    ys = np.ctypeslib.as_array(g.ys)[:g.rows]
+    out = np.empty((g.rows, g.cols, 4), dtype=np.int32)
+    out[..., 0] = xs[None, :]
+    out[..., 1] = ys[:, None]
+    out[..., 2] = g.tile_w
+    out[..., 3] = g.tile_h
+    return out.reshape(-1, 4)
+
+
+def grid_weights(g: TdGrid, tile_weights: Optional[np.ndarray] = None) -> np.ndarray:
+    """fp32 [H, W] host weight canvas (utils.py:167,175)."""
+    out = np.empty((g.H, g.W), dtype=np.float32)
+    tw_ptr = None
+    if tile_weights is not None:
+        tile_weights = np.ascontiguousarray(tile_weights, dtype=np.float32)
+        if tile_weights.shape != (g.tile_h, g.tile_w):
+            raise ValueError(f"tile_weights shape {tile_weights.shape} != tile {(g.tile_h, g.tile_w)}")
+        tw_ptr = tile_weights.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    check(lib.td_grid_weights(ctypes.byref(g), tw_ptr, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
+    return out
+
+
+def rescale_factor(weights: np.ndarray) -> np.ndarray:
+    """1 / weights in fp32 (mixtureofdiffusers.py:32)."""
+    weights = np.ascontiguousarray(weights, dtype=np.float32)
+    out = np.empty_like(weights)
+    check(lib.td_rescale_factor(weights.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), weights.size))
+    return out
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor: this path has no CPU fallback (got device {t.device})")
+
+
+def scatter_tiles(g: TdGrid, x: torch.Tensor, out: Optional[torch.Tensor] = None, tile_begin: int = 0,
+                  tile_end: Optional[int] = None, flags: int = 0) -> torch.Tensor:
+    """x [N,C,H,W] -> tiles [(tile_end-tile_begin)*N, C, th, tw], tile-major (multidiffusion.py:155)."""
+    _require_cuda(x, "x")
+    if x.dim() != 4 or x.shape[2] != g.H or x.shape[3] != g.W:
+        raise ValueError(f"x shape {tuple(x.shape)} does not match the grid canvas {(g.H, g.W)}")
+    x = x.contiguous()
+    N, C = x.shape[0], x.shape[1]
+    tile_end = g.num_tiles if tile_end is None else tile_end
+    shape = ((tile_end - tile_begin) * N, C, g.tile_h, g.tile_w)
+    if out is None or tuple(out.shape) != shape or out.dtype != x.dtype or out.device != x.device:
+        out = torch.empty(shape, dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.td_scatter_tiles(ctypes.byref(g), x.data_ptr(), out.data_ptr(), N, C, dtype_code(x.dtype),
+                                   int(tile_begin), int(tile_end), int(flags), current_stream_ptr(x.device)))
+    return out
+
+
+def _batch_table(g: TdGrid, batch_outs: Sequence[torch.Tensor], N: int, C: int, tile_bs: int):
+    if len(batch_outs) == 0:
+        raise ValueError("no tile outputs to blend")
+    dt = batch_outs[0].dtype
+    keep = []
+    for b, t in enumerate(batch_outs):
+        _require_cuda(t, "tile output")
+        n_tiles = min(tile_bs, g.num_tiles - b * tile_bs)
+        want = (n_tiles * N, C, g.tile_h, g.tile_w)
+        if tuple(t.shape) != want:
+            raise ValueError(f"tile batch {b} has shape {tuple(t.shape)}, expected {want}")
+        if t.dtype != dt:
+            t = t.to(dt)
+        keep.append(t.contiguous())
+    ptrs = (ctypes.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
+    return ptrs, keep, dt
+
+
+def blend_multidiffusion(g: TdGrid, batch_outs: Sequence[torch.Tensor], N: int, C: int, tile_bs: int,
+                         weights: torch.Tensor, acc_dtype: torch.dtype, x_buffer: Optional[torch.Tensor] = None,
+                         flags: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused multidiffusion.py:166-167 + :208.  Returns fp32 [N,C,H,W] (fresh unless `out` is given)."""
+    ptrs, keep, tdt = _batch_table(g, batch_outs, N, C, tile_bs)
+    dev = keep[0].device
+    x_out = out if out is not None else torch.empty((N, C, g.H, g.W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.td_blend_multidiffusion(ctypes.byref(g), ptrs, len(keep), int(tile_bs), N, C, dtype_code(tdt),
+                                          dtype_code(acc_dtype), weights.data_ptr(), x_out.data_ptr(),
+                                          x_buffer.data_ptr() if x_buffer is not None else None, int(flags),
+                                          current_stream_ptr(dev)))
+    return x_out
+
+
+def blend_mixture(g: TdGrid, batch_outs: Sequence[torch.Tensor], N: int, C: int, tile_bs: int,
+                  tile_weights: torch.Tensor, rescale: torch.Tensor, x_buffer: torch.Tensor, flags: int = 0) -> torch.Tensor:
+    """mixtureofdiffusers.py:122-126; writes and returns x_buffer."""
+    ptrs, keep, tdt = _batch_table(g, batch_outs, N, C, tile_bs)
+    dev = keep[0].device
+    with torch.cuda.device(dev):
+        check(lib.td_blend_mixture(ctypes.byref(g), ptrs, len(keep), int(tile_bs), N, C, dtype_code(tdt),
+                                   dtype_code(x_buffer.dtype), tile_weights.data_ptr(), rescale.data_ptr(),
+                                   x_buffer.data_ptr(), int(flags), current_stream_ptr(dev)))
+    return x_buffer

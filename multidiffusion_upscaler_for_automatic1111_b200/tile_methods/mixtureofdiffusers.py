@@ -1,0 +1,122 @@
+"""Mixture of Diffusers tile method with the reference's surface
+(tile_methods/mixtureofdiffusers.py): hooks `sd_model.apply_model`, fuses the
+per-tile eps with gaussian weights that are pre-normalised by 1/sum(weights).
+
+Per UNet call: td_scatter_tiles + td_blend_mixture (the reference: T/TB cats and
+3T elementwise kernels).  The blend reproduces `w = tile_weights *
+rescale_factor[slicer]; x_buffer[slicer] += eps * w` with the same separate
+roundings, so results are bit-identical to the reference.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+from torch import Tensor
+
+from .. import engine, host
+from ..tile_utils.utils import BBox, custom_bbox, gaussian_weights, grid_bbox, keep_signature
+from .abstractdiffusion import AbstractDiffusion, CondDict
+
+
+class MixtureOfDiffusers(AbstractDiffusion):
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.custom_weights: List[Tensor] = []
+        self.get_weight = gaussian_weights
+
+    def hook(self):
+        """mixtureofdiffusers.py:18-21."""
+        sd_model = self._sd_model()
+        if not hasattr(sd_model, "apply_model_original_md"):
+            sd_model.apply_model_original_md = sd_model.apply_model
+        sd_model.apply_model = self.apply_model_hijack
+        self._hooked_model = sd_model
+
+    @staticmethod
+    def unhook():
+        """mixtureofdiffusers.py:23-27."""
+        sd_model = getattr(host.get_shared(), "sd_model", None)
+        if sd_model is not None and hasattr(sd_model, "apply_model_original_md"):
+            sd_model.apply_model = sd_model.apply_model_original_md
+            del sd_model.apply_model_original_md
+
+    def init_done(self):
+        """mixtureofdiffusers.py:29-36: rescale_factor = 1 / weights, once, in fp32."""
+        super().init_done()
+        w_host = self.weights.detach().to("cpu", torch.float32).numpy().reshape(self.h, self.w)
+        rf = engine.rescale_factor(w_host)
+        self.rescale_factor = torch.from_numpy(rf).view(1, 1, self.h, self.w).to(self.weights.device)
+
+    @grid_bbox
+    def get_tile_weights(self) -> Tensor:
+        """mixtureofdiffusers.py:38-43."""
+        if not hasattr(self, "tile_weights"):
+            self.tile_weights = self.get_weight(self.tile_w, self.tile_h)
+        return self.tile_weights
+
+    @custom_bbox
+    def init_custom_bbox(self, *args):
+        super().init_custom_bbox(*args)
+
+    @torch.no_grad()
+    @keep_signature
+    def apply_model_hijack(self, x_in: Tensor, t_in: Tensor, cond: CondDict, noise_inverse_step: int = -1):
+        """mixtureofdiffusers.py:61-179 (grid part).  Returns `x_buffer` (aliases delegate state, like the reference)."""
+        sd_model = self._sd_model()
+        c_in: CondDict = cond
+        N, C, H, W = x_in.shape
+        if (H, W) != (self.h, self.w):
+            self.reset_controlnet_tensors()
+            return sd_model.apply_model_original_md(x_in, t_in, c_in)
+
+        x = self._check_input(x_in)
+        if not self.draw_background:
+            raise NotImplementedError("draw_background=False needs region prompt control (SURVEY.md section 8(f)-1)")
+        self.reset_buffer(x)
+        if self.rescale_factor.device != x.device:
+            self.rescale_factor = self.rescale_factor.to(x.device)
+        if self.tile_weights.device != x.device:
+            self.tile_weights = self.tile_weights.to(x.device)
+
+        tiles = self._scatter_all(x)
+        icond_tiles = None
+        if isinstance(c_in, dict):
+            icond_full = self.get_icond(c_in)
+            if tuple(icond_full.shape[2:]) == (self.h, self.w):
+                icond_tiles = self._icond_tile_batches(icond_full)
+                n_icond = icond_full.shape[0]
+
+        outs = []
+        for batch_id, bboxes in enumerate(self.batched_bboxes):
+            if host.interrupted():
+                return x_in
+            n_rep = len(bboxes)
+            x_tile = self._tile_batch(tiles, batch_id, N)
+            t_tile = torch.cat([t_in] * n_rep, dim=0) if n_rep > 1 else t_in
+            if isinstance(c_in, dict):
+                tcond = self.get_tcond(c_in)
+                tcond_tile = torch.cat([tcond] * n_rep, dim=0) if n_rep > 1 else tcond
+                if icond_tiles is not None:
+                    icond_tile = self._tile_batch(icond_tiles, batch_id, n_icond)
+                else:
+                    icond = self.get_icond(c_in)
+                    icond_tile = torch.cat([icond] * n_rep, dim=0) if n_rep > 1 else icond
+                vcond = self.get_vcond(c_in)
+                vcond_tile = None if vcond is None else (torch.cat([vcond] * n_rep, dim=0) if n_rep > 1 else vcond)
+                c_tile = self.make_cond_dict(c_in, tcond_tile, icond_tile, vcond_tile)
+            else:
+                raise NotImplementedError("non-dict conditioning is not supported by Mixture of Diffusers "
+                                          "(the reference only prints a warning here, mixtureofdiffusers.py:103)")
+            self.switch_controlnet_tensors(batch_id, N, n_rep, is_denoise=True)
+            self.switch_stablesr_tensors(batch_id)
+            outs.append(sd_model.apply_model_original_md(x_tile, t_tile, c_tile))
+            self.update_pbar()
+
+        return engine.blend_mixture(self._grid, outs, N, C, self.tile_bs, self.tile_weights, self.rescale_factor,
+                                    self.x_buffer, flags=self._blend_flags)
+
+    @torch.no_grad()
+    def get_noise(self, x_in: Tensor, sigma_in: Tensor, cond_in: CondDict, step: int) -> Tensor:
+        return self.apply_model_hijack(x_in, sigma_in, cond=cond_in, noise_inverse_step=step)

@@ -1,0 +1,184 @@
+"""TEST INFRASTRUCTURE -- generate tests/golden/*.npz FROM THE UNMODIFIED REFERENCE.
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.make_golden
+
+Every array below is an output of the reference's own code
+(tile_utils/utils.py, tile_methods/{multidiffusion,mixtureofdiffusers}.py,
+scripts/tilevae.py) executed under the stub host of `oracle/ref_shim.py`, on the
+platform-stable synthetic inputs of `oracle/synth.py`.  The fixtures pin the
+oracle (tests/test_oracle_golden.py) and, through it and directly, the CUDA path.
+"""
+from __future__ import annotations
+
+import hashlib
+import itertools
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import ref_shim, synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+BBOX_SWEEP = [c for c in itertools.product([13, 64, 100, 128, 160, 512], [16, 64, 77, 128, 512],
+                                           [8, 16, 96, 128], [8, 24, 96, 128], [0, 4, 8, 16, 48, 64])]
+
+GRID_CASES = [  # (W, H, tile_w, tile_h, overlap, tile_bs)  latent units
+    (64, 64, 16, 16, 4, 4), (72, 72, 24, 16, 6, 3), (128, 128, 96, 96, 4, 4), (128, 128, 96, 96, 48, 4),
+    (100, 77, 32, 24, 8, 5), (160, 64, 96, 96, 48, 2), (64, 160, 200, 48, 16, 1), (57, 43, 16, 16, 12, 8),
+    (512, 512, 96, 96, 48, 4), (512, 512, 96, 96, 8, 4), (1024, 1024, 96, 96, 4, 8),
+]
+
+BLEND_CASES = [  # (name, N, C, W, H, tile_w, tile_h, overlap, tile_bs)
+    ("a", 2, 4, 72, 72, 24, 16, 6, 3),
+    ("b", 2, 4, 64, 48, 16, 16, 8, 4),
+    ("c", 1, 4, 57, 43, 16, 16, 12, 8),     # odd canvas: generic (non-vector) kernels
+    ("d", 3, 4, 96, 64, 40, 24, 4, 2),
+    ("e", 2, 4, 128, 128, 96, 96, 48, 4),   # the UI default tile at a small canvas
+]
+
+HASH_CASES = [  # full-size configs, only a sha256 of the output bytes is stored
+    ("cfg2_ov48", 2, 4, 512, 512, 96, 96, 48, 4),
+    ("cfg2_ov8", 2, 4, 512, 512, 96, 96, 8, 4),
+    ("cfg1", 2, 4, 1024, 1024, 96, 96, 4, 8),
+]
+
+DTYPES = {"f16": torch.float16, "bf16": torch.bfloat16, "f32": torch.float32}
+
+
+def _bits(t: torch.Tensor) -> np.ndarray:
+    t = t.contiguous()
+    if t.dtype == torch.float32:
+        return t.numpy().view(np.uint32)
+    return t.view(torch.int16).numpy().view(np.uint16)
+
+
+def sha(t: torch.Tensor) -> str:
+    return hashlib.sha256(_bits(t).tobytes()).hexdigest()
+
+
+def run_reference_step(ref, method: str, x: torch.Tensor, W, H, tw, th, ov, bs):
+    """One hooked denoiser call of the reference on latent x; fake UNet = synth.fake_denoise."""
+    N = x.shape[0]
+    p = ref_shim.make_p(W * 8, H * 8)
+    cond = {"c_crossattn": [torch.zeros(N, 2, 4)], "c_concat": [torch.zeros(N, 5, 1, 1)]}
+    state = {}
+
+    def unet(x_tile, sigma, cond=None):
+        return synth.fake_denoise(x_tile, state["bboxes"], N)
+
+    sampler = ref_shim.make_kdiff_sampler(unet)
+    cls = ref.multidiffusion.MultiDiffusion if method == "md" else ref.mixtureofdiffusers.MixtureOfDiffusers
+    d = cls(p, sampler)
+    d.init_grid_bbox(tw, th, ov, bs)
+    d.init_done()
+    d.pbar.disable = True
+    # the reference hands `bboxes` to repeat_func only; capture them for the fake UNet
+    if method == "md":
+        def repeat_func(x_tile, bboxes):
+            state["bboxes"] = bboxes
+            return unet(x_tile, None)
+        out = d.sample_one_step(x, None, repeat_func, None)
+    else:
+        batches = iter(d.batched_bboxes)
+
+        def apply_model(x_tile, t, c):
+            state["bboxes"] = next(batches)
+            return unet(x_tile, None)
+        ref.shared.sd_model.apply_model = apply_model
+        d.hook()
+        try:
+            out = ref.shared.sd_model.apply_model(x, torch.ones(N), cond)
+        finally:
+            d.unhook()
+        out = out.clone()
+    return d, out
+
+
+def main():
+    if not ref_shim.available():
+        sys.exit("reference tree not present; goldens can only be generated in the build container")
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    ref = ref_shim.load()
+    torch.set_num_threads(1)
+
+    # 1. split_bboxes sweep (utils.py:160-177) ------------------------------------
+    cases, counts, flat = [], [], []
+    for (w, h, tw, th, ov) in BBOX_SWEEP:
+        tw_, th_ = min(tw, w), min(th, h)
+        ov_ = max(0, min(ov, min(tw, th) - 4))
+        if tw_ <= ov_ or th_ <= ov_:
+            continue
+        bbs, _ = ref.utils.split_bboxes(w, h, tw_, th_, ov_, 1.0)
+        cases.append((w, h, tw_, th_, ov_))
+        counts.append(len(bbs))
+        flat += [(b.x, b.y, b.w, b.h) for b in bbs]
+    splitable = [(w * 8, h * 8, tw, th, ov, int(ref.utils.splitable(w * 8, h * 8, tw, th, ov)))
+                 for (w, h, tw, th, ov) in BBOX_SWEEP if tw > 4 and th > 4]
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "bboxes.npz"), cases=np.array(cases, np.int32),
+                        counts=np.array(counts, np.int32), xywh=np.array(flat, np.int32),
+                        splitable=np.array(splitable, np.int32))
+
+    # 2. gaussian weights (utils.py:180-194) --------------------------------------
+    g = {f"g_{tw}x{th}": ref.utils.gaussian_weights(tw, th).numpy() for (tw, th) in
+         [(96, 96), (64, 48), (128, 128), (16, 24), (24, 16), (33, 17), (192, 192)]}
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "gaussian.npz"), **g)
+
+    # 3. init_grid_bbox state (abstractdiffusion.py:172-186) + MoD rescale -------
+    out = {}
+    for i, (W, H, tw, th, ov, bs) in enumerate(GRID_CASES):
+        for method in ("md", "mod"):
+            p = ref_shim.make_p(W * 8, H * 8)
+            s = ref_shim.make_kdiff_sampler(lambda *a, **k: None)
+            cls = ref.multidiffusion.MultiDiffusion if method == "md" else ref.mixtureofdiffusers.MixtureOfDiffusers
+            d = cls(p, s)
+            d.init_grid_bbox(tw, th, ov, bs)
+            d.init_done()
+            d.pbar.disable = True
+            key = f"{i}_{method}"
+            out[key + "_scalars"] = np.array([d.tile_w, d.tile_h, d.num_tiles, d.num_batches, d.tile_bs], np.int32)
+            out[key + "_bboxes"] = np.array([(b.x, b.y, b.w, b.h) for bb in d.batched_bboxes for b in bb], np.int32)
+            out[key + "_batch_sizes"] = np.array([len(bb) for bb in d.batched_bboxes], np.int32)
+            if W * H <= 128 * 128:
+                out[key + "_weights"] = d.weights[0, 0].numpy()
+                if method == "mod":
+                    out[key + "_rescale"] = d.rescale_factor[0, 0].numpy()
+            else:
+                out[key + "_weights_sha"] = np.frombuffer(sha(d.weights).encode(), np.uint8)
+    out["cases"] = np.array(GRID_CASES, np.int32)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "grid_plans.npz"), **out)
+
+    # 4. one sampler step, small canvases, full outputs --------------------------
+    out = {"cases": np.array([c[1:] for c in BLEND_CASES], np.int32), "names": np.array([c[0] for c in BLEND_CASES])}
+    for (name, N, C, W, H, tw, th, ov, bs) in BLEND_CASES:
+        for dn, dt in DTYPES.items():
+            x = synth.latent(synth.case_seed(name, dn), (N, C, H, W), dt)
+            for method in ("md", "mod"):
+                _, o = run_reference_step(ref, method, x, W, H, tw, th, ov, bs)
+                out[f"{name}_{dn}_{method}"] = _bits(o)
+                out[f"{name}_{dn}_{method}_dtype"] = np.array(str(o.dtype))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "blend_small.npz"), **out)
+
+    # 5. full-size configs, hash only ---------------------------------------------
+    out = {"cases": np.array([c[1:] for c in HASH_CASES], np.int32), "names": np.array([c[0] for c in HASH_CASES])}
+    for (name, N, C, W, H, tw, th, ov, bs) in HASH_CASES:
+        for dn, dt in DTYPES.items():
+            if name == "cfg1" and dn != "f16":
+                continue
+            x = synth.latent(synth.case_seed(name, dn), (N, C, H, W), dt)
+            for method in ("md", "mod"):
+                _, o = run_reference_step(ref, method, x, W, H, tw, th, ov, bs)
+                out[f"{name}_{dn}_{method}"] = np.array(sha(o))
+                out[f"{name}_{dn}_{method}_dtype"] = np.array(str(o.dtype))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "blend_hashes.npz"), **out)
+
+    for f in sorted(os.listdir(GOLDEN_DIR)):
+        print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))
+
+
+if __name__ == "__main__":
+    main()

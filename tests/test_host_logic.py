@@ -1,0 +1,119 @@
+"""Host-side delegate logic that needs no GPU: construction, bookkeeping fields, error behaviour."""
+import types
+
+import pytest
+import torch
+
+
+def _p(w=1024, h=1024, sampler_name="Euler a"):
+    return types.SimpleNamespace(width=w, height=h, sampler_name=sampler_name)
+
+
+def _sampler():
+    inner = types.SimpleNamespace(forward=lambda x, s, cond=None: x)
+    return types.SimpleNamespace(model_wrap_cfg=types.SimpleNamespace(inner_model=inner, image_cfg_scale=None))
+
+
+def test_multidiffusion_fields_like_reference():
+    from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
+    d = MultiDiffusion(_p(4096, 4096), _sampler())
+    d.init_grid_bbox(96, 96, 48, 4)
+    d.init_done()
+    assert (d.w, d.h, d.tile_w, d.tile_h) == (512, 512, 96, 96)
+    assert (d.num_tiles, d.num_batches, d.tile_bs) == (100, 25, 4)
+    assert len(d.batched_bboxes) == 25 and all(len(b) == 4 for b in d.batched_bboxes)
+    assert d.weights.shape == (1, 1, 512, 512) and d.weights.dtype == torch.float32
+    assert float(d.weights.max()) == 9.0 and float(d.weights.min()) == 1.0
+    b = d.batched_bboxes[0][1]
+    assert b.box == [46, 0, 142, 96] and b.slicer[3] == slice(46, 142)
+    assert d.sampler_raw is d.sampler and d.method == "MultiDiffusion"
+
+
+def test_tile_bs_is_rebalanced():
+    from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
+    d = MultiDiffusion(_p(4096, 4096), _sampler())
+    d.init_grid_bbox(96, 96, 48, 8)  # 100 tiles / 8 -> 13 batches -> tile_bs 8 (ceil(100/13))
+    assert (d.num_batches, d.tile_bs) == (13, 8)
+    assert [len(b) for b in d.batched_bboxes] == [8] * 12 + [4]
+
+
+def test_unipc_rejected_and_nothing_to_paint():
+    from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
+    with pytest.raises(AssertionError):
+        MultiDiffusion(_p(sampler_name="UniPC"), _sampler())
+    d = MultiDiffusion(_p(), _sampler())
+    with pytest.raises(AssertionError, match="Nothing to paint"):
+        d.init_done()
+
+
+def test_hook_patches_inner_model_forward():
+    from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
+    s = _sampler()
+    orig = s.model_wrap_cfg.inner_model.forward
+    d = MultiDiffusion(_p(), s)
+    d.init_grid_bbox(96, 96, 48, 4)
+    d.init_done()
+    d.hook()
+    assert d.sampler_forward is orig
+    assert s.model_wrap_cfg.inner_model.forward == d.kdiff_forward
+
+
+def test_mixture_hook_unhook_roundtrip():
+    from multidiffusion_upscaler_for_automatic1111_b200 import MixtureOfDiffusers, host
+    model = types.SimpleNamespace(apply_model=lambda x, t, c: x, model=types.SimpleNamespace(conditioning_key="crossattn"),
+                                  cond_stage_key="txt")
+    orig = model.apply_model
+    host.use_shared(types.SimpleNamespace(state=types.SimpleNamespace(interrupted=False, sampling_step=0, sampling_steps=1),
+                                          sd_model=model))
+    try:
+        d = MixtureOfDiffusers(_p(), _sampler())
+        d.init_grid_bbox(96, 96, 48, 4)
+        d.init_done()
+        assert d.rescale_factor.shape == (1, 1, 128, 128)
+        d.hook()
+        assert model.apply_model == d.apply_model_hijack and model.apply_model_original_md is orig
+        MixtureOfDiffusers.unhook()
+        assert model.apply_model is orig and not hasattr(model, "apply_model_original_md")
+    finally:
+        host.use_shared(None)
+
+
+def test_hires_pass_is_not_tiled():
+    """(H, W) != (self.h, self.w): the original forward runs untiled (multidiffusion.py:141-144)."""
+    from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
+    d = MultiDiffusion(_p(), _sampler())
+    d.init_grid_bbox(96, 96, 48, 4)
+    d.init_done()
+    x = torch.zeros(2, 4, 64, 64)
+    out = d.sample_one_step(x, lambda t: t + 1, None, None)
+    assert torch.equal(out, x + 1)
+
+
+def test_cpu_tensor_is_refused_not_emulated():
+    from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
+    d = MultiDiffusion(_p(), _sampler())
+    d.init_grid_bbox(96, 96, 48, 4)
+    d.init_done()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        d.sample_one_step(torch.zeros(2, 4, 128, 128), None, lambda t, b: t, None)
+
+
+def test_out_of_scope_inits_raise():
+    from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
+    d = MultiDiffusion(_p(), _sampler())
+    for fn in (d.init_noise_inverse, d.init_controlnet, d.init_stablesr):
+        with pytest.raises(NotImplementedError):
+            fn()
+    with pytest.raises(NotImplementedError):
+        d.init_custom_bbox({}, True, False)
+
+
+def test_repeat_tensor_semantics():
+    from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
+    d = MultiDiffusion(_p(), _sampler())
+    a = torch.arange(6.0).view(1, 2, 3)
+    r = d.repeat_tensor(a, 4)
+    assert r.shape == (4, 2, 3) and r.data_ptr() == a.data_ptr()  # expand, not copy
+    b = torch.arange(4.0).view(2, 2)
+    assert torch.equal(d.repeat_tensor(b, 3), b.repeat(3, 1))
+    assert d.repeat_tensor(b, 1) is b
