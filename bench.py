@@ -121,10 +121,29 @@ def cpu_reference_step_fn():
     return step
 
 
+def pick_cpu_threads(step) -> int:
+    """Use the thread count at which the reference path is FASTEST on this host (tiny per-tile ops
+    get slower with too many OpenMP threads); the count used is reported as `cores`."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (1, 4, 8, 16, 32, 64, ncpu) if c <= ncpu})
+    best, best_t = 1, float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        step()
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+        elif dt > 3 * best_t:
+            break
+    return best
+
+
 def run_cpu(steps: int, warmup: int, budget_s: float = None):
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     step = cpu_reference_step_fn()
+    threads = pick_cpu_threads(step)
+    torch.set_num_threads(threads)
     for _ in range(max(warmup, 1)):
         step()
     t0 = time.perf_counter()
@@ -218,20 +237,24 @@ class Workload:
     def set_stream(self):
         self.stream = self.cabi.current_stream_ptr(self.dev)
 
-    def scatter(self, s):
+    def scatter(self, s, flags=0):
         c = self.cabi
         c.check(c.lib.td_scatter_tiles(ctypes.byref(self.g), self.x[s].data_ptr(), self.tiles_in[s].data_ptr(), self.N, self.C,
-                                       c.TD_F16, self.t0, self.t1, 0, self.stream))
+                                       c.TD_F16, self.t0, self.t1, flags, self.stream))
 
     def exchange(self, s):
         if self.world > 1:
             torch.distributed.all_gather_into_tensor(self.gathered[s], self.outs[s][0])
 
-    def blend(self, s):
+    def blend(self, s, flags=0):
         c = self.cabi
         ptrs, nb, tbs = self._tables[s]
         c.check(c.lib.td_blend_multidiffusion(ctypes.byref(self.g), ptrs, nb, tbs, self.N, self.C, c.TD_F16, c.TD_F16,
-                                              self.weights.data_ptr(), self.x_out[s].data_ptr(), None, 0, self.stream))
+                                              self.weights.data_ptr(), self.x_out[s].data_ptr(), None, flags, self.stream))
+
+    def empty(self, s):
+        c = self.cabi
+        c.check(c.lib.td_debug_launch_empty(1024, 128, self.stream))
 
     def step(self, i):
         s = i % self.nsets
@@ -317,6 +340,15 @@ def gpu_arm(args, rank, world, local_rank):
                 return event_time_ms(r, stream) / reps * 1e-3
             t_blend = only(wl.blend)
             t_scatter = only(wl.scatter)
+            if args.variants:
+                tbl = {"empty_1024x128": only(wl.empty)}
+                for name, fl in (("tma", 0), ("reg", 2)):
+                    tbl[f"blend_{name}"] = only(lambda s, fl=fl: wl.blend(s, fl))
+                    tbl[f"blend_{name}_no_tiles"] = only(lambda s, fl=fl: wl.blend(s, fl | 0x100))
+                    tbl[f"blend_{name}_L2hot"] = only(lambda s, fl=fl: wl.blend(0, fl))
+                    tbl[f"scatter_{name}"] = only(lambda s, fl=fl: wl.scatter(s, fl))
+                    tbl[f"scatter_{name}_L2hot"] = only(lambda s, fl=fl: wl.scatter(0, fl))
+                print("VARIANTS(us): " + json.dumps({k: round(v * 1e6, 2) for k, v in tbl.items()}), file=sys.stderr, flush=True)
             roof = {
                 "bound": "hbm", "kernel": "blend_grid_vec_kernel<half, MODE_MD> (td_blend_multidiffusion)",
                 "achieved": wl.bytes_blend / t_blend / 1e9, "peak": peak, "unit": "GB/s",
@@ -394,6 +426,16 @@ def e2e_arm(args, dev, stream, world, rank):
     for _ in range(5):
         step()
     torch.cuda.synchronize()
+    if args.profile_e2e:
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(25)
     t0 = time.perf_counter()
     ms = event_time_ms(lambda: [step() for _ in range(n)], stream)
     wall = time.perf_counter() - t0
@@ -411,6 +453,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--buffer-sets", type=int, default=8)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--profile-e2e", action="store_true")
+    ap.add_argument("--variants", action="store_true", help="print a table of per-kernel micro-timings to stderr")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -39,12 +39,16 @@ typedef enum td_dtype { TD_F16 = 0, TD_BF16 = 1, TD_F32 = 2 } td_dtype;
 
 /* blend flags */
 #define TD_FLAG_FORCE_GENERIC 1u /* use the scalar any-alignment kernel (test / fallback path) */
+#define TD_FLAG_NO_TMA 2u        /* skip the TMA kernels, use the register-staged vector kernels  */
+#define TD_FLAG_DBG_NO_TILES 0x100u /* measurement aid: skip all tile visits (launch + epilogue floor) */
 
 #define TD_MAX_GRID_DIM 256   /* max tile rows / cols of a grid plan            */
 #define TD_MAX_BATCH_PTRS 128 /* max UNet output batch tensors per blend launch */
 
 const char* td_last_error(void);
 int td_abi_version(void);
+/* measurement aid: an empty kernel launch (launch-latency floor of the bench harness) */
+int td_debug_launch_empty(int blocks, int threads, void* stream);
 
 /* ------------------------------------------------------------------------- *
  *  Host bookkeeping (integer-exact; Python float64 semantics reproduced with

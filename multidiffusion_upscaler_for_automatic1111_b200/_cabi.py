@@ -19,6 +19,8 @@ TD_OK = 0
 TD_ERR_INVALID_ARG, TD_ERR_UNSUPPORTED, TD_ERR_CUDA, TD_ERR_CAPACITY = -1, -2, -3, -4
 TD_F16, TD_BF16, TD_F32 = 0, 1, 2
 TD_FLAG_FORCE_GENERIC = 1
+TD_FLAG_NO_TMA = 2
+TD_FLAG_DBG_NO_TILES = 0x100
 TD_MAX_GRID_DIM = 256
 TD_MAX_BATCH_PTRS = 128
 ABI_VERSION = 1
@@ -49,6 +51,7 @@ class TdGrid(ctypes.Structure):
 _SIGNATURES = {
     "td_last_error": (c_char_p, []),
     "td_abi_version": (c_int, []),
+    "td_debug_launch_empty": (c_int, [c_int, c_int, c_void_p]),
     "td_split_bboxes": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int), POINTER(c_int)]),
     "td_splitable": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "td_gaussian_weights": (c_int, [c_int, c_int, POINTER(c_float)]),

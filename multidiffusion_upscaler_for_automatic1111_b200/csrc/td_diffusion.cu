@@ -20,10 +20,12 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <mutex>
 
 #include "td_b200.h"
 #include "td_device.cuh"
 #include "td_internal.h"
+#include "td_tma.cuh"
 
 namespace {
 
@@ -32,6 +34,8 @@ using namespace td;
 struct GeomParams {
     int H, W, th, tw, rows, cols, N, C;
     float inv_dx, inv_dy;  // 1/stride estimates for the origin search (any value is safe)
+    unsigned nc_magic, twv_magic;  // fast division by N*C and by tw/VEC (operands < 2^16)
+    int dbg_no_tiles;              // TD_FLAG_DBG_NO_TILES: skip every tile visit (measures the launch + epilogue floor)
     short ys[TD_MAX_GRID_DIM];
     short xs[TD_MAX_GRID_DIM];
 };
@@ -39,6 +43,7 @@ struct GeomParams {
 struct BlendParams {
     GeomParams g;
     int tile_bs, num_batches;
+    unsigned bs_magic;  // fast division by tile_bs
     long long tile_stride;  // N*C*th*tw elements
     const void* batch_ptrs[TD_MAX_BATCH_PTRS];
 };
@@ -60,37 +65,54 @@ __device__ __forceinline__ void load_origins(const GeomParams& g, short* s_ys, s
     __syncthreads();
 }
 
+// floor(n / d) for n, d < 2^16 with magic = ceil(2^32 / d); d == 1 is passed as magic 0.
+__device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned magic) { return magic ? __umulhi(n, magic) : n; }
+
 // ---------------------------------------------------------------------------
-// Scatter, vector path: one thread = one aligned 16-byte store into the tile
-// batch, fed by two aligned 16-byte loads of the (misaligned) canvas row.
+// Scatter, vector path.  One block = `rows_per_block` rows of one (tile, n, c)
+// plane; tile origin and the funnel shift are block-uniform.  Each thread moves
+// 16-byte vectors: two aligned 128-bit loads of the (misaligned) canvas row,
+// one aligned 128-bit store into the tile batch; 4 vectors in flight per thread.
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 scatter_vec_kernel(const __grid_constant__ GeomParams g, const T* __restrict__ x, T* __restrict__ tiles,
-                   int tile_begin, long long total_vecs) {
+                   int tile_begin, int rows_per_block) {
     constexpr int VEC = Vec<T>::kElems;
     constexpr int L2V = Vec<T>::kLog2;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total_vecs) return;
-    const int twv = g.tw >> L2V;
-    int rem_i;
-    long long rem = idx;
-    const int uv = (int)(rem % twv); rem /= twv;
-    const int v = (int)(rem % g.th); rem /= g.th;
-    const int plane = (int)(rem % (g.N * g.C)); rem /= (g.N * g.C);  // n*C + c
-    const int tl = (int)rem;                                        // tile index local to this launch
-    (void)rem_i;
-    const int t = tile_begin + tl;
+    constexpr int UNROLL = 4;
+    const unsigned tp = blockIdx.x;                       // (tile local, n, c) plane of the tile batch
+    const unsigned tl = fastdiv(tp, g.nc_magic);
+    const int plane = (int)(tp - tl * (unsigned)(g.N * g.C));
+    const int t = tile_begin + (int)tl;
     const int r = t / g.cols, c = t - r * g.cols;
-    const int y = (int)g.ys[r] + v;
-    const int u0 = (int)g.xs[c] + uv * VEC;  // first canvas column of this vector
-    const T* row = x + ((long long)plane * g.H + y) * g.W;
-    const int k = u0 >> L2V, s = u0 & (VEC - 1);
-    const uint4 A = ldg128(row + (size_t)k * VEC);
-    uint4 B = make_uint4(0, 0, 0, 0);
-    if (s != 0) B = ldg128(row + (size_t)(k + 1) * VEC);  // in-bounds: it holds element u0+VEC-1 < W, W % VEC == 0
-    const uint4 o = Vec<T>::window(A, B, s);
-    stg128(tiles + idx * VEC, o);  // idx enumerates the tile batch in memory order
+    const int xs = (int)g.xs[c], ys = (int)g.ys[r];
+    const int twv = g.tw >> L2V;
+    const int v0 = blockIdx.y * rows_per_block;
+    const int nvec = min(rows_per_block, g.th - v0) * twv;
+    const int s = xs & (VEC - 1), k0 = xs >> L2V;         // block-uniform shift
+    const T* src = x + ((long long)plane * g.H + ys + v0) * g.W;
+    T* dst = tiles + ((long long)tp * g.th + v0) * g.tw;
+    for (int base = threadIdx.x; base < nvec; base += 128 * UNROLL) {
+        uint4 A[UNROLL], B[UNROLL];
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q) {
+            const int i = base + q * 128;
+            A[q] = B[q] = make_uint4(0, 0, 0, 0);
+            if (i < nvec) {
+                const unsigned vi = fastdiv((unsigned)i, g.twv_magic);
+                const int uv = i - (int)vi * twv;
+                const T* row = src + (long long)vi * g.W + (long long)(k0 + uv) * VEC;
+                A[q] = ldg128(row);
+                if (s != 0) B[q] = ldg128(row + VEC);   // in-bounds: holds element xs+uv*VEC+VEC-1 < W, W % VEC == 0
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q) {
+            const int i = base + q * 128;
+            if (i < nvec) stg128(dst + (long long)i * VEC, Vec<T>::window(A[q], B[q], s));
+        }
+    }
 }
 
 // Scatter, generic path: any width / alignment, one element per thread.
@@ -111,105 +133,366 @@ scatter_generic_kernel(const __grid_constant__ GeomParams g, const T* __restrict
 
 // ---------------------------------------------------------------------------
 // Blend, vector path.
+//
+// Work decomposition: a warp owns an 8-vector x 8-row patch of one canvas plane
+// (lane = 8 vectors x 4 rows, 2 rows per thread); a block is 4 warps stacked in y.
+// The covering tile rows / cols are computed once per warp (uniform loops); a lane
+// takes part in a tile visit through predicated loads only.  Out-of-tile chunks are
+// never loaded and read as -0.0, the exact additive identity (x + -0.0 == x for
+// every x, signed zeros included), and because tw % VEC == 0 chunk validity IS
+// element validity -- so the MultiDiffusion path needs no per-element masks and
+// accumulates with packed HADD2: round_half(a + b) of the exact sum, which equals
+// torch's half(float(a) + float(b)) (fp32 has >= 2p+2 bits: double rounding is innocuous).
 // ---------------------------------------------------------------------------
+template <typename T> struct PackedAdd;  // acc (+)= e on one 32-bit word of packed T
+template <> struct PackedAdd<__half> {
+    __device__ static __forceinline__ uint32_t add(uint32_t a, uint32_t b) {
+        __half2 r = __hadd2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r);
+    }
+};
+template <> struct PackedAdd<__nv_bfloat16> {
+    __device__ static __forceinline__ uint32_t add(uint32_t a, uint32_t b) {
+        __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r);
+    }
+};
+template <> struct PackedAdd<float> {
+    __device__ static __forceinline__ uint32_t add(uint32_t a, uint32_t b) {
+        return __float_as_uint(__fadd_rn(__uint_as_float(a), __uint_as_float(b)));
+    }
+};
+
+constexpr int kBlendWarps = 2;       // warps per block, stacked in y
+constexpr int kWarpVecs = 8;         // vectors per warp row (lane = 8 vectors x 4 rows)
+constexpr int kGroup = 2;            // tile visits whose loads are in flight together
+
+template <int MODE> struct BlendShape { static constexpr int kRPT = (MODE == 0) ? 4 : 2; };  // rows per thread
+
 template <typename T, int MODE, bool WRITE_BUF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBlendWarps * 32)
 blend_grid_vec_kernel(const __grid_constant__ BlendParams p, const float* __restrict__ weights,
                       const float* __restrict__ tile_weights, const float* __restrict__ rescale,
-                      float* __restrict__ out_f32, T* __restrict__ out_buf, long long total_vecs) {
+                      float* __restrict__ out_f32, T* __restrict__ out_buf) {
     constexpr int VEC = Vec<T>::kElems;
     constexpr int L2V = Vec<T>::kLog2;
+    constexpr int RPT = BlendShape<MODE>::kRPT;
+    constexpr int WROWS = 4 * RPT;                 // rows per warp patch
+    constexpr uint32_t NEG0 = sizeof(T) == 2 ? 0x80008000u : 0x80000000u;
     __shared__ short s_ys[TD_MAX_GRID_DIM];
     __shared__ short s_xs[TD_MAX_GRID_DIM];
     const GeomParams& g = p.g;
     load_origins(g, s_ys, s_xs);
 
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total_vecs) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = lane & 7, ly = lane >> 3;
+    const int plane = blockIdx.z;
     const int wv = g.W >> L2V;
-    long long rem = idx;
-    const int xv = (int)(rem % wv); rem /= wv;
-    const int y = (int)(rem % g.H); rem /= g.H;
-    const int plane = (int)rem;  // n*C + c
+    const int xv0 = blockIdx.x * kWarpVecs;                           // warp's first vector
+    const int yw = (blockIdx.y * kBlendWarps + warp) * WROWS;         // warp's first row
+    if (yw >= g.H) return;                                            // warp-uniform
+    const int x_lo = xv0 * VEC, x_hi = min(x_lo + kWarpVecs * VEC, g.W) - 1;
+    const int y_hi = min(yw + WROWS, g.H) - 1;
+
+    // tiles touching this warp's patch (uniform across the warp)
+    const int r_lo = last_le(s_ys, g.rows, yw - g.th, g.inv_dy) + 1;
+    const int r_hi = last_le(s_ys, g.rows, y_hi, g.inv_dy);
+    const int c_lo = last_le(s_xs, g.cols, x_lo - g.tw, g.inv_dx) + 1;
+    const int c_hi = last_le(s_xs, g.cols, x_hi, g.inv_dx);
+    const int nc = c_hi - c_lo + 1;
+    const int nv = g.dbg_no_tiles ? 0 : (r_hi - r_lo + 1) * nc;       // visits, in ascending tile index
+
+    const int xv = xv0 + lx;
+    const bool x_ok = xv < wv;
     const int x0 = xv * VEC;
-
-    // covering tile rows for y, covering tile cols for any pixel of [x0, x0+VEC)
-    const int r_lo = last_le(s_ys, g.rows, y - g.th, g.inv_dy) + 1;
-    const int r_hi = last_le(s_ys, g.rows, y, g.inv_dy);
-    const int c_lo = last_le(s_xs, g.cols, x0 - g.tw, g.inv_dx) + 1;
-    const int c_hi = last_le(s_xs, g.cols, x0 + VEC - 1, g.inv_dx);
-
-    float acc[VEC];
+    int y[RPT];
+    bool y_ok[RPT];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) acc[j] = 0.0f;
+    for (int q = 0; q < RPT; ++q) { y[q] = yw + ly + 4 * q; y_ok[q] = x_ok && y[q] < g.H; }
 
-    float rs[VEC];
-    if constexpr (MODE == MODE_MOD) {
-        const float4* rp = reinterpret_cast<const float4*>(rescale + (long long)y * g.W + x0);
+    constexpr bool kPacked = (MODE == MODE_MD);   // accumulate directly in T (packed words)
+    uint4 pacc[RPT];
+    float facc[RPT][kPacked ? 1 : VEC];
+    float rs[RPT][kPacked ? 1 : VEC];
 #pragma unroll
-        for (int q = 0; q < VEC / 4; ++q) {
-            const float4 f = __ldg(rp + q);
-            rs[4 * q + 0] = f.x; rs[4 * q + 1] = f.y; rs[4 * q + 2] = f.z; rs[4 * q + 3] = f.w;
-        }
-    }
-
-    const int twv = g.tw >> L2V;
-    for (int r = r_lo; r <= r_hi; ++r) {
-        const int v = y - (int)s_ys[r];
-        const long long row_off = ((long long)plane * g.th + v) * g.tw;
-        for (int c = c_lo; c <= c_hi; ++c) {
-            const int t = r * g.cols + c;
-            const int b = t / p.tile_bs;
-            const T* trow = reinterpret_cast<const T*>(p.batch_ptrs[b]) + (long long)(t - b * p.tile_bs) * p.tile_stride + row_off;
-            const int u0 = x0 - (int)s_xs[c];  // tile-local column of element 0 (may be <0 or >tw-VEC at tile edges)
-            const int k = u0 >> L2V, s = u0 & (VEC - 1);
-            uint4 A = make_uint4(0, 0, 0, 0), B = make_uint4(0, 0, 0, 0);
-            if (k >= 0 && k < twv) A = ldg128(trow + (long long)k * VEC);
-            if (s != 0 && k + 1 >= 0 && k + 1 < twv) B = ldg128(trow + (long long)(k + 1) * VEC);
-            const uint4 e = Vec<T>::window(A, B, s);
+    for (int q = 0; q < RPT; ++q) {
+        pacc[q] = make_uint4(0, 0, 0, 0);
+        if constexpr (!kPacked) {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const bool valid = (unsigned)(u0 + j) < (unsigned)g.tw;
-                float val = Vec<T>::get(e, j);
-                if constexpr (MODE == MODE_MOD) {
-                    // w = tile_weights * rescale_factor[slicer]; x_tile_out * w   (two fp32 roundings, no FMA)
-                    const float tw_ = valid ? __ldg(tile_weights + (long long)v * g.tw + (u0 + j)) : 0.0f;
-                    val = __fmul_rn(val, __fmul_rn(tw_, rs[j]));
+            for (int j = 0; j < VEC; ++j) { facc[q][j] = 0.0f; rs[q][j] = 0.0f; }
+            if (y_ok[q]) {
+                const float4* rp = reinterpret_cast<const float4*>(rescale + (long long)y[q] * g.W + x0);
+#pragma unroll
+                for (int h = 0; h < VEC / 4; ++h) {
+                    const float4 f = __ldg(rp + h);
+                    rs[q][4 * h + 0] = f.x; rs[q][4 * h + 1] = f.y; rs[q][4 * h + 2] = f.z; rs[q][4 * h + 3] = f.w;
                 }
-                const float sum = round_through<T>(__fadd_rn(acc[j], val));
-                acc[j] = valid ? sum : acc[j];
             }
         }
     }
 
-    const long long o = ((long long)plane * g.H + y) * g.W + x0;
-    if constexpr (MODE == MODE_MD) {
-        // x_out = where(weights > 1, x_buffer / weights, x_buffer)  -- fp32, IEEE divide
-        const float4* wp = reinterpret_cast<const float4*>(weights + (long long)y * g.W + x0);
-        float4* op = reinterpret_cast<float4*>(out_f32 + o);
+    const int twv = g.tw >> L2V;
+    const int plane_off = plane * g.th * g.tw;     // < 2^31: checked on the host
+    int r_cur = r_lo, c_cur = c_lo;
+    for (int i0 = 0; i0 < nv; i0 += kGroup) {
+        uint4 A[kGroup][RPT], B[kGroup][RPT];
+        int sft[kGroup], u0s[kGroup], vrow[kGroup][RPT];
+        bool live[kGroup][RPT];
+        // ---- phase 1: issue every load of the group -----------------------------------------
 #pragma unroll
-        for (int q = 0; q < VEC / 4; ++q) {
-            const float4 w = __ldg(wp + q);
-            float4 f;
-            f.x = w.x > 1.0f ? __fdiv_rn(acc[4 * q + 0], w.x) : acc[4 * q + 0];
-            f.y = w.y > 1.0f ? __fdiv_rn(acc[4 * q + 1], w.y) : acc[4 * q + 1];
-            f.z = w.z > 1.0f ? __fdiv_rn(acc[4 * q + 2], w.z) : acc[4 * q + 2];
-            f.w = w.w > 1.0f ? __fdiv_rn(acc[4 * q + 3], w.w) : acc[4 * q + 3];
-            op[q] = f;
+        for (int gi = 0; gi < kGroup; ++gi) {
+            const bool in = i0 + gi < nv;
+            const int r = in ? r_cur : r_lo, c = in ? c_cur : c_lo;
+            if (in) { if (++c_cur > c_hi) { c_cur = c_lo; ++r_cur; } }
+            const unsigned t = (unsigned)(r * g.cols + c);
+            const unsigned b = fastdiv(t, p.bs_magic);
+            const T* tbase = reinterpret_cast<const T*>(p.batch_ptrs[b]) + (long long)(t - b * (unsigned)p.tile_bs) * p.tile_stride;
+            const int ysr = (int)s_ys[r];
+            const int u0 = x0 - (int)s_xs[c];      // tile-local column of element 0; u0 & (VEC-1) is warp-uniform
+            const int k = u0 >> L2V, s = u0 & (VEC - 1);
+            sft[gi] = s; u0s[gi] = u0;
+            const bool okA = in && (unsigned)k < (unsigned)twv;
+            const bool okB = in && s != 0 && (unsigned)(k + 1) < (unsigned)twv;
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) {
+                const int v = y[q] - ysr;
+                const bool rok = y_ok[q] && (unsigned)v < (unsigned)g.th;
+                vrow[gi][q] = v; live[gi][q] = rok && in;
+                A[gi][q] = make_uint4(NEG0, NEG0, NEG0, NEG0);
+                B[gi][q] = A[gi][q];
+                const T* trow = tbase + (plane_off + v * g.tw + k * VEC);
+                if (rok && okA) A[gi][q] = ldg128(trow);
+                if (rok && okB) B[gi][q] = ldg128(trow + VEC);
+            }
+        }
+        // ---- phase 2: consume in tile order ---------------------------------------------------
+#pragma unroll
+        for (int gi = 0; gi < kGroup; ++gi) {
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) {
+                const uint4 e = Vec<T>::window(A[gi][q], B[gi][q], sft[gi]);
+                if constexpr (kPacked) {
+                    pacc[q].x = PackedAdd<T>::add(pacc[q].x, e.x);
+                    pacc[q].y = PackedAdd<T>::add(pacc[q].y, e.y);
+                    pacc[q].z = PackedAdd<T>::add(pacc[q].z, e.z);
+                    pacc[q].w = PackedAdd<T>::add(pacc[q].w, e.w);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        const int u = u0s[gi] + j;
+                        const bool valid = live[gi][q] && (unsigned)u < (unsigned)g.tw;
+                        // w = tile_weights * rescale_factor[slicer]; x_tile_out * w   (two fp32 roundings, no FMA)
+                        const float tw_ = valid ? __ldg(tile_weights + vrow[gi][q] * g.tw + u) : 0.0f;
+                        const float val = __fmul_rn(Vec<T>::get(e, j), __fmul_rn(tw_, rs[q][j]));
+                        const float sum = round_through<T>(__fadd_rn(facc[q][j], val));
+                        facc[q][j] = valid ? sum : facc[q][j];
+                    }
+                }
+            }
         }
     }
-    if constexpr (WRITE_BUF || MODE == MODE_MOD) {
-        uint4 pk;
-        if constexpr (sizeof(T) == 2) {
-            uint32_t w32[4];
+
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                w32[q] = (uint32_t)Elem<T>::f32_to_bits(acc[2 * q]) | ((uint32_t)Elem<T>::f32_to_bits(acc[2 * q + 1]) << 16);
-            pk = make_uint4(w32[0], w32[1], w32[2], w32[3]);
+    for (int q = 0; q < RPT; ++q) {
+        if (!y_ok[q]) continue;
+        const long long o = ((long long)plane * g.H + y[q]) * g.W + x0;
+        float acc[VEC];
+        if constexpr (kPacked) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] = Vec<T>::get(pacc[q], j);
         } else {
-            pk = make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]), __float_as_uint(acc[3]));
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] = facc[q][j];
         }
-        stg128(out_buf + o, pk);
+        if constexpr (MODE == MODE_MD) {
+            // x_out = where(weights > 1, x_buffer / weights, x_buffer)  -- fp32, IEEE divide
+            const float4* wp = reinterpret_cast<const float4*>(weights + (long long)y[q] * g.W + x0);
+            float4* op = reinterpret_cast<float4*>(out_f32 + o);
+#pragma unroll
+            for (int h = 0; h < VEC / 4; ++h) {
+                const float4 w = __ldg(wp + h);
+                float4 f;
+                f.x = w.x > 1.0f ? __fdiv_rn(acc[4 * h + 0], w.x) : acc[4 * h + 0];
+                f.y = w.y > 1.0f ? __fdiv_rn(acc[4 * h + 1], w.y) : acc[4 * h + 1];
+                f.z = w.z > 1.0f ? __fdiv_rn(acc[4 * h + 2], w.z) : acc[4 * h + 2];
+                f.w = w.w > 1.0f ? __fdiv_rn(acc[4 * h + 3], w.w) : acc[4 * h + 3];
+                op[h] = f;
+            }
+        }
+        if constexpr (WRITE_BUF || MODE == MODE_MOD) {
+            uint4 pk;
+            if constexpr (kPacked) {
+                pk = pacc[q];
+            } else if constexpr (sizeof(T) == 2) {
+                uint32_t w32[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h)
+                    w32[h] = (uint32_t)Elem<T>::f32_to_bits(acc[2 * h]) | ((uint32_t)Elem<T>::f32_to_bits(acc[2 * h + 1]) << 16);
+                pk = make_uint4(w32[0], w32[1], w32[2], w32[3]);
+            } else {
+                pk = make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]), __float_as_uint(acc[3]));
+            }
+            stg128(out_buf + o, pk);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Blend + normalise, MultiDiffusion, TMA path (the default when it applies).
+//
+// A CTA owns an 8-row x 16-vector patch of one canvas plane.  For every tile that
+// touches the patch (ascending tile index) one thread issues ONE cp.async.bulk.tensor
+// box load: the copy engine clips the box against the tile and zero-fills the rest.
+// All boxes of a CTA are in flight at once (one mbarrier each, no staging registers);
+// the threads then walk the stages in tile order.  TMA wants a 16-byte aligned inner
+// start coordinate, so the box is the aligned superset of the patch (BX + VEC columns)
+// and the per-tile shift s = (x_lo - xs) mod VEC -- uniform over the CTA -- is applied
+// on the shared-memory read: two aligned LDS.128 + funnel shift, then a packed add.
+// Zero fill is exact: the accumulator starts at +0 and can never become -0.
+// ---------------------------------------------------------------------------
+constexpr int kTmaBXV = 16;   // vectors per patch row
+constexpr int kTmaBY = 8;     // patch rows
+constexpr int kTmaThreads = kTmaBXV * kTmaBY;
+constexpr int kTmaMaxVisits = 96;
+
+template <int NB>
+struct TmaBlendParams {
+    GeomParams g;
+    int tile_bs;
+    unsigned bs_magic;
+    int nv_cap;
+    CUtensorMap maps[NB];
+};
+
+template <typename T, bool WRITE_BUF, int NB>
+__global__ void __launch_bounds__(kTmaThreads)
+blend_md_tma_kernel(const __grid_constant__ TmaBlendParams<NB> p, const float* __restrict__ weights,
+                    float* __restrict__ out_f32, T* __restrict__ out_buf) {
+    constexpr int VEC = Vec<T>::kElems;
+    constexpr int L2V = Vec<T>::kLog2;
+    constexpr int BX = kTmaBXV * VEC;
+    constexpr int PITCH = (BX + VEC) * (int)sizeof(T);   // bytes per staged row (aligned superset)
+    constexpr int STAGE = PITCH * kTmaBY;                // multiple of 128 B
+    extern __shared__ __align__(128) unsigned char td_smem[];
+    __shared__ short s_ys[TD_MAX_GRID_DIM];
+    __shared__ short s_xs[TD_MAX_GRID_DIM];
+    __shared__ signed char s_shift[kTmaMaxVisits];
+    const GeomParams& g = p.g;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(td_smem + (size_t)p.nv_cap * STAGE);
+    load_origins(g, s_ys, s_xs);
+
+    const int plane = blockIdx.z;
+    const int x_lo = blockIdx.x * BX, y_lo = blockIdx.y * kTmaBY;
+    const int x_hi = min(x_lo + BX, g.W) - 1, y_hi = min(y_lo + kTmaBY, g.H) - 1;
+    const int r_lo = last_le(s_ys, g.rows, y_lo - g.th, g.inv_dy) + 1;
+    const int r_hi = last_le(s_ys, g.rows, y_hi, g.inv_dy);
+    const int c_lo = last_le(s_xs, g.cols, x_lo - g.tw, g.inv_dx) + 1;
+    const int c_hi = last_le(s_xs, g.cols, x_hi, g.inv_dx);
+    const int nc = c_hi - c_lo + 1;
+    const int nv = g.dbg_no_tiles ? 0 : (r_hi - r_lo + 1) * nc;   // <= nv_cap by construction on the host
+
+    // visit i is owned by thread i: init its barrier, publish its shift, launch its box
+    for (int i = threadIdx.x; i < nv; i += kTmaThreads) {
+        const int ri = i / nc, ci = i - ri * nc;
+        const int r = r_lo + ri, c = c_lo + ci;
+        const unsigned t = (unsigned)(r * g.cols + c);
+        const unsigned b = fastdiv(t, p.bs_magic);
+        const int pz = (int)(t - b * (unsigned)p.tile_bs) * (g.N * g.C) + plane;   // plane inside batch tensor b
+        const int u0 = x_lo - (int)s_xs[c];          // tile-local column of the patch's first pixel
+        const int k = u0 >> L2V;                     // floor: aligned chunk holding it
+        s_shift[i] = (signed char)(u0 & (VEC - 1));
+        mbar_init(&bars[i], 1);
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&bars[i], STAGE);
+        tma_load_3d(td_smem + (size_t)i * STAGE, &p.maps[b], k * VEC, y_lo - (int)s_ys[r], pz, &bars[i]);
+    }
+    __syncthreads();
+
+    const int tx = threadIdx.x % kTmaBXV, ty = threadIdx.x / kTmaBXV;
+    const unsigned char* mine = td_smem + (size_t)ty * PITCH + (size_t)tx * 16;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < nv; ++i) {
+        const int s = (int)s_shift[i];
+        mbar_wait(&bars[i], 0);
+        const uint4 A = lds128(mine + (size_t)i * STAGE);
+        uint4 e = A;
+        if (s != 0) {
+            const uint4 B = lds128(mine + (size_t)i * STAGE + 16);
+            e = Vec<T>::window(A, B, s);
+        }
+        acc.x = PackedAdd<T>::add(acc.x, e.x);
+        acc.y = PackedAdd<T>::add(acc.y, e.y);
+        acc.z = PackedAdd<T>::add(acc.z, e.z);
+        acc.w = PackedAdd<T>::add(acc.w, e.w);
+    }
+
+    const int x0 = x_lo + tx * VEC, y = y_lo + ty;
+    if (x0 >= g.W || y >= g.H) return;
+    const long long o = ((long long)plane * g.H + y) * g.W + x0;
+    const float4* wp = reinterpret_cast<const float4*>(weights + (long long)y * g.W + x0);
+    float4* op = reinterpret_cast<float4*>(out_f32 + o);
+#pragma unroll
+    for (int h = 0; h < VEC / 4; ++h) {
+        const float4 w = __ldg(wp + h);
+        const float a0 = Vec<T>::get(acc, 4 * h + 0), a1 = Vec<T>::get(acc, 4 * h + 1);
+        const float a2 = Vec<T>::get(acc, 4 * h + 2), a3 = Vec<T>::get(acc, 4 * h + 3);
+        float4 f;   // x_out = where(weights > 1, x_buffer / weights, x_buffer)  -- fp32, IEEE divide
+        f.x = w.x > 1.0f ? __fdiv_rn(a0, w.x) : a0;
+        f.y = w.y > 1.0f ? __fdiv_rn(a1, w.y) : a1;
+        f.z = w.z > 1.0f ? __fdiv_rn(a2, w.z) : a2;
+        f.w = w.w > 1.0f ? __fdiv_rn(a3, w.w) : a3;
+        op[h] = f;
+    }
+    if constexpr (WRITE_BUF) stg128(out_buf + o, acc);
+}
+
+// ---------------------------------------------------------------------------
+// Scatter, TMA path: a CTA moves `rb` rows of one (tile, n, c) plane.  One thread
+// issues a single box load of the aligned superset of the tile rows from the canvas;
+// the threads then re-align (two LDS.128 + funnel shift, block-uniform shift) and
+// write the tile batch with aligned 128-bit stores.
+// ---------------------------------------------------------------------------
+struct TmaScatterParams {
+    GeomParams g;
+    CUtensorMap src;   // canvas  [N*C][H][W], box [1][rb][tw + VEC]
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+scatter_tma_kernel(const __grid_constant__ TmaScatterParams p, T* __restrict__ tiles, int tile_begin, int rb) {
+    constexpr int VEC = Vec<T>::kElems;
+    constexpr int L2V = Vec<T>::kLog2;
+    extern __shared__ __align__(128) unsigned char td_smem[];
+    __shared__ uint64_t bar;
+    const GeomParams& g = p.g;
+    const unsigned tp = blockIdx.x;
+    const unsigned tl = fastdiv(tp, g.nc_magic);
+    const int plane = (int)(tp - tl * (unsigned)(g.N * g.C));
+    const int t = tile_begin + (int)tl;
+    const int r = t / g.cols, c = t - r * g.cols;
+    const int xs = (int)g.xs[c], ys = (int)g.ys[r];
+    const int v0 = blockIdx.y * rb;
+    const int pitch = (g.tw + VEC) * (int)sizeof(T);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&bar, (uint32_t)(pitch * rb));
+        tma_load_3d(td_smem, &p.src, (xs >> L2V) * VEC, ys + v0, plane, &bar);
+    }
+    __syncthreads();
+    const int s = xs & (VEC - 1);
+    const int twv = g.tw >> L2V;
+    const int nvec = min(rb, g.th - v0) * twv;
+    T* dst = tiles + ((long long)tp * g.th + v0) * g.tw;
+    mbar_wait(&bar, 0);
+    for (int i = threadIdx.x; i < nvec; i += 128) {
+        const unsigned vi = fastdiv((unsigned)i, g.twv_magic);
+        const int uv = i - (int)vi * twv;
+        const unsigned char* src = td_smem + (size_t)vi * pitch + (size_t)uv * 16;
+        const uint4 A = lds128(src);
+        uint4 e = A;
+        if (s != 0) e = Vec<T>::window(A, lds128(src + 16), s);
+        stg128(dst + (long long)i * VEC, e);
     }
 }
 
@@ -260,6 +543,9 @@ blend_grid_generic_kernel(const __grid_constant__ BlendParams p, const float* __
 // ---------------------------------------------------------------------------
 // Host-side dispatch
 // ---------------------------------------------------------------------------
+// magic = ceil(2^32 / d) for fastdiv(); 0 encodes d == 1
+unsigned magic_u16(unsigned d) { return d <= 1 ? 0u : (unsigned)(((1ull << 32) + d - 1) / d); }
+
 int fill_geom(const td_grid* g, int N, int C, GeomParams* o) {
     if (g == nullptr) { td_set_error("null grid"); return TD_ERR_INVALID_ARG; }
     if (N <= 0 || C <= 0) { td_set_error("N and C must be positive (N=%d C=%d)", N, C); return TD_ERR_INVALID_ARG; }
@@ -273,6 +559,11 @@ int fill_geom(const td_grid* g, int N, int C, GeomParams* o) {
     o->rows = g->rows; o->cols = g->cols; o->N = N; o->C = C;
     for (int i = 0; i < g->rows; ++i) o->ys[i] = (short)g->ys[i];
     for (int i = 0; i < g->cols; ++i) o->xs[i] = (short)g->xs[i];
+    const unsigned nc = (unsigned)(N * C);
+    if (nc >= 65536u) { td_set_error("N*C = %u too large", nc); return TD_ERR_UNSUPPORTED; }
+    o->nc_magic = magic_u16(nc);
+    o->twv_magic = 0;  // set by the vector launchers (depends on the element size)
+    o->dbg_no_tiles = 0;
     o->inv_dx = g->cols > 1 ? (float)(g->cols - 1) / (float)std::max(1, g->W - g->tile_w) : 0.0f;
     o->inv_dy = g->rows > 1 ? (float)(g->rows - 1) / (float)std::max(1, g->H - g->tile_h) : 0.0f;
     return TD_OK;
@@ -292,12 +583,16 @@ int check_launch(const char* what) {
 inline unsigned blocks_for(long long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
 
 template <typename T>
-int launch_scatter(const GeomParams& gp, const void* x, void* tiles, int tile_begin, int n_tiles, bool vec, cudaStream_t st) {
+int launch_scatter(GeomParams gp, const void* x, void* tiles, int tile_begin, int n_tiles, bool vec, cudaStream_t st) {
     const long long elems = (long long)n_tiles * gp.N * gp.C * gp.th * gp.tw;
     if (elems == 0) return TD_OK;
     if (vec) {
-        const long long total = elems / Vec<T>::kElems;
-        scatter_vec_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>(gp, (const T*)x, (T*)tiles, tile_begin, total);
+        const int twv = gp.tw / Vec<T>::kElems;
+        gp.twv_magic = magic_u16((unsigned)twv);
+        const int rows_per_block = std::max(1, std::min(gp.th, (128 * 4 + twv - 1) / twv));  // ~4 vectors per thread
+        if ((long long)rows_per_block * twv >= 65536) { td_set_error("tile row too wide for the vector scatter"); return TD_ERR_UNSUPPORTED; }
+        dim3 grid((unsigned)(n_tiles * gp.N * gp.C), (unsigned)((gp.th + rows_per_block - 1) / rows_per_block));
+        scatter_vec_kernel<T><<<grid, 128, 0, st>>>(gp, (const T*)x, (T*)tiles, tile_begin, rows_per_block);
     } else {
         scatter_generic_kernel<T><<<blocks_for(elems, 256), 256, 0, st>>>(gp, (const T*)x, (T*)tiles, tile_begin, elems);
     }
@@ -308,13 +603,108 @@ template <typename T, int MODE>
 int launch_blend_vec(const BlendParams& bp, const float* weights, const float* tile_weights, const float* rescale,
                      float* out_f32, void* out_buf, cudaStream_t st) {
     const GeomParams& g = bp.g;
-    const long long total = (long long)g.N * g.C * g.H * (g.W / Vec<T>::kElems);
-    const unsigned nb = blocks_for(total, 256);
+    const int wv = g.W / Vec<T>::kElems;
+    const int rows_per_block = kBlendWarps * 4 * BlendShape<MODE>::kRPT;
+    dim3 grid((unsigned)((wv + kWarpVecs - 1) / kWarpVecs), (unsigned)((g.H + rows_per_block - 1) / rows_per_block),
+              (unsigned)(g.N * g.C));
+    if (grid.y > 65535u || grid.z > 65535u) { td_set_error("canvas too large for the vector blend grid"); return TD_ERR_UNSUPPORTED; }
     if (MODE == MODE_MD && out_buf != nullptr)
-        blend_grid_vec_kernel<T, MODE, true><<<nb, 256, 0, st>>>(bp, weights, tile_weights, rescale, out_f32, (T*)out_buf, total);
+        blend_grid_vec_kernel<T, MODE, true><<<grid, kBlendWarps * 32, 0, st>>>(bp, weights, tile_weights, rescale, out_f32, (T*)out_buf);
     else
-        blend_grid_vec_kernel<T, MODE, false><<<nb, 256, 0, st>>>(bp, weights, tile_weights, rescale, out_f32, (T*)out_buf, total);
+        blend_grid_vec_kernel<T, MODE, false><<<grid, kBlendWarps * 32, 0, st>>>(bp, weights, tile_weights, rescale, out_f32, (T*)out_buf);
     return check_launch("td_blend (vec)");
+}
+
+// max number of tile rows (cols) touching any BY-row (BX-px) patch: bounds the TMA stage count
+int max_union(const int32_t* org, int n, int extent, int size, int patch) {
+    int best = 0;
+    for (int lo = 0; lo < size; lo += patch) {
+        const int hi = std::min(lo + patch, size) - 1;
+        int cnt = 0;
+        for (int i = 0; i < n; ++i)
+            if (org[i] <= hi && org[i] + extent > lo) ++cnt;
+        best = std::max(best, cnt);
+    }
+    return best;
+}
+
+template <typename KernelT>
+int ensure_dyn_smem(KernelT kernel, int bytes, int* configured) {
+    if (bytes <= *configured) return TD_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) { td_set_error("cudaFuncSetAttribute(%d B smem): %s", bytes, cudaGetErrorString(e)); return TD_ERR_CUDA; }
+    *configured = bytes;
+    return TD_OK;
+}
+
+template <typename T, bool WRITE_BUF, int NB>
+int launch_blend_tma_nb(const td_grid* g, const BlendParams& bp, int tile_dtype, const float* weights, float* out_f32, void* out_buf,
+                        int nv_cap, cudaStream_t st) {
+    constexpr int VEC = Vec<T>::kElems;
+    constexpr int BX = kTmaBXV * VEC;
+    constexpr int STAGE = (BX + VEC) * (int)sizeof(T) * kTmaBY;
+    static TmaBlendParams<NB> tp;   // filled per launch under a lock (the params are copied at launch)
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    tp.g = bp.g; tp.tile_bs = bp.tile_bs; tp.bs_magic = bp.bs_magic; tp.nv_cap = nv_cap;
+    const int NC = bp.g.N * bp.g.C;
+    for (int b = 0; b < bp.num_batches; ++b) {
+        const int nt = std::min(bp.tile_bs, g->num_tiles - b * bp.tile_bs);
+        int rc = td_encode_tensor_map_3d(&tp.maps[b], bp.batch_ptrs[b], tile_dtype, (uint64_t)nt * NC, (uint64_t)bp.g.th,
+                                         (uint64_t)bp.g.tw, kTmaBY, BX + VEC);
+        if (rc != TD_OK) return rc;
+    }
+    const int smem = nv_cap * (STAGE + 8);
+    static int configured = 48 * 1024;
+    int rc = ensure_dyn_smem(blend_md_tma_kernel<T, WRITE_BUF, NB>, smem, &configured);
+    if (rc != TD_OK) return rc;
+    dim3 grid((unsigned)((bp.g.W + BX - 1) / BX), (unsigned)((bp.g.H + kTmaBY - 1) / kTmaBY), (unsigned)NC);
+    blend_md_tma_kernel<T, WRITE_BUF, NB><<<grid, kTmaThreads, smem, st>>>(tp, weights, out_f32, (T*)out_buf);
+    return check_launch("td_blend_multidiffusion (tma)");
+}
+
+// returns TD_OK if launched, 1 if the TMA path does not apply (caller falls back), <0 on error
+template <typename T>
+int try_launch_blend_tma(const td_grid* g, const BlendParams& bp, int tile_dtype, const float* weights, float* out_f32,
+                         void* out_buf, cudaStream_t st) {
+    constexpr int VEC = Vec<T>::kElems;
+    constexpr int BX = kTmaBXV * VEC;
+    constexpr int STAGE = (BX + VEC) * (int)sizeof(T) * kTmaBY;
+    if (bp.g.N * bp.g.C > 65535 || (bp.g.H + kTmaBY - 1) / kTmaBY > 65535) return 1;
+    const int nv_cap = max_union(g->ys, g->rows, g->tile_h, g->H, kTmaBY) * max_union(g->xs, g->cols, g->tile_w, g->W, BX);
+    if (nv_cap <= 0 || nv_cap > kTmaMaxVisits || nv_cap * (STAGE + 8) > 200 * 1024) return 1;
+    const bool wb = out_buf != nullptr;
+    if (bp.num_batches <= 32)
+        return wb ? launch_blend_tma_nb<T, true, 32>(g, bp, tile_dtype, weights, out_f32, out_buf, nv_cap, st)
+                  : launch_blend_tma_nb<T, false, 32>(g, bp, tile_dtype, weights, out_f32, out_buf, nv_cap, st);
+    return wb ? launch_blend_tma_nb<T, true, TD_MAX_BATCH_PTRS>(g, bp, tile_dtype, weights, out_f32, out_buf, nv_cap, st)
+              : launch_blend_tma_nb<T, false, TD_MAX_BATCH_PTRS>(g, bp, tile_dtype, weights, out_f32, out_buf, nv_cap, st);
+}
+
+template <typename T>
+int try_launch_scatter_tma(GeomParams gp, const void* x, void* tiles, int dtype, int tile_begin, int n_tiles, cudaStream_t st) {
+    constexpr int VEC = Vec<T>::kElems;
+    const int es = (int)sizeof(T);
+    if (gp.tw + VEC > 256 || n_tiles <= 0) return 1;
+    const long long planes_out = (long long)n_tiles * gp.N * gp.C;
+    if (planes_out > 0x7fffffffLL) return 1;
+    const int pitch = (gp.tw + VEC) * es;
+    int rb = std::min(gp.th, std::max(1, 8192 / pitch));   // ~8 KB per CTA
+    rb = std::min(rb, 256);
+    const int twv = gp.tw / VEC;
+    if ((long long)rb * twv >= 65536) return 1;
+    gp.twv_magic = magic_u16((unsigned)twv);
+    static TmaScatterParams tp;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    tp.g = gp;
+    int rc = td_encode_tensor_map_3d(&tp.src, x, dtype, (uint64_t)gp.N * gp.C, (uint64_t)gp.H, (uint64_t)gp.W, (uint32_t)rb,
+                                     (uint32_t)(gp.tw + VEC));
+    if (rc != TD_OK) return rc;
+    dim3 grid((unsigned)planes_out, (unsigned)((gp.th + rb - 1) / rb));
+    if (grid.y > 65535u) return 1;
+    scatter_tma_kernel<T><<<grid, 128, pitch * rb, st>>>(tp, (T*)tiles, tile_begin, rb);
+    return check_launch("td_scatter_tiles (tma)");
 }
 
 template <typename TIn, typename TAcc, int MODE>
@@ -365,6 +755,7 @@ int fill_blend(const td_grid* g, const void* const* batch_ptrs, int num_batches,
         bp->batch_ptrs[b] = batch_ptrs[b];
     }
     bp->tile_bs = tile_bs;
+    bp->bs_magic = magic_u16((unsigned)tile_bs);
     bp->num_batches = num_batches;
     bp->tile_stride = (long long)N * C * g->tile_h * g->tile_w;
     return TD_OK;
@@ -372,6 +763,7 @@ int fill_blend(const td_grid* g, const void* const* batch_ptrs, int num_batches,
 
 bool blend_vec_ok(const BlendParams& bp, int tile_dtype, int acc_dtype, std::initializer_list<const void*> ptrs) {
     if (tile_dtype != acc_dtype) return false;
+    if (bp.tile_stride >= (1ll << 31)) return false;  // the vector kernel uses 32-bit offsets inside a tile
     const int vec = 16 / td_dtype_size(tile_dtype);
     if (bp.g.W % vec != 0 || bp.g.tw % vec != 0) return false;
     for (int b = 0; b < bp.num_batches; ++b)
@@ -382,6 +774,14 @@ bool blend_vec_ok(const BlendParams& bp, int tile_dtype, int acc_dtype, std::ini
 }
 
 }  // namespace
+
+__global__ void empty_kernel() {}
+
+extern "C" int td_debug_launch_empty(int blocks, int threads, void* stream) {
+    if (blocks <= 0 || threads <= 0 || threads > 1024) { td_set_error("td_debug_launch_empty: bad launch shape"); return TD_ERR_INVALID_ARG; }
+    empty_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>();
+    return check_launch("td_debug_launch_empty");
+}
 
 extern "C" int td_scatter_tiles(const td_grid* g, const void* x, void* tiles, int N, int C, int dtype, int tile_begin,
                                 int tile_end, uint32_t flags, void* stream) {
@@ -398,6 +798,11 @@ extern "C" int td_scatter_tiles(const td_grid* g, const void* x, void* tiles, in
     const int vec = 16 / es;
     const bool vec_ok = !(flags & TD_FLAG_FORCE_GENERIC) && gp.W % vec == 0 && gp.tw % vec == 0 && aligned16(x) && aligned16(tiles);
     cudaStream_t s = (cudaStream_t)stream;
+    if (vec_ok && !(flags & TD_FLAG_NO_TMA)) {
+        const int rc = es == 2 ? try_launch_scatter_tma<__half>(gp, x, tiles, dtype, tile_begin, tile_end - tile_begin, s)
+                               : try_launch_scatter_tma<float>(gp, x, tiles, dtype, tile_begin, tile_end - tile_begin, s);
+        if (rc <= 0) return rc;   // launched (0) or hard error (<0); 1 = not applicable -> vector kernel
+    }
     // fp16 and bf16 are both moved as opaque 16-bit words
     if (es == 2) return launch_scatter<__half>(gp, x, tiles, tile_begin, tile_end - tile_begin, vec_ok, s);
     return launch_scatter<float>(gp, x, tiles, tile_begin, tile_end - tile_begin, vec_ok, s);
@@ -410,8 +815,18 @@ extern "C" int td_blend_multidiffusion(const td_grid* g, const void* const* batc
     int st = fill_blend(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, acc_dtype, &bp);
     if (st != TD_OK) return st;
     if (weights == nullptr || x_out == nullptr) { td_set_error("td_blend_multidiffusion: null weights / x_out"); return TD_ERR_INVALID_ARG; }
+    bp.g.dbg_no_tiles = (flags & TD_FLAG_DBG_NO_TILES) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (!(flags & TD_FLAG_FORCE_GENERIC) && blend_vec_ok(bp, tile_dtype, acc_dtype, {weights, x_out, x_buffer})) {
+        if (!(flags & TD_FLAG_NO_TMA)) {
+            int rc;
+            switch (tile_dtype) {
+                case TD_F16: rc = try_launch_blend_tma<__half>(g, bp, tile_dtype, weights, x_out, x_buffer, s); break;
+                case TD_BF16: rc = try_launch_blend_tma<__nv_bfloat16>(g, bp, tile_dtype, weights, x_out, x_buffer, s); break;
+                default: rc = try_launch_blend_tma<float>(g, bp, tile_dtype, weights, x_out, x_buffer, s); break;
+            }
+            if (rc <= 0) return rc;   // launched or hard error; 1 = not applicable -> register kernel
+        }
         switch (tile_dtype) {
             case TD_F16: return launch_blend_vec<__half, MODE_MD>(bp, weights, nullptr, nullptr, x_out, x_buffer, s);
             case TD_BF16: return launch_blend_vec<__nv_bfloat16, MODE_MD>(bp, weights, nullptr, nullptr, x_out, x_buffer, s);

@@ -32,14 +32,23 @@ def use_shared(ns) -> None:
     _forced_shared = ns
 
 
+_a1111_cache = {}
+
+
+def _a1111(name: str):
+    """`modules.<name>` of the WebUI if importable; looked up once (a failing import is slow)."""
+    if name not in _a1111_cache:
+        try:
+            import importlib
+            _a1111_cache[name] = importlib.import_module(f"modules.{name}")
+        except Exception:
+            _a1111_cache[name] = None
+    return _a1111_cache[name]
+
+
 def _a1111_shared():
-    try:
-        from modules import shared as a1111_shared  # type: ignore
-        if hasattr(a1111_shared, "state"):
-            return a1111_shared
-    except Exception:
-        pass
-    return None
+    m = _a1111("shared")
+    return m if m is not None and hasattr(m, "state") else None
 
 
 def get_shared():
@@ -66,13 +75,14 @@ def interrupted() -> bool:
 
 def device() -> torch.device:
     """Device the delegate keeps its persistent buffers on (CUDA whenever one exists)."""
-    try:
-        from modules import devices as a1111_devices  # type: ignore
-        d = torch.device(a1111_devices.device)
-        if d.type == "cuda":
-            return d
-    except Exception:
-        pass
+    a1111_devices = _a1111("devices")
+    if a1111_devices is not None:
+        try:
+            d = torch.device(a1111_devices.device)
+            if d.type == "cuda":
+                return d
+        except Exception:
+            pass
     if not torch.cuda.is_available():
         # bookkeeping tensors (weight canvases) may live on the host; every compute
         # entry point still refuses CPU tensors -- there is no CPU fallback.
@@ -86,12 +96,9 @@ def _mro_names(obj):
 
 def is_kdiff_sampler(sampler) -> bool:
     """isinstance(sampler, KDiffusionSampler) (abstractdiffusion.py:77-79), duck-typed without A1111."""
-    try:
-        from modules.sd_samplers_kdiffusion import KDiffusionSampler  # type: ignore
-        if isinstance(sampler, KDiffusionSampler):
-            return True
-    except Exception:
-        pass
+    m = _a1111("sd_samplers_kdiffusion")
+    if m is not None and hasattr(m, "KDiffusionSampler") and isinstance(sampler, m.KDiffusionSampler):
+        return True
     names = _mro_names(sampler)
     if "KDiffusionSampler" in names:
         return True
@@ -101,10 +108,7 @@ def is_kdiff_sampler(sampler) -> bool:
 
 
 def is_ddim_sampler(sampler) -> bool:
-    try:
-        from modules.sd_samplers_timesteps import CompVisSampler  # type: ignore
-        if isinstance(sampler, CompVisSampler):
-            return True
-    except Exception:
-        pass
+    m = _a1111("sd_samplers_timesteps")
+    if m is not None and hasattr(m, "CompVisSampler") and isinstance(sampler, m.CompVisSampler):
+        return True
     return bool(_mro_names(sampler) & {"CompVisSampler", "VanillaStableDiffusionSampler"})

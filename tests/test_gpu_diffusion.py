@@ -14,6 +14,8 @@ from oracle import blend, synth, tiling
 pytestmark = pytest.mark.gpu
 
 FORCE_GENERIC = 1
+NO_TMA = 2
+ALL_PATHS = [0, NO_TMA, FORCE_GENERIC]   # TMA kernels, register-staged vector kernels, scalar kernels
 
 
 @pytest.fixture(scope="module")
@@ -34,7 +36,7 @@ SCATTER_CASES = [  # N, C, W, H, tw, th, ov
 
 @pytest.mark.parametrize("case", SCATTER_CASES)
 @pytest.mark.parametrize("dn", list(DTYPES))
-@pytest.mark.parametrize("flags", [0, FORCE_GENERIC])
+@pytest.mark.parametrize("flags", ALL_PATHS)
 def test_scatter_bit_exact(eng, case, dn, flags):
     N, C, W, H, tw, th, ov = case
     g = _grid(eng, W, H, tw, th, ov, 4)
@@ -93,7 +95,7 @@ def _oracle_step(method, x, plan, tile_dtype=None):
 
 @pytest.mark.parametrize("method", ["md", "mod"])
 @pytest.mark.parametrize("dn", list(DTYPES))
-@pytest.mark.parametrize("flags", [0, FORCE_GENERIC])
+@pytest.mark.parametrize("flags", ALL_PATHS)
 def test_blend_small_matches_reference_fixtures(eng, golden_dir, method, dn, flags):
     g = np.load(os.path.join(golden_dir, "blend_small.npz"))
     for name, (N, C, W, H, tw, th, ov, bs) in zip(g["names"], g["cases"]):
@@ -133,7 +135,7 @@ def test_blend_vs_oracle_edge_geometries(eng, method):
     for (N, C, W, H, tw, th, ov, bs) in cases:
         for dn in ("f16", "f32"):
             x = synth.latent(W + H, (N, C, H, W), DTYPES[dn])
-            for flags in (0, FORCE_GENERIC):
+            for flags in ALL_PATHS:
                 out, xb, plan = _run_cuda_step(eng, method, x, W, H, tw, th, ov, bs, flags=flags)
                 want = _oracle_step(method, x, plan)
                 assert_bit_equal(out, want, f"{method} {(N, C, W, H, tw, th, ov, bs)} {dn} flags={flags}")
