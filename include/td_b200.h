@@ -129,6 +129,60 @@ int td_blend_mixture(const td_grid* g, const void* const* batch_ptrs, int num_ba
                      int N, int C, int tile_dtype, int acc_dtype, const float* tile_weights,
                      const float* rescale, void* x_buffer, uint32_t flags, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ *  Tiled VAE (scripts/tilevae.py of the reference).
+ * ------------------------------------------------------------------------- */
+
+/* get_best_tile_size -- tilevae.py:390-403. */
+int td_vae_best_tile_size(int lowerbound, int upperbound);
+
+/* split_tiles -- tilevae.py:405-462.  Writes T input and T output bboxes as int32
+ * [x1, x2, y1, y2] quadruples (input bbox already expanded by `pad` and clipped;
+ * output bbox snapped to the borders and scaled x8 (decoder) or //8 (encoder)).
+ * Pass NULL arrays to query T.  Returns T or a td_status. */
+int td_vae_split_tiles(int h, int w, int tile_size, int pad, int is_decoder,
+                       int32_t* in_bboxes, int32_t* out_bboxes, int cap);
+
+/* Statistics of `nseg` contiguous segments of `seg_len` elements each, ONE read:
+ * get_var_mean -- tilevae.py:207-215 with nseg = B*32, seg_len = (C/32)*H*W (the
+ * channels of a group are adjacent in NCHW); also the per-channel std_mean of the
+ * fast-mode prelude (tilevae.py:553-554, nseg = B*C, seg_len = H*W, unbiased = 1) and
+ * z.min()/z.max() (:559) through the optional seg_min / seg_max outputs.
+ * mean, var (biased unless `unbiased`), seg_min, seg_max: fp32 [nseg] device.
+ * workspace: device scratch of td_gn_stats_workspace_bytes() bytes. */
+int64_t td_gn_stats_workspace_bytes(int64_t nseg, int64_t seg_len, int dtype);
+int td_gn_stats(const void* x, int64_t nseg, int64_t seg_len, int dtype, int unbiased,
+                void* workspace, int64_t workspace_bytes, float* mean, float* var,
+                float* seg_min, float* seg_max, void* stream);
+
+/* custom_group_norm (+ SiLU) -- tilevae.py:218-245 (+ :102-104), fused, one read and one
+ * write:  y = act(((x - mean[g]) / sqrt(var[g] + eps)) * gamma[c] + beta[c]).
+ * x, y: [B, C, HW] of `dtype` (y may alias x).  mean / var: fp32 [groups] shared by the
+ * batch (stats_per_batch = 0: the reference's merged / estimated statistics) or
+ * [B*groups] (stats_per_batch = 1).  gamma / beta: fp32 [C] or NULL.  act: 0 none, 1 SiLU. */
+int td_gn_apply(const void* x, void* y, int B, int C, int64_t HW, int dtype, int groups,
+                const float* mean, const float* var, int stats_per_batch, const float* gamma,
+                const float* beta, float eps, int act, void* stream);
+
+/* Strided 3-D region copy dst[p, r, c] = src[p, r, c]: the tile crop (tilevae.py:532-535,
+ * which the reference stages through host RAM) and crop_valid_region + paste
+ * (tilevae.py:248-259, :632).  Pointers are already offset to the region origin; strides
+ * and pitches are in elements. */
+int td_copy_region(const void* src, void* dst, int planes, int rows, int cols,
+                   int64_t src_plane_stride, int64_t src_pitch, int64_t dst_plane_stride,
+                   int64_t dst_pitch, int dtype, void* stream);
+
+/* Fast-mode estimator input -- tilevae.py:545-559.
+ * td_resample_nearest: out[p, i, j] = in[p, src_y[i], src_x[j]] (F.interpolate
+ * nearest-exact; the index tables are computed on the host with ATen's float32 rule).
+ * td_affine_clamp: x = clamp((x - mean_new[c]) / std_new[c] * std_old[c] + mean_old[c],
+ * lo[0], hi[0]) in place, every step rounded through `dtype` like the eager ops. */
+int td_resample_nearest(const void* in, void* out, int planes, int H, int W, int oh, int ow,
+                        const int32_t* src_y, const int32_t* src_x, int dtype, void* stream);
+int td_affine_clamp(void* x, int B, int C, int64_t HW, int dtype, const float* mean_new,
+                    const float* std_new, const float* mean_old, const float* std_old,
+                    const float* lo, const float* hi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

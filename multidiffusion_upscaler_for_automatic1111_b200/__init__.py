@@ -11,6 +11,7 @@ Importing this package loads `libtd_b200.so`; if it is missing the import fails
 from . import _cabi  # noqa: F401  (loads the shared library or raises)
 from .tile_methods import AbstractDiffusion, MixtureOfDiffusers, MultiDiffusion
 from .tile_utils.utils import BBox, Method, gaussian_weights, split_bboxes, splitable
+from .tilevae import GroupNormParam, VAEHook
 
-__all__ = ["AbstractDiffusion", "MultiDiffusion", "MixtureOfDiffusers", "BBox", "Method", "split_bboxes",
+__all__ = ["AbstractDiffusion", "MultiDiffusion", "MixtureOfDiffusers", "VAEHook", "GroupNormParam", "BBox", "Method", "split_bboxes",
            "splitable", "gaussian_weights"]

@@ -49,6 +49,30 @@ HASH_CASES = [  # full-size configs, only a sha256 of the output bytes is stored
 
 DTYPES = {"f16": torch.float16, "bf16": torch.bfloat16, "f32": torch.float32}
 
+VAE_SUBSAMPLE = 3
+VAE_CASES = [  # name, is_decoder, fast_mode, color_fix, H, W, tile_size
+    ("dec_slow", True, False, False, 40, 52, 16),
+    ("dec_fast", True, True, False, 40, 52, 16),
+    ("enc_slow", False, False, False, 200, 264, 64),
+    ("enc_fast", False, True, False, 200, 264, 64),
+    ("enc_fast_colorfix", False, True, True, 200, 264, 64),
+    ("dec_tiny_bypass", True, True, False, 20, 30, 16),
+]
+
+
+def vae_case_inputs(is_decoder: bool, H: int, W: int):
+    """Tiny ldm-shaped net (4 resolutions, like SD) + platform-stable input for the VAE fixtures."""
+    from . import ldm_vae
+    if is_decoder:
+        net = ldm_vae.seeded_init(ldm_vae.Decoder(ch=32, ch_mult=(1, 1, 2, 2), num_res_blocks=1), 1)
+        z = synth.latent(5, (1, 4, H, W), torch.float32)
+    else:
+        net = ldm_vae.seeded_init(ldm_vae.Encoder(ch=32, ch_mult=(1, 1, 2, 2), num_res_blocks=1), 2)
+        z = synth.latent(6, (1, 3, H, W), torch.float32)
+    net.eval()
+    net.original_forward = net.forward
+    return net, z
+
 
 def _bits(t: torch.Tensor) -> np.ndarray:
     t = t.contiguous()
@@ -175,6 +199,36 @@ def main():
                 out[f"{name}_{dn}_{method}"] = np.array(sha(o))
                 out[f"{name}_{dn}_{method}_dtype"] = np.array(str(o.dtype))
     np.savez_compressed(os.path.join(GOLDEN_DIR, "blend_hashes.npz"), **out)
+
+    # 6. tiled VAE geometry (scripts/tilevae.py:390-462), exact ------------------------------
+    hook_cls = ref.tilevae.VAEHook
+    geo = {}
+    cases = []
+    for (h, w, ts, dec) in itertools.product([40, 97, 128, 200, 333, 1024], [52, 64, 300, 1024], [16, 64, 96, 512, 1536], [1, 0]):
+        hk = hook_cls(None, ts, bool(dec), True, True, False)
+        ib, ob = hk.split_tiles(h, w)
+        geo[f"in_{len(cases)}"] = np.array(ib, np.int32)
+        geo[f"out_{len(cases)}"] = np.array(ob, np.int32)
+        cases.append((h, w, ts, dec))
+    geo["cases"] = np.array(cases, np.int32)
+    geo["cfg4_dec"] = np.array(hook_cls(None, 96, True, True, True, False).split_tiles(1024, 1024)[0], np.int32)
+    geo["cfg4_enc"] = np.array(hook_cls(None, 1536, False, True, True, False).split_tiles(8192, 8192)[0], np.int32)
+    best = [(lo, up, hook_cls(None, 64, True, True, True, False).get_best_tile_size(lo, up)) for lo in range(1, 200, 7) for up in (lo, lo + 5, lo + 31, 256)]
+    geo["best_tile"] = np.array(best, np.int32)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "vae_geometry.npz"), **geo)
+
+    # 7. tiled VAE forward of the reference on a tiny ldm-shaped net (sub-sampled outputs) --
+    from . import ldm_vae
+    out = {}
+    for name, is_dec, fast, cf, H, W, tile in VAE_CASES:
+        net, z = vae_case_inputs(is_dec, H, W)
+        hook = hook_cls(net, tile, is_dec, fast_decoder=fast, fast_encoder=fast, color_fix=cf)
+        with torch.no_grad():
+            y = hook(z)
+        out[name] = y[:, :, ::VAE_SUBSAMPLE, ::VAE_SUBSAMPLE].contiguous().numpy()
+        out[name + "_shape"] = np.array(y.shape, np.int32)
+        out[name + "_absmax"] = np.array(float(y.abs().max()), np.float32)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "vae_small.npz"), **out)
 
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))
