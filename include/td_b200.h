@@ -44,6 +44,8 @@ typedef enum td_dtype { TD_F16 = 0, TD_BF16 = 1, TD_F32 = 2 } td_dtype;
 
 #define TD_MAX_GRID_DIM 256   /* max tile rows / cols of a grid plan            */
 #define TD_MAX_BATCH_PTRS 128 /* max UNet output batch tensors per blend launch */
+#define TD_MAX_PEERS 16       /* max ranks of a tile-sharded step (one process per GPU) */
+#define TD_IPC_HANDLE_BYTES 64
 
 const char* td_last_error(void);
 int td_abi_version(void);
@@ -182,6 +184,30 @@ int td_resample_nearest(const void* in, void* out, int planes, int H, int W, int
 int td_affine_clamp(void* x, int B, int C, int64_t HW, int dtype, const float* mean_new,
                     const float* std_new, const float* mean_old, const float* std_old,
                     const float* lo, const float* hi, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ *  Multi-GPU tile shard (new: the reference is single-device).
+ *  One process per GPU; rank r denoises a contiguous chunk of the tile list into an
+ *  exchange buffer that its peers map through CUDA IPC; td_peer_signal publishes a
+ *  step counter into every peer's flag array; td_blend_multidiffusion_peer waits for
+ *  all ranks' counters and blends, reading peer tile outputs over NVLink in the same
+ *  kernel (batch_ptrs[b] = rank b's buffer).  Deterministic tile order => the latent is
+ *  bit-identical on every rank and to a single-GPU run.
+ * ------------------------------------------------------------------------- */
+int td_dev_alloc(int64_t bytes, void** out);   /* cudaMalloc'd (IPC-exportable), zero-filled */
+int td_dev_free(void* ptr);
+int td_ipc_get_handle(const void* dev_ptr, void* handle_out /* TD_IPC_HANDLE_BYTES */);
+int td_ipc_open(const void* handle, void** dev_ptr_out);
+int td_ipc_close(void* dev_ptr);
+/* flag_ptrs: HOST array [world] of DEVICE pointers to each rank's uint32[world] flag array
+ * (own array for i == rank, IPC-mapped for peers).  Stores `value` into slot `rank` of every array. */
+int td_peer_signal(void* const* flag_ptrs, int world, int rank, uint32_t value, void* stream);
+/* As td_blend_multidiffusion, preceded in-kernel by: wait until wait_flags[i] >= wait_value for
+ * all i < world (acquire, system scope).  wait_flags: this rank's own uint32[world] array. */
+int td_blend_multidiffusion_peer(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs,
+                                 int N, int C, int tile_dtype, int acc_dtype, const float* weights,
+                                 float* x_out, void* x_buffer, const uint32_t* wait_flags, int world,
+                                 uint32_t wait_value, uint32_t flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,8 @@ TD_FLAG_NO_TMA = 2
 TD_FLAG_DBG_NO_TILES = 0x100
 TD_MAX_GRID_DIM = 256
 TD_MAX_BATCH_PTRS = 128
+TD_MAX_PEERS = 16
+TD_IPC_HANDLE_BYTES = 64
 ABI_VERSION = 1
 
 DTYPE_CODE = {torch.float16: TD_F16, torch.bfloat16: TD_BF16, torch.float32: TD_F32}
@@ -70,6 +72,14 @@ _SIGNATURES = {
     "td_copy_region": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "td_resample_nearest": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "td_affine_clamp": (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "td_dev_alloc": (c_int, [c_int64, POINTER(c_void_p)]),
+    "td_dev_free": (c_int, [c_void_p]),
+    "td_ipc_get_handle": (c_int, [c_void_p, c_void_p]),
+    "td_ipc_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "td_ipc_close": (c_int, [c_void_p]),
+    "td_peer_signal": (c_int, [POINTER(c_void_p), c_int, c_int, c_uint32, c_void_p]),
+    "td_blend_multidiffusion_peer": (c_int, [POINTER(TdGrid), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_uint32, c_void_p]),
     "td_blend_mixture": (c_int, [POINTER(TdGrid), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
 }

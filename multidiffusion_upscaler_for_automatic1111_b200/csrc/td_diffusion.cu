@@ -44,6 +44,9 @@ struct BlendParams {
     GeomParams g;
     int tile_bs, num_batches;
     unsigned bs_magic;  // fast division by tile_bs
+    const uint32_t* wait_flags;  // tile shard: spin until wait_flags[i] >= wait_value for i < wait_world
+    int wait_world;
+    uint32_t wait_value;
     long long tile_stride;  // N*C*th*tw elements
     const void* batch_ptrs[TD_MAX_BATCH_PTRS];
 };
@@ -182,7 +185,15 @@ blend_grid_vec_kernel(const __grid_constant__ BlendParams p, const float* __rest
     __shared__ short s_ys[TD_MAX_GRID_DIM];
     __shared__ short s_xs[TD_MAX_GRID_DIM];
     const GeomParams& g = p.g;
-    load_origins(g, s_ys, s_xs);
+    if (p.wait_flags != nullptr) {   // tile shard: peers' tile outputs must be complete before they are read
+        if ((int)threadIdx.x < p.wait_world) {
+            uint32_t v;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.wait_flags + threadIdx.x) : "memory");
+            } while (v < p.wait_value);
+        }
+    }
+    load_origins(g, s_ys, s_xs);   // (contains the __syncthreads that publishes the wait)
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane & 7, ly = lane >> 3;
@@ -755,6 +766,7 @@ int fill_blend(const td_grid* g, const void* const* batch_ptrs, int num_batches,
         bp->batch_ptrs[b] = batch_ptrs[b];
     }
     bp->tile_bs = tile_bs;
+    bp->wait_flags = nullptr; bp->wait_world = 0; bp->wait_value = 0;
     bp->bs_magic = magic_u16((unsigned)tile_bs);
     bp->num_batches = num_batches;
     bp->tile_stride = (long long)N * C * g->tile_h * g->tile_w;
@@ -834,6 +846,29 @@ extern "C" int td_blend_multidiffusion(const td_grid* g, const void* const* batc
         }
     }
     return dispatch_generic<MODE_MD>(tile_dtype, acc_dtype, bp, weights, nullptr, nullptr, x_out, x_buffer, s);
+}
+
+extern "C" int td_blend_multidiffusion_peer(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N,
+                                            int C, int tile_dtype, int acc_dtype, const float* weights, float* x_out,
+                                            void* x_buffer, const uint32_t* wait_flags, int world, uint32_t wait_value,
+                                            uint32_t flags, void* stream) {
+    BlendParams bp;
+    int st = fill_blend(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, acc_dtype, &bp);
+    if (st != TD_OK) return st;
+    if (weights == nullptr || x_out == nullptr) { td_set_error("td_blend_multidiffusion_peer: null weights / x_out"); return TD_ERR_INVALID_ARG; }
+    if (wait_flags == nullptr || world <= 0 || world > TD_MAX_PEERS) { td_set_error("td_blend_multidiffusion_peer: bad wait table"); return TD_ERR_INVALID_ARG; }
+    if (!blend_vec_ok(bp, tile_dtype, acc_dtype, {weights, x_out, x_buffer})) {
+        td_set_error("td_blend_multidiffusion_peer: needs the vector path (same tile / canvas dtype, W and tile_w multiples of the vector, 16-byte aligned buffers)");
+        return TD_ERR_UNSUPPORTED;
+    }
+    (void)flags;
+    bp.wait_flags = wait_flags; bp.wait_world = world; bp.wait_value = wait_value;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (tile_dtype) {
+        case TD_F16: return launch_blend_vec<__half, MODE_MD>(bp, weights, nullptr, nullptr, x_out, x_buffer, s);
+        case TD_BF16: return launch_blend_vec<__nv_bfloat16, MODE_MD>(bp, weights, nullptr, nullptr, x_out, x_buffer, s);
+        default: return launch_blend_vec<float, MODE_MD>(bp, weights, nullptr, nullptr, x_out, x_buffer, s);
+    }
 }
 
 extern "C" int td_blend_mixture(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N, int C,

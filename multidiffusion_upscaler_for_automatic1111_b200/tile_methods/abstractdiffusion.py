@@ -81,6 +81,11 @@ class AbstractDiffusion:
         self._tiles: Optional[Tensor] = None  # persistent [T*N, C, th, tw] scatter target
         self._icond_tiles: Optional[Tensor] = None
         self._blend_flags = 0                 # tests flip TD_FLAG_FORCE_GENERIC here
+        self._shard = None                    # parallel.TileShard when tiles are sharded over ranks
+        self._shard_group = None
+        self._shard_fused = False
+        self._exchange = None                 # parallel.PeerExchange (fused path)
+        self._shard_step = 0
 
     # ----------------------------------------------------------------- helpers
     def _sd_model(self):
@@ -198,6 +203,50 @@ class AbstractDiffusion:
     @grid_bbox
     def get_tile_weights(self) -> Union[Tensor, float]:
         return 1.0
+
+    # ------------------------------------------------------------- multi-GPU
+    def init_tile_shard(self, group=None, fused: bool = True):
+        """Shard the tile list over the ranks of `group` (one process per GPU).  Call after init_grid_bbox.
+
+        Each rank denoises `tiles[begin:end)` only; per step the tile outputs are exchanged (fused: peer
+        reads over NVLink inside the blend kernel; else NCCL all-gather) and every rank blends the full
+        latent deterministically (bit-identical across ranks and to a single-GPU run)."""
+        import torch.distributed as dist
+        from .. import parallel
+        if self._grid is None:
+            raise RuntimeError("init_tile_shard() must follow init_grid_bbox()")
+        self._shard = parallel.TileShard(self.num_tiles, dist.get_rank(group), dist.get_world_size(group))
+        self._shard_group, self._shard_fused = group, fused
+        bboxes = [b for batch in self.batched_bboxes for b in batch]
+        local = bboxes[self._shard.begin:self._shard.end]
+        self.local_batched_bboxes = [local[i:i + self.tile_bs] for i in range(0, len(local), self.tile_bs)]
+        return self._shard
+
+    def _exchange_and_blend_md(self, outs, x: Tensor, N: int, C: int) -> Tensor:
+        """Tile-shard tail of MultiDiffusion.sample_one_step."""
+        from .. import parallel
+        sh, g = self._shard, self._grid
+        plane = N * C * g.tile_h * g.tile_w
+        dt = outs[0].dtype if outs else x.dtype
+        self._shard_step += 1
+        if self._shard_fused:
+            if self._exchange is None:
+                self._exchange = parallel.PeerExchange(sh.chunk * plane * x.element_size(), x.device, self._shard_group)
+            parity = self._shard_step & 1
+            if outs:
+                buf = self._exchange.local_buffer(parity, dt)[:sh.num_local * plane].view(sh.num_local * N, C, g.tile_h, g.tile_w)
+                torch.cat([o.to(dt) for o in outs], dim=0, out=buf)
+            self._exchange.signal(self._shard_step)
+            return parallel.blend_multidiffusion_peer(g, self._exchange, parity, sh, N, C, self.weights, dt, self._shard_step)
+        local = torch.zeros((sh.chunk * N, C, g.tile_h, g.tile_w), dtype=dt, device=x.device)
+        if outs:
+            torch.cat(outs, dim=0, out=local[:sh.num_local * N])
+        gathered = parallel.gather_tile_outputs(local, self._shard_group)
+        chunks = []
+        for b in range(sh.num_chunks):
+            nt = min(sh.chunk, sh.num_tiles - b * sh.chunk)
+            chunks.append(gathered[b * sh.chunk * N: (b * sh.chunk + nt) * N])
+        return engine.blend_multidiffusion(g, chunks, N, C, sh.chunk, self.weights, x.dtype, x_buffer=None, flags=self._blend_flags)
 
     # ------------------------------------------- later rows of the scope table
     @custom_bbox

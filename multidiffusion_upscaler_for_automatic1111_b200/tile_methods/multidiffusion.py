@@ -118,6 +118,9 @@ class MultiDiffusion(AbstractDiffusion):
         if not self.draw_background:
             raise NotImplementedError("draw_background=False needs region prompt control (SURVEY.md section 8(f)-1)")
 
+        if self._shard is not None:
+            return self._sample_one_step_sharded(x_in, x, repeat_func, N, C)
+
         tiles = self._scatter_all(x)
         outs = []
         for batch_id, bboxes in enumerate(self.batched_bboxes):
@@ -131,6 +134,23 @@ class MultiDiffusion(AbstractDiffusion):
 
         return engine.blend_multidiffusion(self._grid, outs, N, C, self.tile_bs, self.weights, x.dtype,
                                            x_buffer=None, flags=self._blend_flags)
+
+    def _sample_one_step_sharded(self, x_in: Tensor, x: Tensor, repeat_func: Callable, N: int, C: int) -> Tensor:
+        """This rank's chunk of the tile list, then exchange + deterministic blend (init_tile_shard)."""
+        sh = self._shard
+        outs = []
+        if sh.num_local > 0:
+            self._tiles = engine.scatter_tiles(self._grid, x, out=self._tiles, tile_begin=sh.begin, tile_end=sh.end,
+                                               flags=self._blend_flags)
+            off = 0
+            for batch_id, bboxes in enumerate(self.local_batched_bboxes):
+                if host.interrupted():
+                    return x_in
+                x_tile = self._tiles[off * N:(off + len(bboxes)) * N]
+                off += len(bboxes)
+                outs.append(repeat_func(x_tile, bboxes))
+                self.update_pbar()
+        return self._exchange_and_blend_md(outs, x, N, C)
 
     def get_noise(self, x_in: Tensor, sigma_in: Tensor, cond_in: CondDict, step: int) -> Tensor:
         """Tiled eps prediction used by noise inversion (multidiffusion.py:220-243, grid part)."""
