@@ -195,7 +195,9 @@ class Workload:
         self.g = engine.make_grid(c["W"], c["H"], c["tile"], c["tile"], c["overlap"], c["tile_bs"])
         g = self.g
         self.T = g.num_tiles
-        self.weights = torch.from_numpy(engine.grid_weights(g)).to(device)
+        w_host = engine.grid_weights(g)
+        self.weights = torch.from_numpy(w_host).to(device)
+        self.rcp_weights = torch.from_numpy(engine.exact_reciprocals(w_host)).to(device)   # MultiDiffusion weights are integers
         # tile shard of this rank (contiguous chunk of the row-major tile list)
         self.chunk = -(-self.T // world)
         self.t0 = min(rank * self.chunk, self.T)
@@ -250,7 +252,8 @@ class Workload:
         c = self.cabi
         ptrs, nb, tbs = self._tables[s]
         c.check(c.lib.td_blend_multidiffusion(ctypes.byref(self.g), ptrs, nb, tbs, self.N, self.C, c.TD_F16, c.TD_F16,
-                                              self.weights.data_ptr(), self.x_out[s].data_ptr(), None, flags, self.stream))
+                                              self.weights.data_ptr(), None if (flags & 0x200) else self.rcp_weights.data_ptr(),
+                                              self.x_out[s].data_ptr(), None, flags & 0x1ff, self.stream))
 
     def empty(self, s):
         c = self.cabi
@@ -342,7 +345,8 @@ def gpu_arm(args, rank, world, local_rank):
             t_scatter = only(wl.scatter)
             if args.variants:
                 tbl = {"empty_1024x128": only(wl.empty)}
-                for name, fl in (("tma", 0), ("reg", 2)):
+                tbl["blend_async_ieee_div"] = only(lambda s: wl.blend(s, 0x200))
+                for name, fl in (("async", 0), ("tma", 4), ("reg", 2)):
                     tbl[f"blend_{name}"] = only(lambda s, fl=fl: wl.blend(s, fl))
                     tbl[f"blend_{name}_no_tiles"] = only(lambda s, fl=fl: wl.blend(s, fl | 0x100))
                     tbl[f"blend_{name}_L2hot"] = only(lambda s, fl=fl: wl.blend(0, fl))
@@ -350,11 +354,11 @@ def gpu_arm(args, rank, world, local_rank):
                     tbl[f"scatter_{name}_L2hot"] = only(lambda s, fl=fl: wl.scatter(0, fl))
                 print("VARIANTS(us): " + json.dumps({k: round(v * 1e6, 2) for k, v in tbl.items()}), file=sys.stderr, flush=True)
             roof = {
-                "bound": "hbm", "kernel": "blend_grid_vec_kernel<half, MODE_MD> (td_blend_multidiffusion)",
+                "bound": "hbm", "kernel": "blend_md_async_kernel<half> (td_blend_multidiffusion, cp.async-staged)",
                 "achieved": wl.bytes_blend / t_blend / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": wl.bytes_blend / t_blend / 1e9 / peak, "traffic": load_traffic("blend"),
                 "peak_source": peak_src, "algorithmic_bytes": wl.bytes_blend, "avg_launch_us": t_blend * 1e6,
-                "scatter": {"kernel": "scatter_vec_kernel<half> (td_scatter_tiles)", "achieved": wl.bytes_scatter / t_scatter / 1e9,
+                "scatter": {"kernel": "scatter_tma_kernel<half> (td_scatter_tiles, TMA-staged)", "achieved": wl.bytes_scatter / t_scatter / 1e9,
                             "frac": wl.bytes_scatter / t_scatter / 1e9 / peak, "algorithmic_bytes": wl.bytes_scatter,
                             "avg_launch_us": t_scatter * 1e6, "traffic": load_traffic("scatter")},
                 "note": "back-to-back launches inside a CUDA graph; avg includes the inter-kernel dependency gap",

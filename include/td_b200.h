@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TD_ABI_VERSION 1
+#define TD_ABI_VERSION 2
 
 typedef enum td_status {
     TD_OK = 0,
@@ -39,7 +39,8 @@ typedef enum td_dtype { TD_F16 = 0, TD_BF16 = 1, TD_F32 = 2 } td_dtype;
 
 /* blend flags */
 #define TD_FLAG_FORCE_GENERIC 1u /* use the scalar any-alignment kernel (test / fallback path) */
-#define TD_FLAG_NO_TMA 2u        /* skip the TMA kernels, use the register-staged vector kernels  */
+#define TD_FLAG_NO_TMA 2u        /* use the register-staged vector kernels (no smem staging)      */
+#define TD_FLAG_TMA 4u           /* blend: use the TMA-staged kernel instead of the cp.async one   */
 #define TD_FLAG_DBG_NO_TILES 0x100u /* measurement aid: skip all tile visits (launch + epilogue floor) */
 
 #define TD_MAX_GRID_DIM 256   /* max tile rows / cols of a grid plan            */
@@ -51,6 +52,8 @@ const char* td_last_error(void);
 int td_abi_version(void);
 /* measurement aid: an empty kernel launch (launch-latency floor of the bench harness) */
 int td_debug_launch_empty(int blocks, int threads, void* stream);
+/* measurement / test aid: counts (16-bit numerator, integer w <= max_w) pairs where the fast divide differs from IEEE */
+int td_debug_check_fast_div(int dtype, int max_w, unsigned long long* mismatches_dev, void* stream);
 
 /* ------------------------------------------------------------------------- *
  *  Host bookkeeping (integer-exact; Python float64 semantics reproduced with
@@ -118,10 +121,15 @@ int td_scatter_tiles(const td_grid* g, const void* x, void* tiles, int N, int C,
  * [b*tile_bs, min((b+1)*tile_bs, T)) as [.*N, C, tile_h, tile_w] contiguous
  * (the UNet's output tensors; peer-GPU pointers are allowed).
  * weights: fp32 [H*W] device.  x_out: fp32 [N,C,H,W].  x_buffer (acc_dtype,
- * [N,C,H,W]) is optional (NULL = do not materialise abstractdiffusion.py:24). */
+ * [N,C,H,W]) is optional (NULL = do not materialise abstractdiffusion.py:24).
+ * rcp_weights: optional fp32 [H*W] = correctly rounded 1/weights (td_rescale_factor).  Pass it
+ * ONLY when every weight is an integer <= 4096 (MultiDiffusion's always are) and the canvas is
+ * fp16/bf16: the divide then runs as q=a*rcp; r=fma(-q,w,a); q+=r*rcp, which is the correctly
+ * rounded quotient on that domain (exhaustively verified by td_debug_check_fast_div). */
 int td_blend_multidiffusion(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs,
                             int N, int C, int tile_dtype, int acc_dtype, const float* weights,
-                            float* x_out, void* x_buffer, uint32_t flags, void* stream);
+                            const float* rcp_weights, float* x_out, void* x_buffer, uint32_t flags,
+                            void* stream);
 
 /* Blend, Mixture of Diffusers -- mixtureofdiffusers.py:122-126, returns x_buffer (:169):
  *   w   = tile_weights[v,u] * rescale[y,x]                       (fp32 product)

@@ -20,12 +20,13 @@ TD_ERR_INVALID_ARG, TD_ERR_UNSUPPORTED, TD_ERR_CUDA, TD_ERR_CAPACITY = -1, -2, -
 TD_F16, TD_BF16, TD_F32 = 0, 1, 2
 TD_FLAG_FORCE_GENERIC = 1
 TD_FLAG_NO_TMA = 2
+TD_FLAG_TMA = 4
 TD_FLAG_DBG_NO_TILES = 0x100
 TD_MAX_GRID_DIM = 256
 TD_MAX_BATCH_PTRS = 128
 TD_MAX_PEERS = 16
 TD_IPC_HANDLE_BYTES = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 DTYPE_CODE = {torch.float16: TD_F16, torch.bfloat16: TD_BF16, torch.float32: TD_F32}
 
@@ -62,7 +63,8 @@ _SIGNATURES = {
     "td_rescale_factor": (c_int, [POINTER(c_float), POINTER(c_float), c_int64]),
     "td_scatter_tiles": (c_int, [POINTER(TdGrid), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_uint32, c_void_p]),
     "td_blend_multidiffusion": (c_int, [POINTER(TdGrid), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int,
-                                        c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
+    "td_debug_check_fast_div": (c_int, [c_int, c_int, c_void_p, c_void_p]),
     "td_vae_best_tile_size": (c_int, [c_int, c_int]),
     "td_vae_split_tiles": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32), c_int]),
     "td_gn_stats_workspace_bytes": (c_int64, [c_int64, c_int64, c_int]),

@@ -349,7 +349,229 @@ blend_grid_vec_kernel(const __grid_constant__ BlendParams p, const float* __rest
 }
 
 // ---------------------------------------------------------------------------
-// Blend + normalise, MultiDiffusion, TMA path (the default when it applies).
+// Blend + normalise, MultiDiffusion, cp.async path (the default when it applies).
+//
+// A CTA owns a 16-row x 8-vector patch of one canvas plane.  For every tile touching the
+// patch (ascending tile index) the threads copy the aligned superset of the intersection
+// (9 chunks x 16 rows) global -> shared with 16-byte cp.async; chunks outside the tile
+// use src-size 0, i.e. the copy itself zero-fills them (exact: the accumulator starts at
+// +0 and can never become -0).  Every copy of the CTA is in flight before the first wait:
+// memory-level parallelism without staging registers and without the per-box cost of TMA.
+// The consume loop is specialised on the per-tile shift s (uniform over the CTA): two
+// LDS.128, at most four funnel shifts with an immediate, four packed adds.
+// With integer weights (MultiDiffusion's always are) and their correctly rounded
+// reciprocals supplied, the IEEE divide is q = a*rcp; r = fma(-q, w, a); q' = fma(r, rcp, q)
+// -- correctly rounded for every 16-bit numerator and w <= 4096 (checked exhaustively by
+// td_debug_check_fast_div / tests).
+// ---------------------------------------------------------------------------
+constexpr int kAsX = 8;                          // vectors per patch row
+constexpr int kAsY = 16;                         // patch rows
+constexpr int kAsThreads = kAsX * kAsY;          // 128
+constexpr int kAsChunks = kAsX + 1;              // staged chunks per row (aligned superset)
+constexpr int kAsSlots = kAsY * kAsChunks;       // 144 copy slots per tile visit
+constexpr int kAsStage = kAsSlots * 16;          // 2304 bytes per tile visit
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <typename T, int S>
+__device__ __forceinline__ void consume_shifted(uint4& acc, const unsigned char* p) {
+    const uint4 A = lds128(p);
+    uint4 e;
+    if constexpr (S == 0) {
+        e = A;
+    } else {
+        const uint4 B = lds128(p + 16);
+        e = Vec<T>::window(A, B, S);    // S is a compile-time constant: register selection / immediate shifts only
+    }
+    acc.x = PackedAdd<T>::add(acc.x, e.x);
+    acc.y = PackedAdd<T>::add(acc.y, e.y);
+    acc.z = PackedAdd<T>::add(acc.z, e.z);
+    acc.w = PackedAdd<T>::add(acc.w, e.w);
+}
+
+__device__ __forceinline__ float div_exact_small_int(float a, float w, float rcp) {
+    const float q = __fmul_rn(a, rcp);
+    const float r = __fmaf_rn(-q, w, a);
+    const float q2 = __fmaf_rn(r, rcp, q);
+    // w > 0: the quotient carries a's sign (this also keeps -0 / w = -0, which the fma chain turns into +0)
+    return __uint_as_float((__float_as_uint(q2) & 0x7fffffffu) | (__float_as_uint(a) & 0x80000000u));
+}
+
+// uniform origin search straight from the (constant-bank) kernel parameters
+__device__ __forceinline__ int last_le_c(const short* a, int n, int val, float inv_d) {
+    int i = min(n - 1, max(0, (int)((float)val * inv_d)));
+    while (i + 1 < n && (int)a[i + 1] <= val) ++i;
+    while (i >= 0 && (int)a[i] > val) --i;
+    return i;
+}
+
+struct __align__(16) VisitEntry {   // per tile visit of a CTA, computed once by one thread
+    const void* base;               // element (0, 0) of this plane of the tile
+    short v0, k0;                   // tile row / tile chunk of the patch origin (may be negative)
+    short shift, pad;               // (x_lo - xs) mod VEC
+};
+constexpr int kAsMaxVisits = 64;
+
+template <typename T, bool WRITE_BUF, bool FASTDIV>
+__global__ void __launch_bounds__(kAsThreads)
+blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __restrict__ weights, const float* __restrict__ rcp_weights,
+                      float* __restrict__ out_f32, T* __restrict__ out_buf) {
+    constexpr int VEC = Vec<T>::kElems;
+    constexpr int L2V = Vec<T>::kLog2;
+    constexpr int BX = kAsX * VEC;
+    extern __shared__ __align__(16) unsigned char td_smem[];
+    __shared__ int s_rng[4];
+    __shared__ VisitEntry s_visit[kAsMaxVisits];
+    const GeomParams& g = p.g;
+    const int tid = threadIdx.x;
+    const int plane = blockIdx.z;
+    const int x_lo = blockIdx.x * BX, y_lo = blockIdx.y * kAsY;
+
+    // ---- which tiles touch this patch: four searches, one thread each ---------------------------------
+    if (tid < 4) {
+        const int x_hi = min(x_lo + BX, g.W) - 1, y_hi = min(y_lo + kAsY, g.H) - 1;
+        int v;
+        if (tid == 0) v = last_le_c(g.ys, g.rows, y_lo - g.th, g.inv_dy) + 1;
+        else if (tid == 1) v = last_le_c(g.ys, g.rows, y_hi, g.inv_dy);
+        else if (tid == 2) v = last_le_c(g.xs, g.cols, x_lo - g.tw, g.inv_dx) + 1;
+        else v = last_le_c(g.xs, g.cols, x_hi, g.inv_dx);
+        s_rng[tid] = v;
+    }
+    __syncthreads();
+    const int r_lo = s_rng[0], c_lo = s_rng[2];
+    const int nc = s_rng[3] - c_lo + 1;
+    const int nv = g.dbg_no_tiles ? 0 : (s_rng[1] - r_lo + 1) * nc;   // <= the host's stage count
+
+    // ---- per-visit constants: thread i prepares visit i -------------------------------------------------
+    if (tid < nv) {
+        const int ri = tid / nc, ci = tid - ri * nc;
+        const int r = r_lo + ri, c = c_lo + ci;
+        const unsigned t = (unsigned)(r * g.cols + c);
+        const unsigned b = fastdiv(t, p.bs_magic);
+        const T* base = reinterpret_cast<const T*>(p.batch_ptrs[b]) + (long long)(t - b * (unsigned)p.tile_bs) * p.tile_stride +
+                        (long long)plane * g.th * g.tw;
+        const int u0 = x_lo - (int)g.xs[c];
+        VisitEntry e;
+        e.base = base;
+        e.v0 = (short)(y_lo - (int)g.ys[r]);
+        e.k0 = (short)(u0 >> L2V);
+        e.shift = (short)(u0 & (VEC - 1));
+        e.pad = 0;
+        s_visit[tid] = e;
+    }
+    __syncthreads();
+
+    // ---- issue every copy of this CTA -------------------------------------------------------------------
+    const int row0 = tid / kAsChunks, j0 = tid - row0 * kAsChunks;                 // slot tid
+    const int slot1 = tid + kAsThreads;                                            // slot tid + 128 (threads 0..15)
+    const int row1 = slot1 / kAsChunks, j1 = slot1 - row1 * kAsChunks;
+    const bool has1 = slot1 < kAsSlots;
+    const int twv = g.tw >> L2V;
+    {
+        unsigned char* dst0 = td_smem + tid * 16;
+        for (int i = 0; i < nv; ++i, dst0 += kAsStage) {
+            const VisitEntry e = s_visit[i];
+            const T* base = reinterpret_cast<const T*>(e.base);
+            {
+                const int v = (int)e.v0 + row0, k = (int)e.k0 + j0;
+                const bool ok = (unsigned)v < (unsigned)g.th && (unsigned)k < (unsigned)twv;
+                const int off = ok ? v * g.tw + k * VEC : 0;
+                cp_async16(dst0, base + off, ok ? 16 : 0);
+            }
+            if (has1) {
+                const int v = (int)e.v0 + row1, k = (int)e.k0 + j1;
+                const bool ok = (unsigned)v < (unsigned)g.th && (unsigned)k < (unsigned)twv;
+                const int off = ok ? v * g.tw + k * VEC : 0;
+                cp_async16(dst0 + kAsThreads * 16, base + off, ok ? 16 : 0);
+            }
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---- consume in tile order ------------------------------------------------------------------------
+    const int tx = tid % kAsX, ty = tid / kAsX;
+    const unsigned char* mine = td_smem + (ty * kAsChunks + tx) * 16;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    {
+        for (int i = 0; i < nv; ++i, mine += kAsStage) {
+            const int s = (int)s_visit[i].shift;   // uniform over the CTA
+            if constexpr (VEC == 8) {
+                switch (s) {
+                    case 0: consume_shifted<T, 0>(acc, mine); break;
+                    case 1: consume_shifted<T, 1>(acc, mine); break;
+                    case 2: consume_shifted<T, 2>(acc, mine); break;
+                    case 3: consume_shifted<T, 3>(acc, mine); break;
+                    case 4: consume_shifted<T, 4>(acc, mine); break;
+                    case 5: consume_shifted<T, 5>(acc, mine); break;
+                    case 6: consume_shifted<T, 6>(acc, mine); break;
+                    default: consume_shifted<T, 7>(acc, mine); break;
+                }
+            } else {
+                switch (s) {
+                    case 0: consume_shifted<T, 0>(acc, mine); break;
+                    case 1: consume_shifted<T, 1>(acc, mine); break;
+                    case 2: consume_shifted<T, 2>(acc, mine); break;
+                    default: consume_shifted<T, 3>(acc, mine); break;
+                }
+            }
+        }
+    }
+
+    // ---- normalise + store --------------------------------------------------------------------------
+    const int x0 = x_lo + tx * VEC, y = y_lo + ty;
+    if (x0 >= g.W || y >= g.H) return;
+    const long long o = ((long long)plane * g.H + y) * g.W + x0;
+    const long long wo = (long long)y * g.W + x0;
+    float4* op = reinterpret_cast<float4*>(out_f32 + o);
+#pragma unroll
+    for (int h = 0; h < VEC / 4; ++h) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(weights + wo) + h);
+        const float a0 = Vec<T>::get(acc, 4 * h + 0), a1 = Vec<T>::get(acc, 4 * h + 1);
+        const float a2 = Vec<T>::get(acc, 4 * h + 2), a3 = Vec<T>::get(acc, 4 * h + 3);
+        float4 f;   // x_out = where(weights > 1, x_buffer / weights, x_buffer)  -- fp32, correctly rounded divide
+        if constexpr (FASTDIV) {
+            const float4 rc = __ldg(reinterpret_cast<const float4*>(rcp_weights + wo) + h);
+            f.x = w.x > 1.0f ? div_exact_small_int(a0, w.x, rc.x) : a0;
+            f.y = w.y > 1.0f ? div_exact_small_int(a1, w.y, rc.y) : a1;
+            f.z = w.z > 1.0f ? div_exact_small_int(a2, w.z, rc.z) : a2;
+            f.w = w.w > 1.0f ? div_exact_small_int(a3, w.w, rc.w) : a3;
+        } else {
+            f.x = w.x > 1.0f ? __fdiv_rn(a0, w.x) : a0;
+            f.y = w.y > 1.0f ? __fdiv_rn(a1, w.y) : a1;
+            f.z = w.z > 1.0f ? __fdiv_rn(a2, w.z) : a2;
+            f.w = w.w > 1.0f ? __fdiv_rn(a3, w.w) : a3;
+        }
+        op[h] = f;
+    }
+    if constexpr (WRITE_BUF) stg128(out_buf + o, acc);
+}
+
+// exhaustive check of div_exact_small_int against the IEEE divide: every 16-bit pattern of T x w in [1, max_w]
+template <typename T>
+__global__ void check_fast_div_kernel(int max_w, unsigned long long* mismatches) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;   // 16-bit pattern
+    if (idx >= 65536u) return;
+    const float a = Elem<T>::bits_to_f32((uint16_t)idx);
+    if (isnan(a) || isinf(a)) return;
+    unsigned long long bad = 0;
+    for (int wi = 1; wi <= max_w; ++wi) {
+        const float w = (float)wi;
+        const float rcp = __fdiv_rn(1.0f, w);
+        const float q = div_exact_small_int(a, w, rcp);
+        const float ref = __fdiv_rn(a, w);
+        if (__float_as_uint(q) != __float_as_uint(ref)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+// ---------------------------------------------------------------------------
+// Blend + normalise, MultiDiffusion, TMA path (TD_FLAG_TMA; kept as the measured alternative).
 //
 // A CTA owns an 8-row x 16-vector patch of one canvas plane.  For every tile that
 // touches the patch (ascending tile index) one thread issues ONE cp.async.bulk.tensor
@@ -639,6 +861,9 @@ int max_union(const int32_t* org, int n, int extent, int size, int patch) {
     return best;
 }
 
+// dynamic shared memory a kernel may request without opting in (48 KB minus its static allocation, with margin)
+constexpr int kNoOptInSmem = 40 * 1024;
+
 template <typename KernelT>
 int ensure_dyn_smem(KernelT kernel, int bytes, int* configured) {
     if (bytes <= *configured) return TD_OK;
@@ -666,7 +891,7 @@ int launch_blend_tma_nb(const td_grid* g, const BlendParams& bp, int tile_dtype,
         if (rc != TD_OK) return rc;
     }
     const int smem = nv_cap * (STAGE + 8);
-    static int configured = 48 * 1024;
+    static int configured = kNoOptInSmem;
     int rc = ensure_dyn_smem(blend_md_tma_kernel<T, WRITE_BUF, NB>, smem, &configured);
     if (rc != TD_OK) return rc;
     dim3 grid((unsigned)((bp.g.W + BX - 1) / BX), (unsigned)((bp.g.H + kTmaBY - 1) / kTmaBY), (unsigned)NC);
@@ -716,6 +941,47 @@ int try_launch_scatter_tma(GeomParams gp, const void* x, void* tiles, int dtype,
     if (grid.y > 65535u) return 1;
     scatter_tma_kernel<T><<<grid, 128, pitch * rb, st>>>(tp, (T*)tiles, tile_begin, rb);
     return check_launch("td_scatter_tiles (tma)");
+}
+
+template <typename T, bool WRITE_BUF>
+int launch_blend_async(const td_grid* g, const BlendParams& bp, const float* weights, const float* rcp_weights, float* out_f32,
+                       void* out_buf, int nv_cap, cudaStream_t st) {
+    constexpr int VEC = Vec<T>::kElems;
+    constexpr int BX = kAsX * VEC;
+    const int smem = nv_cap * kAsStage;
+    dim3 grid((unsigned)((bp.g.W + BX - 1) / BX), (unsigned)((bp.g.H + kAsY - 1) / kAsY), (unsigned)(bp.g.N * bp.g.C));
+    static int configured_fast = kNoOptInSmem, configured_ieee = kNoOptInSmem;
+    if (rcp_weights != nullptr && sizeof(T) == 2) {
+        int rc = ensure_dyn_smem(blend_md_async_kernel<T, WRITE_BUF, true>, smem, &configured_fast);
+        if (rc != TD_OK) return rc;
+        blend_md_async_kernel<T, WRITE_BUF, true><<<grid, kAsThreads, smem, st>>>(bp, weights, rcp_weights, out_f32, (T*)out_buf);
+    } else {
+        int rc = ensure_dyn_smem(blend_md_async_kernel<T, WRITE_BUF, false>, smem, &configured_ieee);
+        if (rc != TD_OK) return rc;
+        blend_md_async_kernel<T, WRITE_BUF, false><<<grid, kAsThreads, smem, st>>>(bp, weights, nullptr, out_f32, (T*)out_buf);
+    }
+    int st2 = check_launch("td_blend_multidiffusion (cp.async)");
+    if (st2 != TD_OK) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, blend_md_async_kernel<T, WRITE_BUF, false>);
+        td_set_error("td_blend_multidiffusion (cp.async): launch failed: smem=%d nv_cap=%d grid=(%u,%u,%u) static=%zu maxdyn=%d cfg_fast=%d cfg_ieee=%d",
+                     smem, nv_cap, grid.x, grid.y, grid.z, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, configured_fast, configured_ieee);
+    }
+    return st2;
+}
+
+// returns TD_OK if launched, 1 if the path does not apply (caller falls back), <0 on error
+template <typename T>
+int try_launch_blend_async(const td_grid* g, const BlendParams& bp, const float* weights, const float* rcp_weights, float* out_f32,
+                           void* out_buf, cudaStream_t st) {
+    constexpr int VEC = Vec<T>::kElems;
+    constexpr int BX = kAsX * VEC;
+    if (bp.g.N * bp.g.C > 65535 || (bp.g.H + kAsY - 1) / kAsY > 65535) return 1;
+    if (bp.tile_stride >= (1ll << 31)) return 1;
+    const int nv_cap = max_union(g->ys, g->rows, g->tile_h, g->H, kAsY) * max_union(g->xs, g->cols, g->tile_w, g->W, BX);
+    if (nv_cap <= 0 || nv_cap > kAsMaxVisits || nv_cap > kAsThreads || nv_cap * kAsStage > 200 * 1024) return 1;
+    return out_buf != nullptr ? launch_blend_async<T, true>(g, bp, weights, rcp_weights, out_f32, out_buf, nv_cap, st)
+                              : launch_blend_async<T, false>(g, bp, weights, rcp_weights, out_f32, out_buf, nv_cap, st);
 }
 
 template <typename TIn, typename TAcc, int MODE>
@@ -821,24 +1087,30 @@ extern "C" int td_scatter_tiles(const td_grid* g, const void* x, void* tiles, in
 }
 
 extern "C" int td_blend_multidiffusion(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N,
-                                       int C, int tile_dtype, int acc_dtype, const float* weights, float* x_out,
-                                       void* x_buffer, uint32_t flags, void* stream) {
+                                       int C, int tile_dtype, int acc_dtype, const float* weights, const float* rcp_weights,
+                                       float* x_out, void* x_buffer, uint32_t flags, void* stream) {
     BlendParams bp;
     int st = fill_blend(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, acc_dtype, &bp);
     if (st != TD_OK) return st;
     if (weights == nullptr || x_out == nullptr) { td_set_error("td_blend_multidiffusion: null weights / x_out"); return TD_ERR_INVALID_ARG; }
     bp.g.dbg_no_tiles = (flags & TD_FLAG_DBG_NO_TILES) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!(flags & TD_FLAG_FORCE_GENERIC) && blend_vec_ok(bp, tile_dtype, acc_dtype, {weights, x_out, x_buffer})) {
-        if (!(flags & TD_FLAG_NO_TMA)) {
-            int rc;
+    if (!(flags & TD_FLAG_FORCE_GENERIC) && blend_vec_ok(bp, tile_dtype, acc_dtype, {weights, rcp_weights, x_out, x_buffer})) {
+        int rc = 1;
+        if (flags & TD_FLAG_TMA) {
             switch (tile_dtype) {
                 case TD_F16: rc = try_launch_blend_tma<__half>(g, bp, tile_dtype, weights, x_out, x_buffer, s); break;
                 case TD_BF16: rc = try_launch_blend_tma<__nv_bfloat16>(g, bp, tile_dtype, weights, x_out, x_buffer, s); break;
                 default: rc = try_launch_blend_tma<float>(g, bp, tile_dtype, weights, x_out, x_buffer, s); break;
             }
-            if (rc <= 0) return rc;   // launched or hard error; 1 = not applicable -> register kernel
+        } else if (!(flags & TD_FLAG_NO_TMA)) {
+            switch (tile_dtype) {
+                case TD_F16: rc = try_launch_blend_async<__half>(g, bp, weights, rcp_weights, x_out, x_buffer, s); break;
+                case TD_BF16: rc = try_launch_blend_async<__nv_bfloat16>(g, bp, weights, rcp_weights, x_out, x_buffer, s); break;
+                default: rc = try_launch_blend_async<float>(g, bp, weights, nullptr, x_out, x_buffer, s); break;
+            }
         }
+        if (rc <= 0) return rc;   // launched or hard error; 1 = not applicable -> register-staged kernel
         switch (tile_dtype) {
             case TD_F16: return launch_blend_vec<__half, MODE_MD>(bp, weights, nullptr, nullptr, x_out, x_buffer, s);
             case TD_BF16: return launch_blend_vec<__nv_bfloat16, MODE_MD>(bp, weights, nullptr, nullptr, x_out, x_buffer, s);
@@ -846,6 +1118,16 @@ extern "C" int td_blend_multidiffusion(const td_grid* g, const void* const* batc
         }
     }
     return dispatch_generic<MODE_MD>(tile_dtype, acc_dtype, bp, weights, nullptr, nullptr, x_out, x_buffer, s);
+}
+
+extern "C" int td_debug_check_fast_div(int dtype, int max_w, unsigned long long* mismatches_dev, void* stream) {
+    if (mismatches_dev == nullptr || max_w < 1 || (dtype != TD_F16 && dtype != TD_BF16)) {
+        td_set_error("td_debug_check_fast_div: bad arguments");
+        return TD_ERR_INVALID_ARG;
+    }
+    if (dtype == TD_F16) check_fast_div_kernel<__half><<<256, 256, 0, (cudaStream_t)stream>>>(max_w, mismatches_dev);
+    else check_fast_div_kernel<__nv_bfloat16><<<256, 256, 0, (cudaStream_t)stream>>>(max_w, mismatches_dev);
+    return check_launch("td_debug_check_fast_div");
 }
 
 extern "C" int td_blend_multidiffusion_peer(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N,

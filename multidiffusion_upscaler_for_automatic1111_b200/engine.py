@@ -98,17 +98,30 @@ def _batch_table(g: TdGrid, batch_outs: Sequence[torch.Tensor], N: int, C: int, 
 
 def blend_multidiffusion(g: TdGrid, batch_outs: Sequence[torch.Tensor], N: int, C: int, tile_bs: int,
                          weights: torch.Tensor, acc_dtype: torch.dtype, x_buffer: Optional[torch.Tensor] = None,
-                         flags: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Fused multidiffusion.py:166-167 + :208.  Returns fp32 [N,C,H,W] (fresh unless `out` is given)."""
+                         flags: int = 0, out: Optional[torch.Tensor] = None, rcp_weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused multidiffusion.py:166-167 + :208.  Returns fp32 [N,C,H,W] (fresh unless `out` is given).
+
+    rcp_weights (see `exact_reciprocals`) enables the 3-instruction exact divide for integer weights."""
     ptrs, keep, tdt = _batch_table(g, batch_outs, N, C, tile_bs)
     dev = keep[0].device
     x_out = out if out is not None else torch.empty((N, C, g.H, g.W), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         check(lib.td_blend_multidiffusion(ctypes.byref(g), ptrs, len(keep), int(tile_bs), N, C, dtype_code(tdt),
-                                          dtype_code(acc_dtype), weights.data_ptr(), x_out.data_ptr(),
+                                          dtype_code(acc_dtype), weights.data_ptr(),
+                                          rcp_weights.data_ptr() if rcp_weights is not None else None, x_out.data_ptr(),
                                           x_buffer.data_ptr() if x_buffer is not None else None, int(flags),
                                           current_stream_ptr(dev)))
     return x_out
+
+
+def exact_reciprocals(weights_host: np.ndarray) -> Optional[np.ndarray]:
+    """RN(1/w) for a weight canvas whose entries are all integers in [0, 4096] (MultiDiffusion's
+    uniform counts), else None: the precondition of td_blend_multidiffusion's fast exact divide."""
+    w = np.ascontiguousarray(weights_host, dtype=np.float32)
+    if not (np.all(w == np.floor(w)) and w.min() >= 0 and w.max() <= 4096):
+        return None
+    with np.errstate(divide="ignore"):
+        return rescale_factor(w)
 
 
 def blend_mixture(g: TdGrid, batch_outs: Sequence[torch.Tensor], N: int, C: int, tile_bs: int,

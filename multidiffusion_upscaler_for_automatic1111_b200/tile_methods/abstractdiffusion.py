@@ -81,6 +81,7 @@ class AbstractDiffusion:
         self._tiles: Optional[Tensor] = None  # persistent [T*N, C, th, tw] scatter target
         self._icond_tiles: Optional[Tensor] = None
         self._blend_flags = 0                 # tests flip TD_FLAG_FORCE_GENERIC here
+        self._rcp_weights: Optional[Tensor] = None   # RN(1/weights) when all weights are small integers
         self._shard = None                    # parallel.TileShard when tiles are sharded over ranks
         self._shard_group = None
         self._shard_fused = False
@@ -123,6 +124,8 @@ class AbstractDiffusion:
 
     def init_done(self):
         """abstractdiffusion.py:104-117: sanity check + progress accounting."""
+        rcp = engine.exact_reciprocals(self.weights.detach().to("cpu", torch.float32).numpy().reshape(self.h, self.w))
+        self._rcp_weights = None if rcp is None else torch.from_numpy(rcp).to(self.weights.device)
         self.total_bboxes = 0
         if self.enable_grid_bbox:
             self.total_bboxes += self.num_batches
@@ -246,7 +249,8 @@ class AbstractDiffusion:
         for b in range(sh.num_chunks):
             nt = min(sh.chunk, sh.num_tiles - b * sh.chunk)
             chunks.append(gathered[b * sh.chunk * N: (b * sh.chunk + nt) * N])
-        return engine.blend_multidiffusion(g, chunks, N, C, sh.chunk, self.weights, x.dtype, x_buffer=None, flags=self._blend_flags)
+        return engine.blend_multidiffusion(g, chunks, N, C, sh.chunk, self.weights, x.dtype, x_buffer=None, flags=self._blend_flags,
+                                           rcp_weights=self._rcp_weights)
 
     # ------------------------------------------- later rows of the scope table
     @custom_bbox
@@ -282,6 +286,8 @@ class AbstractDiffusion:
             raise RuntimeError(f"{self.method}: init_grid_bbox() has not been called")
         if self.weights.device != x_in.device:
             self.weights = self.weights.to(x_in.device)
+        if self._rcp_weights is not None and self._rcp_weights.device != x_in.device:
+            self._rcp_weights = self._rcp_weights.to(x_in.device)
         return x_in.contiguous()
 
     def _scatter_all(self, x_in: Tensor) -> Tensor:

@@ -133,7 +133,7 @@ class MultiDiffusion(AbstractDiffusion):
             self.update_pbar()
 
         return engine.blend_multidiffusion(self._grid, outs, N, C, self.tile_bs, self.weights, x.dtype,
-                                           x_buffer=None, flags=self._blend_flags)
+                                           x_buffer=None, flags=self._blend_flags, rcp_weights=self._rcp_weights)
 
     def _sample_one_step_sharded(self, x_in: Tensor, x: Tensor, repeat_func: Callable, N: int, C: int) -> Tensor:
         """This rank's chunk of the tile list, then exchange + deterministic blend (init_tile_shard)."""

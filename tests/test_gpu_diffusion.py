@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 
 FORCE_GENERIC = 1
 NO_TMA = 2
-ALL_PATHS = [0, NO_TMA, FORCE_GENERIC]   # TMA kernels, register-staged vector kernels, scalar kernels
+TMA = 4
+ALL_PATHS = [0, TMA, NO_TMA, FORCE_GENERIC]   # cp.async-staged (default), TMA-staged, register-staged, scalar kernels
 
 
 @pytest.fixture(scope="module")
@@ -52,7 +53,7 @@ def test_scatter_bit_exact(eng, case, dn, flags):
         assert_bit_equal(part, want[lo * N:hi * N], "scatter range")
 
 
-def _run_cuda_step(eng, method, x, W, H, tw, th, ov, bs, flags=0, one_batch=False, tile_dtype=None):
+def _run_cuda_step(eng, method, x, W, H, tw, th, ov, bs, flags=0, one_batch=False, tile_dtype=None, use_rcp=False):
     """scatter -> fake UNet per batch (on the GPU) -> fused blend, through the engine wrappers."""
     N, C = x.shape[:2]
     g = _grid(eng, W, H, tw, th, ov, bs)
@@ -73,7 +74,8 @@ def _run_cuda_step(eng, method, x, W, H, tw, th, ov, bs, flags=0, one_batch=Fals
     if method == "md":
         w = torch.from_numpy(plan.weights).cuda()
         xb = torch.empty_like(xd)
-        out = eng.blend_multidiffusion(g, outs, N, C, tile_bs, w, xd.dtype, x_buffer=xb, flags=flags)
+        rcp = torch.from_numpy(eng.exact_reciprocals(plan.weights)).cuda() if use_rcp else None
+        out = eng.blend_multidiffusion(g, outs, N, C, tile_bs, w, xd.dtype, x_buffer=xb, flags=flags, rcp_weights=rcp)
         return out, xb, plan
     twt = torch.from_numpy(plan.tile_weights).cuda()
     rf = torch.from_numpy(plan.rescale_factor).cuda()
@@ -104,6 +106,33 @@ def test_blend_small_matches_reference_fixtures(eng, golden_dir, method, dn, fla
         key = f"{name}_{dn}_{method}"
         assert str(out.dtype) == str(g[key + "_dtype"]), key
         assert np.array_equal(bits(out), g[key]), f"{key}: CUDA output differs from the reference's"
+
+
+@pytest.mark.parametrize("dn", ["f16", "bf16"])
+def test_fast_exact_divide_is_ieee_on_its_domain(dn):
+    """q = a*rcp; r = fma(-q, w, a); q += r*rcp  ==  IEEE a / w for EVERY 16-bit numerator and integer w <= 4096."""
+    import ctypes
+    from multidiffusion_upscaler_for_automatic1111_b200 import _cabi
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _cabi.check(_cabi.lib.td_debug_check_fast_div(_cabi.dtype_code(DTYPES[dn]), 4096, bad.data_ptr(), _cabi.current_stream_ptr()))
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
+
+
+@pytest.mark.parametrize("dn", ["f16", "bf16"])
+@pytest.mark.parametrize("flags", [0, TMA, NO_TMA])
+def test_blend_with_reciprocal_weights_matches_reference(eng, golden_dir, dn, flags):
+    g = np.load(os.path.join(golden_dir, "blend_small.npz"))
+    for name, (N, C, W, H, tw, th, ov, bs) in zip(g["names"], g["cases"]):
+        x = synth.latent(synth.case_seed(str(name), dn), (int(N), int(C), int(H), int(W)), DTYPES[dn])
+        out, _, _ = _run_cuda_step(eng, "md", x, int(W), int(H), int(tw), int(th), int(ov), int(bs), flags=flags, use_rcp=True)
+        assert np.array_equal(bits(out), g[f"{name}_{dn}_md"]), f"{name}: fast-divide output differs from the reference's"
+    h = np.load(os.path.join(golden_dir, "blend_hashes.npz"))
+    idx = list(h["names"]).index("cfg2_ov48")
+    N, C, W, H, tw, th, ov, bs = map(int, h["cases"][idx])
+    x = synth.latent(synth.case_seed("cfg2_ov48", dn), (N, C, H, W), DTYPES[dn])
+    out, _, _ = _run_cuda_step(eng, "md", x, W, H, tw, th, ov, bs, flags=flags, use_rcp=True)
+    assert sha(out) == str(h[f"cfg2_ov48_{dn}_md"])
 
 
 @pytest.mark.parametrize("method", ["md", "mod"])
