@@ -346,7 +346,7 @@ def gpu_arm(args, rank, world, local_rank):
             if args.variants:
                 tbl = {"empty_1024x128": only(wl.empty)}
                 tbl["blend_async_ieee_div"] = only(lambda s: wl.blend(s, 0x200))
-                for name, fl in (("async", 0), ("tma", 4), ("reg", 2)):
+                for name, fl in (("async", 0), ("pipe", 8), ("tma", 4), ("reg", 2)):
                     tbl[f"blend_{name}"] = only(lambda s, fl=fl: wl.blend(s, fl))
                     tbl[f"blend_{name}_no_tiles"] = only(lambda s, fl=fl: wl.blend(s, fl | 0x100))
                     tbl[f"blend_{name}_L2hot"] = only(lambda s, fl=fl: wl.blend(0, fl))

@@ -21,6 +21,7 @@ TD_F16, TD_BF16, TD_F32 = 0, 1, 2
 TD_FLAG_FORCE_GENERIC = 1
 TD_FLAG_NO_TMA = 2
 TD_FLAG_TMA = 4
+TD_FLAG_PIPELINE = 8
 TD_FLAG_DBG_NO_TILES = 0x100
 TD_MAX_GRID_DIM = 256
 TD_MAX_BATCH_PTRS = 128

@@ -44,6 +44,9 @@ struct BlendParams {
     GeomParams g;
     int tile_bs, num_batches;
     unsigned bs_magic;  // fast division by tile_bs
+    // cp.async kernel: tiles touching patch row / patch col i (first index, count), computed on the host
+    unsigned char prow_lo[TD_MAX_GRID_DIM], prow_n[TD_MAX_GRID_DIM];
+    unsigned char pcol_lo[TD_MAX_GRID_DIM], pcol_n[TD_MAX_GRID_DIM];
     const uint32_t* wait_flags;  // tile shard: spin until wait_flags[i] >= wait_value for i < wait_world
     int wait_world;
     uint32_t wait_value;
@@ -366,13 +369,23 @@ blend_grid_vec_kernel(const __grid_constant__ BlendParams p, const float* __rest
 // ---------------------------------------------------------------------------
 constexpr int kAsX = 8;                          // vectors per patch row
 constexpr int kAsY = 16;                         // patch rows
-constexpr int kAsThreads = kAsX * kAsY;          // 128
+constexpr int kAsVecThreads = kAsX * kAsY;       // 128 threads own one output vector each
 constexpr int kAsChunks = kAsX + 1;              // staged chunks per row (aligned superset)
-constexpr int kAsSlots = kAsY * kAsChunks;       // 144 copy slots per tile visit
+constexpr int kAsSlots = kAsY * kAsChunks;       // 144 copy slots per tile visit: one per thread
+constexpr int kAsThreads = 160;                  // 5 warps: 144 copy threads (the last half warp idles)
 constexpr int kAsStage = kAsSlots * 16;          // 2304 bytes per tile visit
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+// 16-byte copy that writes zeros instead (no global access) when `neg_if_skip` is negative
+__device__ __forceinline__ void cp_async16_zfill(uint32_t smem_dst, long long gmem_src, int neg_if_skip) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.lt.s32 p, %2, 0;\n\t"
+        "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t}"
+        ::"r"(smem_dst), "l"(gmem_src), "r"(neg_if_skip)
+        : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -411,9 +424,8 @@ __device__ __forceinline__ int last_le_c(const short* a, int n, int val, float i
 }
 
 struct __align__(16) VisitEntry {   // per tile visit of a CTA, computed once by one thread
-    const void* base;               // element (0, 0) of this plane of the tile
-    short v0, k0;                   // tile row / tile chunk of the patch origin (may be negative)
-    short shift, pad;               // (x_lo - xs) mod VEC
+    long long origin;               // byte address of tile element (v0, k0*VEC) of this plane (may lie before the tile)
+    int v0, k0;                     // tile row / tile chunk of the patch origin (may be negative)
 };
 constexpr int kAsMaxVisits = 64;
 
@@ -425,27 +437,29 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
     constexpr int L2V = Vec<T>::kLog2;
     constexpr int BX = kAsX * VEC;
     extern __shared__ __align__(16) unsigned char td_smem[];
-    __shared__ int s_rng[4];
     __shared__ VisitEntry s_visit[kAsMaxVisits];
+    __shared__ int s_shift[kAsMaxVisits];
     const GeomParams& g = p.g;
     const int tid = threadIdx.x;
     const int plane = blockIdx.z;
     const int x_lo = blockIdx.x * BX, y_lo = blockIdx.y * kAsY;
 
-    // ---- which tiles touch this patch: four searches, one thread each ---------------------------------
-    if (tid < 4) {
-        const int x_hi = min(x_lo + BX, g.W) - 1, y_hi = min(y_lo + kAsY, g.H) - 1;
-        int v;
-        if (tid == 0) v = last_le_c(g.ys, g.rows, y_lo - g.th, g.inv_dy) + 1;
-        else if (tid == 1) v = last_le_c(g.ys, g.rows, y_hi, g.inv_dy);
-        else if (tid == 2) v = last_le_c(g.xs, g.cols, x_lo - g.tw, g.inv_dx) + 1;
-        else v = last_le_c(g.xs, g.cols, x_hi, g.inv_dx);
-        s_rng[tid] = v;
+    // tiles touching this patch: host-computed per patch row / col (uniform constant-bank reads)
+    const int r_lo = p.prow_lo[blockIdx.y], c_lo = p.pcol_lo[blockIdx.x];
+    const int nc = p.pcol_n[blockIdx.x];
+    const int nv = g.dbg_no_tiles ? 0 : (int)p.prow_n[blockIdx.y] * nc;   // <= the host's stage count
+
+    // this thread's output vector; its weights are fetched now so that their latency hides behind the tile copies
+    const int tx = tid % kAsX, ty = tid / kAsX;
+    const int x0 = x_lo + tx * VEC, y = y_lo + ty;
+    const bool inside = tid < kAsVecThreads && x0 < g.W && y < g.H;
+    const long long wo = (long long)y * g.W + x0;
+    float4 wv[VEC / 4], rv[VEC / 4];
+#pragma unroll
+    for (int h = 0; h < VEC / 4; ++h) {
+        wv[h] = inside ? __ldg(reinterpret_cast<const float4*>(weights + wo) + h) : make_float4(1.f, 1.f, 1.f, 1.f);
+        if constexpr (FASTDIV) rv[h] = inside ? __ldg(reinterpret_cast<const float4*>(rcp_weights + wo) + h) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
-    __syncthreads();
-    const int r_lo = s_rng[0], c_lo = s_rng[2];
-    const int nc = s_rng[3] - c_lo + 1;
-    const int nv = g.dbg_no_tiles ? 0 : (s_rng[1] - r_lo + 1) * nc;   // <= the host's stage count
 
     // ---- per-visit constants: thread i prepares visit i -------------------------------------------------
     if (tid < nv) {
@@ -453,54 +467,43 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
         const int r = r_lo + ri, c = c_lo + ci;
         const unsigned t = (unsigned)(r * g.cols + c);
         const unsigned b = fastdiv(t, p.bs_magic);
-        const T* base = reinterpret_cast<const T*>(p.batch_ptrs[b]) + (long long)(t - b * (unsigned)p.tile_bs) * p.tile_stride +
-                        (long long)plane * g.th * g.tw;
         const int u0 = x_lo - (int)g.xs[c];
+        const int v0 = y_lo - (int)g.ys[r], k0 = u0 >> L2V;
+        const long long elem = (long long)(t - b * (unsigned)p.tile_bs) * p.tile_stride + (long long)plane * g.th * g.tw +
+                               (long long)v0 * g.tw + (long long)k0 * VEC;
         VisitEntry e;
-        e.base = base;
-        e.v0 = (short)(y_lo - (int)g.ys[r]);
-        e.k0 = (short)(u0 >> L2V);
-        e.shift = (short)(u0 & (VEC - 1));
-        e.pad = 0;
+        e.origin = (long long)reinterpret_cast<uintptr_t>(p.batch_ptrs[b]) + elem * (long long)sizeof(T);
+        e.v0 = v0;
+        e.k0 = k0;
         s_visit[tid] = e;
+        s_shift[tid] = u0 & (VEC - 1);
     }
     __syncthreads();
 
-    // ---- issue every copy of this CTA -------------------------------------------------------------------
-    const int row0 = tid / kAsChunks, j0 = tid - row0 * kAsChunks;                 // slot tid
-    const int slot1 = tid + kAsThreads;                                            // slot tid + 128 (threads 0..15)
-    const int row1 = slot1 / kAsChunks, j1 = slot1 - row1 * kAsChunks;
-    const bool has1 = slot1 < kAsSlots;
-    const int twv = g.tw >> L2V;
-    {
-        unsigned char* dst0 = td_smem + tid * 16;
-        for (int i = 0; i < nv; ++i, dst0 += kAsStage) {
+    // ---- issue every copy of this CTA: src = origin(visit) + offset(thread), zero-fill outside the tile -----
+    if (tid < kAsSlots) {
+        const int row = tid / kAsChunks, j = tid - row * kAsChunks;    // this thread's copy slot (same in every stage)
+        const int th1 = g.th - 1 - row, tw1 = (g.tw >> L2V) - 1 - j;   // v0 <= th1 and k0 <= tw1 <=> inside the tile (upper bounds)
+        const long long off = ((long long)row * g.tw + (long long)j * VEC) * (long long)sizeof(T);
+        uint32_t dst = smem_u32(td_smem) + (uint32_t)tid * 16u;
+#pragma unroll 4
+        for (int i = 0; i < nv; ++i, dst += kAsStage) {
             const VisitEntry e = s_visit[i];
-            const T* base = reinterpret_cast<const T*>(e.base);
-            {
-                const int v = (int)e.v0 + row0, k = (int)e.k0 + j0;
-                const bool ok = (unsigned)v < (unsigned)g.th && (unsigned)k < (unsigned)twv;
-                const int off = ok ? v * g.tw + k * VEC : 0;
-                cp_async16(dst0, base + off, ok ? 16 : 0);
-            }
-            if (has1) {
-                const int v = (int)e.v0 + row1, k = (int)e.k0 + j1;
-                const bool ok = (unsigned)v < (unsigned)g.th && (unsigned)k < (unsigned)twv;
-                const int off = ok ? v * g.tw + k * VEC : 0;
-                cp_async16(dst0 + kAsThreads * 16, base + off, ok ? 16 : 0);
-            }
+            // negative (= outside the tile) iff v < 0, v >= th, k < 0 or k >= twv, with v = v0 + row, k = k0 + j
+            const int skip = (e.v0 + row) | (th1 - e.v0) | (e.k0 + j) | (tw1 - e.k0);
+            cp_async16_zfill(dst, e.origin + off, skip);
         }
     }
     cp_async_wait_all();
     __syncthreads();
+    if (tid >= kAsVecThreads) return;
 
     // ---- consume in tile order ------------------------------------------------------------------------
-    const int tx = tid % kAsX, ty = tid / kAsX;
     const unsigned char* mine = td_smem + (ty * kAsChunks + tx) * 16;
     uint4 acc = make_uint4(0, 0, 0, 0);
     {
         for (int i = 0; i < nv; ++i, mine += kAsStage) {
-            const int s = (int)s_visit[i].shift;   // uniform over the CTA
+            const int s = s_shift[i];   // uniform over the CTA
             if constexpr (VEC == 8) {
                 switch (s) {
                     case 0: consume_shifted<T, 0>(acc, mine); break;
@@ -524,19 +527,17 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
     }
 
     // ---- normalise + store --------------------------------------------------------------------------
-    const int x0 = x_lo + tx * VEC, y = y_lo + ty;
-    if (x0 >= g.W || y >= g.H) return;
+    if (!inside) return;
     const long long o = ((long long)plane * g.H + y) * g.W + x0;
-    const long long wo = (long long)y * g.W + x0;
     float4* op = reinterpret_cast<float4*>(out_f32 + o);
 #pragma unroll
     for (int h = 0; h < VEC / 4; ++h) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(weights + wo) + h);
+        const float4 w = wv[h];
         const float a0 = Vec<T>::get(acc, 4 * h + 0), a1 = Vec<T>::get(acc, 4 * h + 1);
         const float a2 = Vec<T>::get(acc, 4 * h + 2), a3 = Vec<T>::get(acc, 4 * h + 3);
         float4 f;   // x_out = where(weights > 1, x_buffer / weights, x_buffer)  -- fp32, correctly rounded divide
         if constexpr (FASTDIV) {
-            const float4 rc = __ldg(reinterpret_cast<const float4*>(rcp_weights + wo) + h);
+            const float4 rc = rv[h];
             f.x = w.x > 1.0f ? div_exact_small_int(a0, w.x, rc.x) : a0;
             f.y = w.y > 1.0f ? div_exact_small_int(a1, w.y, rc.y) : a1;
             f.z = w.z > 1.0f ? div_exact_small_int(a2, w.z, rc.z) : a2;
@@ -550,6 +551,170 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
         op[h] = f;
     }
     if constexpr (WRITE_BUF) stg128(out_buf + o, acc);
+}
+
+// ---------------------------------------------------------------------------
+// Persistent, software-pipelined form of the cp.async blend (TD_FLAG_PIPELINE, opt-in): a CTA walks
+// patches pi = blockIdx.x, += gridDim.x with two stage sets -- the copies of patch n+1
+// are in flight while patch n is consumed, normalised and stored, so DRAM stays busy
+// instead of all CTAs of a wave issuing, waiting and computing in lock step.  Measured on B200
+// (cfg2): 13.9 us vs 10.0 us for one-patch-per-CTA -- 15 resident warps per SM and three
+// barriers per patch lose more than the overlap wins -- so it is not the default.
+// ---------------------------------------------------------------------------
+template <typename T, bool WRITE_BUF, bool FASTDIV>
+__global__ void __launch_bounds__(kAsThreads)
+blend_md_pipe_kernel(const __grid_constant__ BlendParams p, const float* __restrict__ weights, const float* __restrict__ rcp_weights,
+                     float* __restrict__ out_f32, T* __restrict__ out_buf, int nv_cap, int px_count, int py_count, int total_patches) {
+    constexpr int VEC = Vec<T>::kElems;
+    constexpr int L2V = Vec<T>::kLog2;
+    constexpr int BX = kAsX * VEC;
+    extern __shared__ __align__(16) unsigned char td_smem[];
+    __shared__ VisitEntry s_visit[2][kAsMaxVisits];
+    __shared__ int s_shift[2][kAsMaxVisits];
+    const GeomParams& g = p.g;
+    const int tid = threadIdx.x;
+    const int set_bytes = nv_cap * kAsStage;
+
+    // per-thread constants: copy slot (same in every stage) and output vector
+    const int row = tid / kAsChunks, j = tid - row * kAsChunks;
+    const int th1 = g.th - 1 - row, tw1 = (g.tw >> L2V) - 1 - j;
+    const long long off = ((long long)row * g.tw + (long long)j * VEC) * (long long)sizeof(T);
+    const uint32_t smem0 = smem_u32(td_smem);
+    const int tx = tid % kAsX, ty = tid / kAsX;
+    const bool vec_thread = tid < kAsVecThreads;
+
+    struct Patch { int x_lo, y_lo, plane, nv; };
+    auto decode = [&](int pi) {
+        Patch q;
+        const int px = pi % px_count, t = pi / px_count;
+        const int py = t % py_count;
+        q.plane = t / py_count;
+        q.x_lo = px * BX; q.y_lo = py * kAsY;
+        q.nv = g.dbg_no_tiles ? 0 : (int)p.prow_n[py] * (int)p.pcol_n[px];
+        return q;
+    };
+    auto build_table = [&](const Patch& q, int set) {   // thread i prepares visit i
+        if (tid < q.nv) {
+            const int px = q.x_lo / BX, py = q.y_lo / kAsY;
+            const int nc = p.pcol_n[px];
+            const int ri = tid / nc, ci = tid - ri * nc;
+            const int r = (int)p.prow_lo[py] + ri, c = (int)p.pcol_lo[px] + ci;
+            const unsigned t = (unsigned)(r * g.cols + c);
+            const unsigned b = fastdiv(t, p.bs_magic);
+            const int u0 = q.x_lo - (int)g.xs[c];
+            const int v0 = q.y_lo - (int)g.ys[r], k0 = u0 >> L2V;
+            const long long elem = (long long)(t - b * (unsigned)p.tile_bs) * p.tile_stride + (long long)q.plane * g.th * g.tw +
+                                   (long long)v0 * g.tw + (long long)k0 * VEC;
+            VisitEntry e;
+            e.origin = (long long)reinterpret_cast<uintptr_t>(p.batch_ptrs[b]) + elem * (long long)sizeof(T);
+            e.v0 = v0;
+            e.k0 = k0;
+            s_visit[set][tid] = e;
+            s_shift[set][tid] = u0 & (VEC - 1);
+        }
+    };
+    auto issue = [&](const Patch& q, int set) {
+        if (tid < kAsSlots) {
+            uint32_t dst = smem0 + (uint32_t)(set * set_bytes) + (uint32_t)tid * 16u;
+#pragma unroll 4
+            for (int i = 0; i < q.nv; ++i, dst += kAsStage) {
+                const VisitEntry e = s_visit[set][i];
+                const int skip = (e.v0 + row) | (th1 - e.v0) | (e.k0 + j) | (tw1 - e.k0);
+                cp_async16_zfill(dst, e.origin + off, skip);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float4 wv[VEC / 4], rv[VEC / 4], wn[VEC / 4], rn[VEC / 4];
+    auto prefetch_weights = [&](const Patch& q) {
+        const int x0 = q.x_lo + tx * VEC, y = q.y_lo + ty;
+        const bool inside = vec_thread && x0 < g.W && y < g.H;
+        const long long wo = (long long)y * g.W + x0;
+#pragma unroll
+        for (int h = 0; h < VEC / 4; ++h) {
+            wn[h] = inside ? __ldg(reinterpret_cast<const float4*>(weights + wo) + h) : make_float4(1.f, 1.f, 1.f, 1.f);
+            if constexpr (FASTDIV) rn[h] = inside ? __ldg(reinterpret_cast<const float4*>(rcp_weights + wo) + h) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+    };
+
+    int pi = blockIdx.x;
+    if (pi >= total_patches) return;
+    Patch nxt = decode(pi);
+    build_table(nxt, 0);
+    __syncthreads();
+    issue(nxt, 0);
+    prefetch_weights(nxt);
+    int b = 0;
+    while (true) {
+        const Patch cur = nxt;
+#pragma unroll
+        for (int h = 0; h < VEC / 4; ++h) { wv[h] = wn[h]; if constexpr (FASTDIV) rv[h] = rn[h]; }
+        const int next_pi = pi + gridDim.x;
+        const bool has_next = next_pi < total_patches;
+        __syncthreads();                       // everyone is done with set / table 1-b (consumed one iteration ago)
+        if (has_next) { nxt = decode(next_pi); build_table(nxt, 1 - b); }
+        __syncthreads();                       // table 1-b visible
+        if (has_next) { issue(nxt, 1 - b); prefetch_weights(nxt); }
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();                       // set b has landed for every thread
+
+        if (vec_thread) {
+            const unsigned char* mine = td_smem + b * set_bytes + (ty * kAsChunks + tx) * 16;
+            uint4 acc = make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < cur.nv; ++i, mine += kAsStage) {
+                const int s = s_shift[b][i];   // uniform over the CTA
+                if constexpr (VEC == 8) {
+                    switch (s) {
+                        case 0: consume_shifted<T, 0>(acc, mine); break;
+                        case 1: consume_shifted<T, 1>(acc, mine); break;
+                        case 2: consume_shifted<T, 2>(acc, mine); break;
+                        case 3: consume_shifted<T, 3>(acc, mine); break;
+                        case 4: consume_shifted<T, 4>(acc, mine); break;
+                        case 5: consume_shifted<T, 5>(acc, mine); break;
+                        case 6: consume_shifted<T, 6>(acc, mine); break;
+                        default: consume_shifted<T, 7>(acc, mine); break;
+                    }
+                } else {
+                    switch (s) {
+                        case 0: consume_shifted<T, 0>(acc, mine); break;
+                        case 1: consume_shifted<T, 1>(acc, mine); break;
+                        case 2: consume_shifted<T, 2>(acc, mine); break;
+                        default: consume_shifted<T, 3>(acc, mine); break;
+                    }
+                }
+            }
+            const int x0 = cur.x_lo + tx * VEC, y = cur.y_lo + ty;
+            if (x0 < g.W && y < g.H) {
+                const long long o = ((long long)cur.plane * g.H + y) * g.W + x0;
+                float4* op = reinterpret_cast<float4*>(out_f32 + o);
+#pragma unroll
+                for (int h = 0; h < VEC / 4; ++h) {
+                    const float4 w = wv[h];
+                    const float a0 = Vec<T>::get(acc, 4 * h + 0), a1 = Vec<T>::get(acc, 4 * h + 1);
+                    const float a2 = Vec<T>::get(acc, 4 * h + 2), a3 = Vec<T>::get(acc, 4 * h + 3);
+                    float4 f;   // x_out = where(weights > 1, x_buffer / weights, x_buffer)  -- fp32, correctly rounded divide
+                    if constexpr (FASTDIV) {
+                        const float4 rc = rv[h];
+                        f.x = w.x > 1.0f ? div_exact_small_int(a0, w.x, rc.x) : a0;
+                        f.y = w.y > 1.0f ? div_exact_small_int(a1, w.y, rc.y) : a1;
+                        f.z = w.z > 1.0f ? div_exact_small_int(a2, w.z, rc.z) : a2;
+                        f.w = w.w > 1.0f ? div_exact_small_int(a3, w.w, rc.w) : a3;
+                    } else {
+                        f.x = w.x > 1.0f ? __fdiv_rn(a0, w.x) : a0;
+                        f.y = w.y > 1.0f ? __fdiv_rn(a1, w.y) : a1;
+                        f.z = w.z > 1.0f ? __fdiv_rn(a2, w.z) : a2;
+                        f.w = w.w > 1.0f ? __fdiv_rn(a3, w.w) : a3;
+                    }
+                    op[h] = f;
+                }
+                if constexpr (WRITE_BUF) stg128(out_buf + o, acc);
+            }
+        }
+        if (!has_next) break;
+        pi = next_pi;
+        b ^= 1;
+    }
 }
 
 // exhaustive check of div_exact_small_int against the IEEE divide: every 16-bit pattern of T x w in [1, max_w]
@@ -943,45 +1108,82 @@ int try_launch_scatter_tma(GeomParams gp, const void* x, void* tiles, int dtype,
     return check_launch("td_scatter_tiles (tma)");
 }
 
-template <typename T, bool WRITE_BUF>
-int launch_blend_async(const td_grid* g, const BlendParams& bp, const float* weights, const float* rcp_weights, float* out_f32,
-                       void* out_buf, int nv_cap, cudaStream_t st) {
+// tiles touching each patch along one axis: first index and count (both fit a byte: <= 256 tiles per axis)
+void fill_patch_table(const int32_t* org, int n, int extent, int size, int patch, unsigned char* lo_out, unsigned char* n_out) {
+    int idx = 0;
+    for (int lo = 0; lo < size; lo += patch, ++idx) {
+        const int hi = std::min(lo + patch, size) - 1;
+        int first = -1, cnt = 0;
+        for (int i = 0; i < n; ++i)
+            if (org[i] <= hi && org[i] + extent > lo) { if (first < 0) first = i; ++cnt; }
+        lo_out[idx] = (unsigned char)std::max(first, 0);
+        n_out[idx] = (unsigned char)std::min(cnt, 255);
+    }
+}
+
+int sm_count() {
+    static int n = [] {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        return v;
+    }();
+    return n;
+}
+
+template <typename T, bool WRITE_BUF, bool FASTDIV>
+int launch_blend_async_impl(const BlendParams& bp, const float* weights, const float* rcp_weights, float* out_f32, void* out_buf,
+                            int nv_cap, bool pipelined, cudaStream_t st) {
     constexpr int VEC = Vec<T>::kElems;
     constexpr int BX = kAsX * VEC;
-    const int smem = nv_cap * kAsStage;
-    dim3 grid((unsigned)((bp.g.W + BX - 1) / BX), (unsigned)((bp.g.H + kAsY - 1) / kAsY), (unsigned)(bp.g.N * bp.g.C));
-    static int configured_fast = kNoOptInSmem, configured_ieee = kNoOptInSmem;
-    if (rcp_weights != nullptr && sizeof(T) == 2) {
-        int rc = ensure_dyn_smem(blend_md_async_kernel<T, WRITE_BUF, true>, smem, &configured_fast);
+    const int px = (bp.g.W + BX - 1) / BX, py = (bp.g.H + kAsY - 1) / kAsY, planes = bp.g.N * bp.g.C;
+    if (pipelined) {
+        const int smem = 2 * nv_cap * kAsStage;
+        static int configured = kNoOptInSmem;
+        int rc = ensure_dyn_smem(blend_md_pipe_kernel<T, WRITE_BUF, FASTDIV>, smem, &configured);
         if (rc != TD_OK) return rc;
-        blend_md_async_kernel<T, WRITE_BUF, true><<<grid, kAsThreads, smem, st>>>(bp, weights, rcp_weights, out_f32, (T*)out_buf);
+        const long long total = (long long)px * py * planes;
+        const int per_sm = std::max(1, std::min(8, (220 * 1024) / (smem + 3 * 1024)));   // CTAs that fit one SM's shared memory
+        const int grid = (int)std::min<long long>(total, (long long)sm_count() * per_sm);
+        blend_md_pipe_kernel<T, WRITE_BUF, FASTDIV><<<grid, kAsThreads, smem, st>>>(bp, weights, rcp_weights, out_f32, (T*)out_buf, nv_cap,
+                                                                                   px, py, (int)total);
     } else {
-        int rc = ensure_dyn_smem(blend_md_async_kernel<T, WRITE_BUF, false>, smem, &configured_ieee);
+        const int smem = nv_cap * kAsStage;
+        static int configured = kNoOptInSmem;
+        int rc = ensure_dyn_smem(blend_md_async_kernel<T, WRITE_BUF, FASTDIV>, smem, &configured);
         if (rc != TD_OK) return rc;
-        blend_md_async_kernel<T, WRITE_BUF, false><<<grid, kAsThreads, smem, st>>>(bp, weights, nullptr, out_f32, (T*)out_buf);
+        dim3 grid((unsigned)px, (unsigned)py, (unsigned)planes);
+        blend_md_async_kernel<T, WRITE_BUF, FASTDIV><<<grid, kAsThreads, smem, st>>>(bp, weights, rcp_weights, out_f32, (T*)out_buf);
     }
-    int st2 = check_launch("td_blend_multidiffusion (cp.async)");
-    if (st2 != TD_OK) {
-        cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, blend_md_async_kernel<T, WRITE_BUF, false>);
-        td_set_error("td_blend_multidiffusion (cp.async): launch failed: smem=%d nv_cap=%d grid=(%u,%u,%u) static=%zu maxdyn=%d cfg_fast=%d cfg_ieee=%d",
-                     smem, nv_cap, grid.x, grid.y, grid.z, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, configured_fast, configured_ieee);
-    }
-    return st2;
+    return check_launch("td_blend_multidiffusion (cp.async)");
+}
+
+template <typename T, bool WRITE_BUF>
+int launch_blend_async(const td_grid* g, const BlendParams& bp_in, const float* weights, const float* rcp_weights, float* out_f32,
+                       void* out_buf, int nv_cap, bool pipelined, cudaStream_t st) {
+    constexpr int VEC = Vec<T>::kElems;
+    constexpr int BX = kAsX * VEC;
+    BlendParams bp = bp_in;
+    fill_patch_table(g->ys, g->rows, g->tile_h, g->H, kAsY, bp.prow_lo, bp.prow_n);
+    fill_patch_table(g->xs, g->cols, g->tile_w, g->W, BX, bp.pcol_lo, bp.pcol_n);
+    if (rcp_weights != nullptr && sizeof(T) == 2)
+        return launch_blend_async_impl<T, WRITE_BUF, true>(bp, weights, rcp_weights, out_f32, out_buf, nv_cap, pipelined, st);
+    return launch_blend_async_impl<T, WRITE_BUF, false>(bp, weights, nullptr, out_f32, out_buf, nv_cap, pipelined, st);
 }
 
 // returns TD_OK if launched, 1 if the path does not apply (caller falls back), <0 on error
 template <typename T>
 int try_launch_blend_async(const td_grid* g, const BlendParams& bp, const float* weights, const float* rcp_weights, float* out_f32,
-                           void* out_buf, cudaStream_t st) {
+                           void* out_buf, bool pipelined, cudaStream_t st) {
     constexpr int VEC = Vec<T>::kElems;
     constexpr int BX = kAsX * VEC;
     if (bp.g.N * bp.g.C > 65535 || (bp.g.H + kAsY - 1) / kAsY > 65535) return 1;
     if (bp.tile_stride >= (1ll << 31)) return 1;
     const int nv_cap = max_union(g->ys, g->rows, g->tile_h, g->H, kAsY) * max_union(g->xs, g->cols, g->tile_w, g->W, BX);
     if (nv_cap <= 0 || nv_cap > kAsMaxVisits || nv_cap > kAsThreads || nv_cap * kAsStage > 200 * 1024) return 1;
-    return out_buf != nullptr ? launch_blend_async<T, true>(g, bp, weights, rcp_weights, out_f32, out_buf, nv_cap, st)
-                              : launch_blend_async<T, false>(g, bp, weights, rcp_weights, out_f32, out_buf, nv_cap, st);
+    if ((bp.g.H + kAsY - 1) / kAsY > TD_MAX_GRID_DIM || (bp.g.W + BX - 1) / BX > TD_MAX_GRID_DIM) return 1;   // patch tables
+    if (pipelined && 2 * nv_cap * kAsStage > 200 * 1024) pipelined = false;
+    return out_buf != nullptr ? launch_blend_async<T, true>(g, bp, weights, rcp_weights, out_f32, out_buf, nv_cap, pipelined, st)
+                              : launch_blend_async<T, false>(g, bp, weights, rcp_weights, out_f32, out_buf, nv_cap, pipelined, st);
 }
 
 template <typename TIn, typename TAcc, int MODE>
@@ -1104,10 +1306,11 @@ extern "C" int td_blend_multidiffusion(const td_grid* g, const void* const* batc
                 default: rc = try_launch_blend_tma<float>(g, bp, tile_dtype, weights, x_out, x_buffer, s); break;
             }
         } else if (!(flags & TD_FLAG_NO_TMA)) {
+            const bool pipe = (flags & TD_FLAG_PIPELINE) != 0;   // measured slower on B200; opt-in
             switch (tile_dtype) {
-                case TD_F16: rc = try_launch_blend_async<__half>(g, bp, weights, rcp_weights, x_out, x_buffer, s); break;
-                case TD_BF16: rc = try_launch_blend_async<__nv_bfloat16>(g, bp, weights, rcp_weights, x_out, x_buffer, s); break;
-                default: rc = try_launch_blend_async<float>(g, bp, weights, nullptr, x_out, x_buffer, s); break;
+                case TD_F16: rc = try_launch_blend_async<__half>(g, bp, weights, rcp_weights, x_out, x_buffer, pipe, s); break;
+                case TD_BF16: rc = try_launch_blend_async<__nv_bfloat16>(g, bp, weights, rcp_weights, x_out, x_buffer, pipe, s); break;
+                default: rc = try_launch_blend_async<float>(g, bp, weights, nullptr, x_out, x_buffer, pipe, s); break;
             }
         }
         if (rc <= 0) return rc;   // launched or hard error; 1 = not applicable -> register-staged kernel

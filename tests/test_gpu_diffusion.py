@@ -16,7 +16,9 @@ pytestmark = pytest.mark.gpu
 FORCE_GENERIC = 1
 NO_TMA = 2
 TMA = 4
-ALL_PATHS = [0, TMA, NO_TMA, FORCE_GENERIC]   # cp.async-staged (default), TMA-staged, register-staged, scalar kernels
+PIPE = 8
+# cp.async-staged (default), persistent pipelined cp.async, TMA-staged, register-staged, scalar kernels
+ALL_PATHS = [0, PIPE, TMA, NO_TMA, FORCE_GENERIC]
 
 
 @pytest.fixture(scope="module")
@@ -120,7 +122,7 @@ def test_fast_exact_divide_is_ieee_on_its_domain(dn):
 
 
 @pytest.mark.parametrize("dn", ["f16", "bf16"])
-@pytest.mark.parametrize("flags", [0, TMA, NO_TMA])
+@pytest.mark.parametrize("flags", [0, PIPE, TMA, NO_TMA])
 def test_blend_with_reciprocal_weights_matches_reference(eng, golden_dir, dn, flags):
     g = np.load(os.path.join(golden_dir, "blend_small.npz"))
     for name, (N, C, W, H, tw, th, ov, bs) in zip(g["names"], g["cases"]):
