@@ -185,7 +185,7 @@ def workload_config():
 
 # ----------------------------------------------------------------------------- GPU arm
 class Workload:
-    def __init__(self, device, rank, world, nsets):
+    def __init__(self, device, rank, world, nsets, exchange="peer"):
         from multidiffusion_upscaler_for_automatic1111_b200 import _cabi, engine
         from oracle import synth
         self.cabi, self.engine = _cabi, engine
@@ -225,6 +225,14 @@ class Workload:
         self.set_mb = (self.x[0].numel() * 2 + self.tiles_in[0].numel() * 2 + sum(o.numel() for o in self.outs[0]) * 2 +
                        self.x_out[0].numel() * 4 + (self.gathered[0].numel() * 2 if self.gathered else 0)) / 1e6
         self.stream = ctypes.c_void_p(0)
+        self.exchange_mode = exchange if world > 1 else "none"
+        self.peer = None
+        self.step_no = 0
+        if self.exchange_mode == "peer":
+            from multidiffusion_upscaler_for_automatic1111_b200 import parallel
+            self.parallel = parallel
+            self.shard = parallel.TileShard(self.T, rank, world)
+            self.peer = parallel.PeerExchange(self.chunk * self.N * self.C * g.tile_h * g.tile_w * es, device)
         self._tables = []
         for s in range(nsets):
             if world == 1:
@@ -245,7 +253,7 @@ class Workload:
                                        c.TD_F16, self.t0, self.t1, flags, self.stream))
 
     def exchange(self, s):
-        if self.world > 1:
+        if self.exchange_mode == "nccl":
             torch.distributed.all_gather_into_tensor(self.gathered[s], self.outs[s][0])
 
     def blend(self, s, flags=0):
@@ -262,8 +270,45 @@ class Workload:
     def step(self, i):
         s = i % self.nsets
         self.scatter(s)
+        if self.exchange_mode == "peer":
+            # UNet output -> IPC-shared exchange buffer (double-buffered by step parity), publish the step
+            # counter, then ONE kernel waits for the peers and blends while reading their tiles over NVLink
+            self.step_no += 1
+            parity = self.step_no & 1
+            n = (self.t1 - self.t0) * self.N
+            if n > 0:
+                buf = self.peer.local_buffer(parity, torch.float16)[:self.outs[s][0][:n].numel()].view_as(self.outs[s][0][:n])
+                buf.copy_(self.outs[s][0][:n])
+            self.peer.signal()
+            self.parallel.blend_multidiffusion_peer(self.g, self.peer, parity, self.shard, self.N, self.C, self.weights,
+                                                    torch.float16, out=self.x_out[s])
+            return
         self.exchange(s)
         self.blend(s)
+
+
+def vae_kernel_rooflines(dev, stream, peak):
+    """Tiled-VAE streaming kernels at BASELINE cfg4's level-0 decoder tile: [1,128,944,944] fp16 (228 MB)."""
+    from multidiffusion_upscaler_for_automatic1111_b200 import tilevae
+    x = (torch.randn((1, 128, 944, 944), device=dev, dtype=torch.float32) * 0.7).half()
+    y = torch.empty_like(x)
+    gamma = torch.ones(128, device=dev)
+    beta = torch.zeros(128, device=dev)
+    nbytes = x.numel() * 2
+    var, mean = tilevae.get_var_mean(x, 32)
+    reps = 20
+    t_stats = event_time_ms(lambda: [tilevae.get_var_mean(x, 32) for _ in range(reps)], stream) / reps * 1e-3
+    def apply():
+        for _ in range(reps):
+            tilevae.check(tilevae.lib.td_gn_apply(x.data_ptr(), y.data_ptr(), 1, 128, 944 * 944, 0, 32, mean.data_ptr(), var.data_ptr(), 0,
+                                                  gamma.data_ptr(), beta.data_ptr(), 1e-6, 1, tilevae.current_stream_ptr(dev)))
+    apply()
+    t_apply = event_time_ms(apply, stream) / reps * 1e-3
+    return {"workload": "decoder level-0 tile [1,128,944,944] fp16 (BASELINE cfg4: 8192^2 RGB, tile 96)",
+            "gn_stats": {"algorithmic_bytes": nbytes, "avg_launch_us": t_stats * 1e6, "achieved": nbytes / t_stats / 1e9,
+                         "frac": nbytes / t_stats / 1e9 / peak, "note": "two launches (partials + finaliser) per call, 228 MB read > L2"},
+            "gn_apply_silu": {"algorithmic_bytes": 2 * nbytes, "avg_launch_us": t_apply * 1e6, "achieved": 2 * nbytes / t_apply / 1e9,
+                              "frac": 2 * nbytes / t_apply / 1e9 / peak}}
 
 
 def timed_graph_loop(fn_step, steps, stream, chunk=1024):
@@ -302,7 +347,10 @@ def gpu_arm(args, rank, world, local_rank):
         torch.distributed.init_process_group("nccl", device_id=dev)
     peak, peak_src = load_peaks()
     nsets = args.buffer_sets
-    wl = Workload(dev, rank, world, nsets)
+    if world > 1:   # peer exchange is double-buffered by step parity: keep every launch group even
+        args.steps += args.steps & 1
+        args.warmup = max(args.warmup, 4) + (max(args.warmup, 4) & 1)
+    wl = Workload(dev, rank, world, nsets, args.exchange)
     stream = torch.cuda.Stream(dev)
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
 
@@ -312,7 +360,7 @@ def gpu_arm(args, rank, world, local_rank):
 
     with torch.cuda.stream(stream):
         wl.set_stream()
-        for i in range(max(args.warmup, 3)):          # eager warm-up steps
+        for i in range(max(args.warmup, 3) + (max(args.warmup, 3) & 1 if world > 1 else 0)):   # eager warm-up steps
             wl.step(i)
         torch.cuda.synchronize()
         use_graph = not args.no_graph
@@ -363,6 +411,10 @@ def gpu_arm(args, rank, world, local_rank):
                             "avg_launch_us": t_scatter * 1e6, "traffic": load_traffic("scatter")},
                 "note": "back-to-back launches inside a CUDA graph; avg includes the inter-kernel dependency gap",
             }
+            try:
+                roof["vae"] = vae_kernel_rooflines(dev, stream, peak)
+            except Exception as e:   # never let the side measurement break the headline line
+                roof["vae"] = {"error": repr(e)[:200]}
 
         # --- e2e through the public class API with host buffers ----------------------------------------
         e2e = e2e_arm(args, dev, stream, world, rank) if world == 1 else None
@@ -376,8 +428,12 @@ def gpu_arm(args, rank, world, local_rank):
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {**workload_config(), "buffer_sets": nsets, "set_mb": round(wl.set_mb, 1),
                        "cuda_graph": use_graph,
-                       "parallelism": "single GPU" if world == 1 else f"tile-shard over {world} ranks, NCCL all-gather of tile outputs, replicated blend"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (2 if world == 1 else 2),
+                       "parallelism": "single GPU" if world == 1 else (
+                           f"tile-shard over {world} ranks; tile outputs exchanged through IPC-mapped peer buffers and read over "
+                           "NVLink inside the blend kernel (td_peer_signal + td_blend_multidiffusion_peer), replicated deterministic blend"
+                           if wl.exchange_mode == "peer" else
+                           f"tile-shard over {world} ranks, NCCL all-gather of tile outputs, replicated blend")},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (2 if world == 1 else (4 if wl.exchange_mode == "peer" else 2)),
             "roofline": roof,
             "cpu_baseline": {"value": mp_per_s(cpu_dt), "unit": "MP/s", "cores": cpu_threads, "kind": "port",
                              "ms_per_step": cpu_dt * 1e3,
@@ -387,7 +443,13 @@ def gpu_arm(args, rank, world, local_rank):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        sys.stdout.flush()
+        torch.distributed.barrier()
+        if wl.peer is not None:
+            wl.peer.close()
+            torch.distributed.destroy_process_group()
+        else:
+            os._exit(0)   # NCCL communicators captured in CUDA graphs can block a clean teardown; the line is out
 
 
 def load_traffic(kernel: str):
@@ -457,6 +519,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--buffer-sets", type=int, default=8)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N>1: how tile outputs reach the other ranks")
     ap.add_argument("--profile-e2e", action="store_true")
     ap.add_argument("--variants", action="store_true", help="print a table of per-kernel micro-timings to stderr")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")

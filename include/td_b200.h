@@ -209,14 +209,17 @@ int td_ipc_get_handle(const void* dev_ptr, void* handle_out /* TD_IPC_HANDLE_BYT
 int td_ipc_open(const void* handle, void** dev_ptr_out);
 int td_ipc_close(void* dev_ptr);
 /* flag_ptrs: HOST array [world] of DEVICE pointers to each rank's uint32[world] flag array
- * (own array for i == rank, IPC-mapped for peers).  Stores `value` into slot `rank` of every array. */
-int td_peer_signal(void* const* flag_ptrs, int world, int rank, uint32_t value, void* stream);
-/* As td_blend_multidiffusion, preceded in-kernel by: wait until wait_flags[i] >= wait_value for
- * all i < world (acquire, system scope).  wait_flags: this rank's own uint32[world] array. */
+ * (own array for i == rank, IPC-mapped for peers).  Bumps this rank's device-side *step_counter
+ * and stores the new value into slot `rank` of every array (CUDA-graph replayable: no host-side
+ * step number). */
+int td_peer_signal(void* const* flag_ptrs, int world, int rank, uint32_t* step_counter, void* stream);
+/* As td_blend_multidiffusion, preceded in-kernel by: wait until wait_flags[i] >= *wait_value for
+ * all i < world (acquire, system scope).  wait_flags: this rank's own uint32[world] array;
+ * wait_value: this rank's step counter (the one td_peer_signal bumps). */
 int td_blend_multidiffusion_peer(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs,
                                  int N, int C, int tile_dtype, int acc_dtype, const float* weights,
                                  float* x_out, void* x_buffer, const uint32_t* wait_flags, int world,
-                                 uint32_t wait_value, uint32_t flags, void* stream);
+                                 const uint32_t* wait_value, uint32_t flags, void* stream);
 
 #ifdef __cplusplus
 }

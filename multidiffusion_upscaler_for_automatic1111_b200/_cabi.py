@@ -80,9 +80,9 @@ _SIGNATURES = {
     "td_ipc_get_handle": (c_int, [c_void_p, c_void_p]),
     "td_ipc_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "td_ipc_close": (c_int, [c_void_p]),
-    "td_peer_signal": (c_int, [POINTER(c_void_p), c_int, c_int, c_uint32, c_void_p]),
+    "td_peer_signal": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p]),
     "td_blend_multidiffusion_peer": (c_int, [POINTER(TdGrid), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int,
-                                             c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_uint32, c_uint32, c_void_p]),
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_uint32, c_void_p]),
     "td_blend_mixture": (c_int, [POINTER(TdGrid), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
 }

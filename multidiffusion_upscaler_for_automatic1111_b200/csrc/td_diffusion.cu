@@ -47,9 +47,9 @@ struct BlendParams {
     // cp.async kernel: tiles touching patch row / patch col i (first index, count), computed on the host
     unsigned char prow_lo[TD_MAX_GRID_DIM], prow_n[TD_MAX_GRID_DIM];
     unsigned char pcol_lo[TD_MAX_GRID_DIM], pcol_n[TD_MAX_GRID_DIM];
-    const uint32_t* wait_flags;  // tile shard: spin until wait_flags[i] >= wait_value for i < wait_world
+    const uint32_t* wait_flags;  // tile shard: spin until wait_flags[i] >= *wait_value for i < wait_world
     int wait_world;
-    uint32_t wait_value;
+    const uint32_t* wait_value;  // this rank's device-side step counter (bumped by td_peer_signal)
     long long tile_stride;  // N*C*th*tw elements
     const void* batch_ptrs[TD_MAX_BATCH_PTRS];
 };
@@ -190,10 +190,11 @@ blend_grid_vec_kernel(const __grid_constant__ BlendParams p, const float* __rest
     const GeomParams& g = p.g;
     if (p.wait_flags != nullptr) {   // tile shard: peers' tile outputs must be complete before they are read
         if ((int)threadIdx.x < p.wait_world) {
+            const uint32_t want = *p.wait_value;
             uint32_t v;
             do {
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.wait_flags + threadIdx.x) : "memory");
-            } while (v < p.wait_value);
+            } while ((int32_t)(v - want) < 0);
         }
     }
     load_origins(g, s_ys, s_xs);   // (contains the __syncthreads that publishes the wait)
@@ -459,6 +460,16 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
     for (int h = 0; h < VEC / 4; ++h) {
         wv[h] = inside ? __ldg(reinterpret_cast<const float4*>(weights + wo) + h) : make_float4(1.f, 1.f, 1.f, 1.f);
         if constexpr (FASTDIV) rv[h] = inside ? __ldg(reinterpret_cast<const float4*>(rcp_weights + wo) + h) : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+
+    if (p.wait_flags != nullptr && tid >= kAsThreads - 32 && tid - (kAsThreads - 32) < p.wait_world) {
+        // tile shard: the peers' tile outputs must be complete before any copy reads them (last warp spins,
+        // the barrier below publishes it to the CTA)
+        const uint32_t want = *p.wait_value;
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.wait_flags + (tid - (kAsThreads - 32))) : "memory");
+        } while ((int32_t)(v - want) < 0);
     }
 
     // ---- per-visit constants: thread i prepares visit i -------------------------------------------------
@@ -1234,7 +1245,7 @@ int fill_blend(const td_grid* g, const void* const* batch_ptrs, int num_batches,
         bp->batch_ptrs[b] = batch_ptrs[b];
     }
     bp->tile_bs = tile_bs;
-    bp->wait_flags = nullptr; bp->wait_world = 0; bp->wait_value = 0;
+    bp->wait_flags = nullptr; bp->wait_world = 0; bp->wait_value = nullptr;
     bp->bs_magic = magic_u16((unsigned)tile_bs);
     bp->num_batches = num_batches;
     bp->tile_stride = (long long)N * C * g->tile_h * g->tile_w;
@@ -1335,20 +1346,28 @@ extern "C" int td_debug_check_fast_div(int dtype, int max_w, unsigned long long*
 
 extern "C" int td_blend_multidiffusion_peer(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N,
                                             int C, int tile_dtype, int acc_dtype, const float* weights, float* x_out,
-                                            void* x_buffer, const uint32_t* wait_flags, int world, uint32_t wait_value,
+                                            void* x_buffer, const uint32_t* wait_flags, int world, const uint32_t* wait_value,
                                             uint32_t flags, void* stream) {
     BlendParams bp;
     int st = fill_blend(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, acc_dtype, &bp);
     if (st != TD_OK) return st;
     if (weights == nullptr || x_out == nullptr) { td_set_error("td_blend_multidiffusion_peer: null weights / x_out"); return TD_ERR_INVALID_ARG; }
-    if (wait_flags == nullptr || world <= 0 || world > TD_MAX_PEERS) { td_set_error("td_blend_multidiffusion_peer: bad wait table"); return TD_ERR_INVALID_ARG; }
+    if (wait_flags == nullptr || wait_value == nullptr || world <= 0 || world > TD_MAX_PEERS) { td_set_error("td_blend_multidiffusion_peer: bad wait table"); return TD_ERR_INVALID_ARG; }
     if (!blend_vec_ok(bp, tile_dtype, acc_dtype, {weights, x_out, x_buffer})) {
         td_set_error("td_blend_multidiffusion_peer: needs the vector path (same tile / canvas dtype, W and tile_w multiples of the vector, 16-byte aligned buffers)");
         return TD_ERR_UNSUPPORTED;
     }
-    (void)flags;
     bp.wait_flags = wait_flags; bp.wait_world = world; bp.wait_value = wait_value;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!(flags & TD_FLAG_NO_TMA)) {   // cp.async-staged kernel (peer pointers are ordinary global addresses to LDGSTS)
+        int rc;
+        switch (tile_dtype) {
+            case TD_F16: rc = try_launch_blend_async<__half>(g, bp, weights, nullptr, x_out, x_buffer, false, s); break;
+            case TD_BF16: rc = try_launch_blend_async<__nv_bfloat16>(g, bp, weights, nullptr, x_out, x_buffer, false, s); break;
+            default: rc = try_launch_blend_async<float>(g, bp, weights, nullptr, x_out, x_buffer, false, s); break;
+        }
+        if (rc <= 0) return rc;
+    }
     switch (tile_dtype) {
         case TD_F16: return launch_blend_vec<__half, MODE_MD>(bp, weights, nullptr, nullptr, x_out, x_buffer, s);
         case TD_BF16: return launch_blend_vec<__nv_bfloat16, MODE_MD>(bp, weights, nullptr, nullptr, x_out, x_buffer, s);

@@ -14,22 +14,24 @@
 
 namespace {
 
-__global__ void peer_signal_kernel(uint32_t* const* __restrict__ flag_ptrs, int world, int rank, uint32_t value) {
-    const int t = threadIdx.x;
-    if (t >= world) return;
-    __threadfence_system();  // everything this GPU wrote before the signal is visible system-wide first
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_ptrs[t] + rank), "r"(value) : "memory");
-}
-
 struct SignalTable {
     uint32_t* ptrs[TD_MAX_PEERS];
 };
 
-__global__ void peer_signal_kernel_v(const __grid_constant__ SignalTable tbl, int world, int rank, uint32_t value) {
+// One warp: bump this rank's device-side step counter, then publish the new value into slot `rank`
+// of every rank's flag array (release, system scope).  Keeping the counter on the device makes the
+// launch replayable inside a CUDA graph (no host-supplied step number in the parameters).
+__global__ void peer_signal_kernel(const __grid_constant__ SignalTable tbl, int world, int rank, uint32_t* step_counter) {
     const int t = threadIdx.x;
+    uint32_t v = 0;
+    if (t == 0) {
+        v = *step_counter + 1u;
+        *step_counter = v;
+    }
+    v = __shfl_sync(0xffffffffu, v, 0);
     if (t >= world) return;
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(tbl.ptrs[t] + rank), "r"(value) : "memory");
+    __threadfence_system();  // everything this GPU wrote before the signal is visible system-wide first
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(tbl.ptrs[t] + rank), "r"(v) : "memory");
 }
 
 int cuda_fail(const char* what, cudaError_t e) {
@@ -78,8 +80,8 @@ extern "C" int td_ipc_close(void* dev_ptr) {
     return e == cudaSuccess ? TD_OK : cuda_fail("td_ipc_close", e);
 }
 
-extern "C" int td_peer_signal(void* const* flag_ptrs, int world, int rank, uint32_t value, void* stream) {
-    if (flag_ptrs == nullptr || world <= 0 || world > TD_MAX_PEERS || rank < 0 || rank >= world) {
+extern "C" int td_peer_signal(void* const* flag_ptrs, int world, int rank, uint32_t* step_counter, void* stream) {
+    if (flag_ptrs == nullptr || step_counter == nullptr || world <= 0 || world > TD_MAX_PEERS || rank < 0 || rank >= world) {
         td_set_error("td_peer_signal: bad arguments (world=%d rank=%d)", world, rank);
         return TD_ERR_INVALID_ARG;
     }
@@ -88,7 +90,7 @@ extern "C" int td_peer_signal(void* const* flag_ptrs, int world, int rank, uint3
         if (flag_ptrs[i] == nullptr) { td_set_error("td_peer_signal: flag_ptrs[%d] is null", i); return TD_ERR_INVALID_ARG; }
         tbl.ptrs[i] = (uint32_t*)flag_ptrs[i];
     }
-    peer_signal_kernel_v<<<1, 32, 0, (cudaStream_t)stream>>>(tbl, world, rank, value);
+    peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(tbl, world, rank, step_counter);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? TD_OK : cuda_fail("td_peer_signal", e);
 }

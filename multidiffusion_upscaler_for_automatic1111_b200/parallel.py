@@ -119,9 +119,16 @@ class PeerExchange:
     def local_buffer(self, parity: int, dtype: torch.dtype) -> torch.Tensor:
         return self._bufs[parity].tensor(self.device).view(dtype)
 
-    def signal(self, value: int):
+    @property
+    def counter_ptr(self) -> int:
+        """This rank's device-side step counter (lives behind the flag slots of the same allocation)."""
+        return self._flags.ptr + 128
+
+    def signal(self):
+        """Bump the device-side step counter and publish it to every rank (replayable in a CUDA graph)."""
         with torch.cuda.device(self.device):
-            check(lib.td_peer_signal(self._flag_table, self.world, self.rank, int(value), _cabi.current_stream_ptr(self.device)))
+            check(lib.td_peer_signal(self._flag_table, self.world, self.rank, ctypes.c_void_p(self.counter_ptr),
+                                     _cabi.current_stream_ptr(self.device)))
 
     def close(self):
         for p in self._opened:
@@ -132,15 +139,15 @@ class PeerExchange:
 
 
 def blend_multidiffusion_peer(g, exchange: PeerExchange, parity: int, shard: TileShard, N: int, C: int, weights: torch.Tensor,
-                              dtype: torch.dtype, step: int) -> torch.Tensor:
+                              dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Wait for every rank's step counter, then blend reading the peers' chunks over NVLink (one kernel)."""
     dev = exchange.device
     nb = shard.num_chunks
     ptrs = (ctypes.c_void_p * nb)(*exchange.buf_ptrs[parity][:nb])
-    x_out = torch.empty((N, C, g.H, g.W), dtype=torch.float32, device=dev)
+    x_out = out if out is not None else torch.empty((N, C, g.H, g.W), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         check(lib.td_blend_multidiffusion_peer(ctypes.byref(g), ptrs, nb, shard.chunk, N, C, _cabi.dtype_code(dtype),
                                                _cabi.dtype_code(dtype), weights.data_ptr(), x_out.data_ptr(), None,
-                                               ctypes.c_void_p(exchange.flag_ptrs[exchange.rank]), exchange.world, int(step), 0,
-                                               _cabi.current_stream_ptr(dev)))
+                                               ctypes.c_void_p(exchange.flag_ptrs[exchange.rank]), exchange.world,
+                                               ctypes.c_void_p(exchange.counter_ptr), 0, _cabi.current_stream_ptr(dev)))
     return x_out

@@ -239,8 +239,8 @@ class AbstractDiffusion:
             if outs:
                 buf = self._exchange.local_buffer(parity, dt)[:sh.num_local * plane].view(sh.num_local * N, C, g.tile_h, g.tile_w)
                 torch.cat([o.to(dt) for o in outs], dim=0, out=buf)
-            self._exchange.signal(self._shard_step)
-            return parallel.blend_multidiffusion_peer(g, self._exchange, parity, sh, N, C, self.weights, dt, self._shard_step)
+            self._exchange.signal()
+            return parallel.blend_multidiffusion_peer(g, self._exchange, parity, sh, N, C, self.weights, dt)
         local = torch.zeros((sh.chunk * N, C, g.tile_h, g.tile_w), dtype=dt, device=x.device)
         if outs:
             torch.cat(outs, dim=0, out=local[:sh.num_local * N])
@@ -306,10 +306,22 @@ class AbstractDiffusion:
         return self._icond_tiles
 
     def repeat_tensor(self, x: Tensor, n: int) -> Tensor:
-        """Repeat on dim 0 (multidiffusion.py:100-110): expand when B == 1, else tile."""
+        """Repeat on dim 0 (multidiffusion.py:100-110): expand when B == 1, else tile.
+
+        The tiled copy is memoised per source tensor OBJECT (+ version): all T/tile_bs batches of a step
+        repeat the same cond, so the reference's per-batch `repeat` becomes one launch per step."""
         if n == 1:
             return x
         r_dims = x.dim() - 1
         if x.shape[0] == 1:
             return x.expand([n] + [-1] * r_dims)
-        return x.repeat([n] + [1] * r_dims)
+        cache = self.__dict__.setdefault("_repeat_cache", {})
+        key = (id(x), n)
+        hit = cache.get(key)
+        if hit is not None and hit[0] is x and hit[1] == x._version:
+            return hit[2]
+        out = x.repeat([n] + [1] * r_dims)
+        if len(cache) > 16:
+            cache.clear()
+        cache[key] = (x, x._version, out)   # the strong reference keeps id(x) from being recycled
+        return out
