@@ -263,6 +263,20 @@ class Workload:
                                               self.weights.data_ptr(), None if (flags & 0x200) else self.rcp_weights.data_ptr(),
                                               self.x_out[s].data_ptr(), None, flags & 0x1ff, self.stream))
 
+    def blend_mod(self, s, flags=0):
+        """Mixture of Diffusers blend on the same tile outputs (BASELINE config 3's method)."""
+        c = self.cabi
+        if not hasattr(self, "_mod"):
+            from multidiffusion_upscaler_for_automatic1111_b200.tile_utils import utils
+            tw = utils.gaussian_weights_np(self.g.tile_w, self.g.tile_h)
+            w = self.engine.grid_weights(self.g, tw)
+            self._mod = (torch.from_numpy(tw).to(self.dev), torch.from_numpy(self.engine.rescale_factor(w)).to(self.dev),
+                         [torch.empty((self.N, self.C, self.g.H, self.g.W), dtype=torch.float16, device=self.dev) for _ in range(self.nsets)])
+        twt, rs, bufs = self._mod
+        ptrs, nb, tbs = self._tables[s]
+        c.check(c.lib.td_blend_mixture(ctypes.byref(self.g), ptrs, nb, tbs, self.N, self.C, c.TD_F16, c.TD_F16, twt.data_ptr(),
+                                       rs.data_ptr(), bufs[s].data_ptr(), flags, self.stream))
+
     def empty(self, s):
         c = self.cabi
         c.check(c.lib.td_debug_launch_empty(1024, 128, self.stream))
@@ -394,6 +408,8 @@ def gpu_arm(args, rank, world, local_rank):
             if args.variants:
                 tbl = {"empty_1024x128": only(wl.empty)}
                 tbl["blend_async_ieee_div"] = only(lambda s: wl.blend(s, 0x200))
+                wl.blend_mod(0)
+                tbl["blend_mixture_reg"] = only(lambda s: wl.blend_mod(s, 0))
                 for name, fl in (("async", 0), ("pipe", 8), ("tma", 4), ("reg", 2)):
                     tbl[f"blend_{name}"] = only(lambda s, fl=fl: wl.blend(s, fl))
                     tbl[f"blend_{name}_no_tiles"] = only(lambda s, fl=fl: wl.blend(s, fl | 0x100))

@@ -221,6 +221,31 @@ int td_blend_multidiffusion_peer(const td_grid* g, const void* const* batch_ptrs
                                  float* x_out, void* x_buffer, const uint32_t* wait_flags, int world,
                                  const uint32_t* wait_value, uint32_t flags, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ *  DemoFusion extras (tile_methods/demofusion.py); jitter off.
+ * ------------------------------------------------------------------------- */
+
+/* Dilated global views -- demofusion.py:283-308: out[(v*N+n), c, i, j] = src_v[n, c, by_v + i*s, bx_v + j*s],
+ * src_v = x1 where view_second[v] (mixture mode: the blurred latent) else x0.  Host int arrays of n_views. */
+int td_dilated_gather(const void* x0, const void* x1, void* out, int N, int C, int H, int W, int s,
+                      int out_h, int out_w, const int32_t* view_bx, const int32_t* view_by,
+                      const int32_t* view_second, int n_views, int dtype, void* stream);
+
+/* demofusion.py:296-322 fused: strided `x_global[:, :, by::s, bx::s] += view` in view order (each add
+ * rounded through dtype), `/ 2` in mixture mode, and out = x_local*(1-c2) + x_global*c2 (each product and
+ * the sum rounded through dtype).  view_batch_ptrs: HOST array of DEVICE pointers, batch b holding
+ * views [b*views_per_batch, ...) as [.*N, C, out_h, out_w].  Pixels with y >= end_y or x >= end_x get
+ * x_global = 0 (the reference's `end = W - jitter_range` slice bound, demofusion.py:280). */
+int td_demofusion_combine(const void* x_local, const void* const* view_batch_ptrs, int num_batches,
+                          int views_per_batch, int n_views, void* out, int N, int C, int H, int W, int s,
+                          int out_h, int out_w, int end_y, int end_x, int mixture, float c2,
+                          float one_minus_c2, int dtype, void* stream);
+
+/* gaussian_filter -- demofusion.py:173-178: depthwise k x k convolution, zero padding k/2, fp32
+ * accumulate, result rounded to dtype.  kernel_host: k*k fp32 values (already rounded through dtype). */
+int td_depthwise_conv2d(const void* in, void* out, int planes, int H, int W, const float* kernel_host,
+                        int k, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -856,23 +856,40 @@ blend_md_tma_kernel(const __grid_constant__ TmaBlendParams<NB> p, const float* _
 }
 
 // ---------------------------------------------------------------------------
-// Scatter, TMA path: a CTA moves `rb` rows of one (tile, n, c) plane.  One thread
-// issues a single box load of the aligned superset of the tile rows from the canvas;
-// the threads then re-align (two LDS.128 + funnel shift, block-uniform shift) and
-// write the tile batch with aligned 128-bit stores.
+// Scatter, TMA path: a CTA moves one whole (tile, n, c) plane.  One thread issues up to
+// kScBoxes box loads (aligned superset of `rb` tile rows each, one mbarrier per box) from
+// the canvas, all in flight at once; the threads then walk the boxes in order: re-align
+// (two LDS.128 + funnel shift specialised on the block-uniform shift) and write the tile
+// batch with aligned 128-bit stores, so the first stores overlap the later loads.
 // ---------------------------------------------------------------------------
+constexpr int kScBoxes = 8;
+constexpr int kScThreads = 256;
+
 struct TmaScatterParams {
     GeomParams g;
     CUtensorMap src;   // canvas  [N*C][H][W], box [1][rb][tw + VEC]
 };
 
+template <typename T, int S>
+__device__ __forceinline__ void scatter_rows(const unsigned char* box, T* dst, int nvec, int twv, unsigned twv_magic, int pitch) {
+    for (int i = threadIdx.x; i < nvec; i += kScThreads) {
+        const unsigned vi = fastdiv((unsigned)i, twv_magic);
+        const int uv = i - (int)vi * twv;
+        const unsigned char* src = box + (size_t)vi * pitch + (size_t)uv * 16;
+        const uint4 A = lds128(src);
+        uint4 e = A;
+        if constexpr (S != 0) e = Vec<T>::window(A, lds128(src + 16), S);
+        stg128(dst + (long long)i * Vec<T>::kElems, e);
+    }
+}
+
 template <typename T>
-__global__ void __launch_bounds__(128)
-scatter_tma_kernel(const __grid_constant__ TmaScatterParams p, T* __restrict__ tiles, int tile_begin, int rb) {
+__global__ void __launch_bounds__(kScThreads)
+scatter_tma_kernel(const __grid_constant__ TmaScatterParams p, T* __restrict__ tiles, int tile_begin, int rb, int nboxes, int box_bytes) {
     constexpr int VEC = Vec<T>::kElems;
     constexpr int L2V = Vec<T>::kLog2;
     extern __shared__ __align__(128) unsigned char td_smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bars[kScBoxes];
     const GeomParams& g = p.g;
     const unsigned tp = blockIdx.x;
     const unsigned tl = fastdiv(tp, g.nc_magic);
@@ -880,28 +897,43 @@ scatter_tma_kernel(const __grid_constant__ TmaScatterParams p, T* __restrict__ t
     const int t = tile_begin + (int)tl;
     const int r = t / g.cols, c = t - r * g.cols;
     const int xs = (int)g.xs[c], ys = (int)g.ys[r];
-    const int v0 = blockIdx.y * rb;
     const int pitch = (g.tw + VEC) * (int)sizeof(T);
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+        for (int b = 0; b < nboxes; ++b) mbar_init(&bars[b], 1);
         fence_proxy_async();
-        mbar_arrive_expect_tx(&bar, (uint32_t)(pitch * rb));
-        tma_load_3d(td_smem, &p.src, (xs >> L2V) * VEC, ys + v0, plane, &bar);
+        for (int b = 0; b < nboxes; ++b) {
+            mbar_arrive_expect_tx(&bars[b], (uint32_t)(pitch * rb));
+            tma_load_3d(td_smem + (size_t)b * box_bytes, &p.src, (xs >> L2V) * VEC, ys + b * rb, plane, &bars[b]);
+        }
     }
     __syncthreads();
     const int s = xs & (VEC - 1);
     const int twv = g.tw >> L2V;
-    const int nvec = min(rb, g.th - v0) * twv;
-    T* dst = tiles + ((long long)tp * g.th + v0) * g.tw;
-    mbar_wait(&bar, 0);
-    for (int i = threadIdx.x; i < nvec; i += 128) {
-        const unsigned vi = fastdiv((unsigned)i, g.twv_magic);
-        const int uv = i - (int)vi * twv;
-        const unsigned char* src = td_smem + (size_t)vi * pitch + (size_t)uv * 16;
-        const uint4 A = lds128(src);
-        uint4 e = A;
-        if (s != 0) e = Vec<T>::window(A, lds128(src + 16), s);
-        stg128(dst + (long long)i * VEC, e);
+    T* dst = tiles + (long long)tp * g.th * g.tw;
+    for (int b = 0; b < nboxes; ++b) {
+        const int nvec = min(rb, g.th - b * rb) * twv;
+        const unsigned char* box = td_smem + (size_t)b * box_bytes;
+        T* d = dst + (long long)b * rb * g.tw;
+        mbar_wait(&bars[b], 0);
+        if constexpr (VEC == 8) {
+            switch (s) {
+                case 0: scatter_rows<T, 0>(box, d, nvec, twv, g.twv_magic, pitch); break;
+                case 1: scatter_rows<T, 1>(box, d, nvec, twv, g.twv_magic, pitch); break;
+                case 2: scatter_rows<T, 2>(box, d, nvec, twv, g.twv_magic, pitch); break;
+                case 3: scatter_rows<T, 3>(box, d, nvec, twv, g.twv_magic, pitch); break;
+                case 4: scatter_rows<T, 4>(box, d, nvec, twv, g.twv_magic, pitch); break;
+                case 5: scatter_rows<T, 5>(box, d, nvec, twv, g.twv_magic, pitch); break;
+                case 6: scatter_rows<T, 6>(box, d, nvec, twv, g.twv_magic, pitch); break;
+                default: scatter_rows<T, 7>(box, d, nvec, twv, g.twv_magic, pitch); break;
+            }
+        } else {
+            switch (s) {
+                case 0: scatter_rows<T, 0>(box, d, nvec, twv, g.twv_magic, pitch); break;
+                case 1: scatter_rows<T, 1>(box, d, nvec, twv, g.twv_magic, pitch); break;
+                case 2: scatter_rows<T, 2>(box, d, nvec, twv, g.twv_magic, pitch); break;
+                default: scatter_rows<T, 3>(box, d, nvec, twv, g.twv_magic, pitch); break;
+            }
+        }
     }
 }
 
@@ -1101,8 +1133,14 @@ int try_launch_scatter_tma(GeomParams gp, const void* x, void* tiles, int dtype,
     const long long planes_out = (long long)n_tiles * gp.N * gp.C;
     if (planes_out > 0x7fffffffLL) return 1;
     const int pitch = (gp.tw + VEC) * es;
-    int rb = std::min(gp.th, std::max(1, 8192 / pitch));   // ~8 KB per CTA
-    rb = std::min(rb, 256);
+    // whole plane per CTA in <= kScBoxes boxes of rb rows (<= 256 rows per box, ~8 KB each when possible)
+    int rb = std::max(1, std::min(256, 8192 / pitch));
+    rb = std::max(rb, (gp.th + kScBoxes - 1) / kScBoxes);
+    if (rb > 256) return 1;
+    const int nboxes = (gp.th + rb - 1) / rb;
+    const int box_bytes = (rb * pitch + 127) / 128 * 128;
+    const int smem = nboxes * box_bytes;
+    if (smem > 200 * 1024) return 1;
     const int twv = gp.tw / VEC;
     if ((long long)rb * twv >= 65536) return 1;
     gp.twv_magic = magic_u16((unsigned)twv);
@@ -1113,9 +1151,10 @@ int try_launch_scatter_tma(GeomParams gp, const void* x, void* tiles, int dtype,
     int rc = td_encode_tensor_map_3d(&tp.src, x, dtype, (uint64_t)gp.N * gp.C, (uint64_t)gp.H, (uint64_t)gp.W, (uint32_t)rb,
                                      (uint32_t)(gp.tw + VEC));
     if (rc != TD_OK) return rc;
-    dim3 grid((unsigned)planes_out, (unsigned)((gp.th + rb - 1) / rb));
-    if (grid.y > 65535u) return 1;
-    scatter_tma_kernel<T><<<grid, 128, pitch * rb, st>>>(tp, (T*)tiles, tile_begin, rb);
+    static int configured = kNoOptInSmem;
+    rc = ensure_dyn_smem(scatter_tma_kernel<T>, smem, &configured);
+    if (rc != TD_OK) return rc;
+    scatter_tma_kernel<T><<<(unsigned)planes_out, kScThreads, smem, st>>>(tp, (T*)tiles, tile_begin, rb, nboxes, box_bytes);
     return check_launch("td_scatter_tiles (tma)");
 }
 

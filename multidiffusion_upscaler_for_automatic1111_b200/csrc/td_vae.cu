@@ -69,21 +69,25 @@ __device__ __forceinline__ Moments block_merge(Moments m, Moments* s_part) {
     return m;  // valid in thread 0
 }
 
-// per-thread accumulator on data shifted by the first value seen (keeps sumsq small)
+// per-thread accumulator on data shifted by the first value seen (keeps the sum of squares small:
+// no E[x^2] - E[x]^2 cancellation).  3 fp32 ops per element; min / max only when asked for.
+template <bool MINMAX>
 struct Shifted {
-    float k, s, ss, n, lo, hi;
-    __device__ __forceinline__ void init() { n = 0.f; s = 0.f; ss = 0.f; k = 0.f; lo = FLT_MAX; hi = -FLT_MAX; }
+    float k, s, ss, lo, hi;
+    int n;
+    __device__ __forceinline__ void init(float first) { k = first; s = 0.f; ss = 0.f; n = 0; lo = FLT_MAX; hi = -FLT_MAX; }
     __device__ __forceinline__ void add(float x) {
-        if (n == 0.f) k = x;
         const float d = x - k;
-        s += d; ss += d * d; n += 1.f;
-        lo = fminf(lo, x); hi = fmaxf(hi, x);
+        s += d;
+        ss = fmaf(d, d, ss);
+        ++n;
+        if constexpr (MINMAX) { lo = fminf(lo, x); hi = fmaxf(hi, x); }
     }
     __device__ __forceinline__ Moments moments() const {
         Moments m;
-        m.n = n;
-        if (n == 0.f) { m.mean = 0.f; m.m2 = 0.f; m.lo = FLT_MAX; m.hi = -FLT_MAX; return m; }
-        const float md = s / n;
+        m.n = (float)n;
+        if (n == 0) { m.mean = 0.f; m.m2 = 0.f; m.lo = FLT_MAX; m.hi = -FLT_MAX; return m; }
+        const float md = s / m.n;
         m.mean = k + md;
         m.m2 = fmaxf(ss - s * md, 0.f);
         m.lo = lo; m.hi = hi;
@@ -94,7 +98,7 @@ struct Shifted {
 constexpr int kStatThreads = 256;
 
 // One CTA reduces `chunk` elements of one contiguous segment (= one (batch, group)).
-template <typename T, bool VECTOR>
+template <typename T, bool VECTOR, bool MINMAX>
 __global__ void __launch_bounds__(kStatThreads)
 gn_stats_partial_kernel(const T* __restrict__ x, long long seg_len, long long chunk, int chunks_per_seg, float* __restrict__ ws) {
     constexpr int VEC = Vec<T>::kElems;
@@ -102,8 +106,8 @@ gn_stats_partial_kernel(const T* __restrict__ x, long long seg_len, long long ch
     const int seg = blockIdx.y, ck = blockIdx.x;
     const T* base = x + (long long)seg * seg_len;
     const long long lo = (long long)ck * chunk, hi = min(lo + chunk, seg_len);
-    Shifted acc;
-    acc.init();
+    Shifted<MINMAX> acc;
+    acc.init(lo < hi ? Elem<T>::to_f32(base[lo]) : 0.f);   // block-uniform shift: the chunk's first element
     if constexpr (VECTOR) {
         const long long v_lo = lo / VEC, v_hi = hi / VEC;   // chunk and seg_len are multiples of VEC on this path
         for (long long v = v_lo + threadIdx.x; v < v_hi; v += 4 * kStatThreads) {
@@ -149,7 +153,9 @@ __global__ void gn_stats_final_kernel(const float* __restrict__ ws, int chunks_p
     }
 }
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+// SiLU with the SFU approximations (ex2.approx + rcp.approx, ~1e-6 relative): two MUFU per element keep the
+// kernel under its HBM time; the result is rounded to fp16 / bf16 (or compared at 3e-4 in fp32) anyway.
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 // y = act(((x - mean) * invstd) * gamma + beta): one CTA walks part of one (b, c) plane.
 template <typename T, bool VECTOR>
@@ -166,10 +172,10 @@ gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, int C, long long HW,
     const float ga = gamma ? gamma[c] : 1.0f, be = beta ? beta[c] : 0.0f;
     const T* xp = x + (long long)plane * HW;
     T* yp = y + (long long)plane * HW;
+    // ((v - mu) * invstd) * ga + be folded into one FMA per element (per-plane constants)
+    const float A = invstd * ga, Bc = fmaf(-mu, A, be);
     auto f = [&](float v) {
-        float t = (v - mu) * invstd;
-        t = t * ga;
-        t = t + be;
+        const float t = fmaf(v, A, Bc);
         return act ? silu_f(t) : t;
     };
     if constexpr (VECTOR) {
@@ -303,9 +309,11 @@ extern "C" int td_gn_stats(const void* x, int64_t nseg, int64_t seg_len, int dty
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid((unsigned)p.chunks, (unsigned)p.nseg);
     float* ws = (float*)workspace;
+    const bool mm = seg_min != nullptr || seg_max != nullptr;
 #define TD_LAUNCH(T) \
-    if (p.vec) gn_stats_partial_kernel<T, true><<<grid, kStatThreads, 0, s>>>((const T*)x, p.seg_len, p.chunk, p.chunks, ws); \
-    else gn_stats_partial_kernel<T, false><<<grid, kStatThreads, 0, s>>>((const T*)x, p.seg_len, p.chunk, p.chunks, ws);
+    if (p.vec && mm) gn_stats_partial_kernel<T, true, true><<<grid, kStatThreads, 0, s>>>((const T*)x, p.seg_len, p.chunk, p.chunks, ws); \
+    else if (p.vec) gn_stats_partial_kernel<T, true, false><<<grid, kStatThreads, 0, s>>>((const T*)x, p.seg_len, p.chunk, p.chunks, ws); \
+    else gn_stats_partial_kernel<T, false, true><<<grid, kStatThreads, 0, s>>>((const T*)x, p.seg_len, p.chunk, p.chunks, ws);
     if (dtype == TD_F16) { TD_LAUNCH(__half) } else if (dtype == TD_BF16) { TD_LAUNCH(__nv_bfloat16) } else { TD_LAUNCH(float) }
 #undef TD_LAUNCH
     int st = check_launch_v("td_gn_stats (partial)");

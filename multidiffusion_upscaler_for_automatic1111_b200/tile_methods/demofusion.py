@@ -1,0 +1,259 @@
+"""DemoFusion (arXiv 2311.16973) tile method with the reference's surface
+(tile_methods/demofusion.py), on the sm_100a kernels:
+
+    local windows   td_scatter_tiles + td_blend_multidiffusion (count-normalised)     demofusion.py:254-264
+    gaussian blur   td_depthwise_conv2d                                                demofusion.py:173-178
+    renormalise     td_gn_stats (whole-tensor mean / unbiased std) + td_affine_clamp   demofusion.py:269-273
+    global views    td_dilated_gather                                                  demofusion.py:283-308
+    add-back + mix  td_demofusion_combine (one launch)                                 demofusion.py:296-322
+
+Random jitter (demofusion.py:116-134, Python's unseeded `random`) makes the window list non-separable
+and is not on this path yet: `p.random_jitter=True` raises NotImplementedError.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+from .. import engine, host, tilevae
+from .._cabi import check, current_stream_ptr, dtype_code, lib
+from ..tile_utils.utils import BBox, grid_bbox, keep_signature
+from .abstractdiffusion import AbstractDiffusion, CondDict
+
+
+class DemoFusion(AbstractDiffusion):
+
+    def __init__(self, p, *args, **kwargs):
+        super().__init__(p, *args, **kwargs)
+        assert p.sampler_name != 'UniPC', 'Demofusion is not compatible with UniPC!'
+        self.jitter_range = 0
+        self.repeat_3 = False
+
+    # ------------------------------------------------------------------ hooks
+    def hook(self):
+        """demofusion.py:21-35: replaces CFGDenoiser.forward; inner_model.forward is patched per call."""
+        steps_fn = getattr(host._a1111("sd_samplers_common"), "setup_img2img_steps", None) if host._a1111("sd_samplers_common") else None
+        if steps_fn is not None:
+            _, self.t_enc = steps_fn(self.p, None)
+        else:
+            self.t_enc = getattr(self.p, "t_enc", getattr(self.p, "steps", 1) - 1)
+        cfg = self.sampler.model_wrap_cfg
+        cfg.forward_ori = cfg.forward
+        self.sampler_forward = cfg.inner_model.forward
+        cfg.forward = self.forward_one_step
+        if not self.is_kdiff:
+            self.timesteps = self.sampler.get_timesteps(self.p, getattr(self.p, "steps", None))
+
+    @staticmethod
+    def unhook():
+        sd_model = getattr(host.get_shared(), "sd_model", None)
+        if sd_model is not None and hasattr(sd_model, 'apply_model_ori'):
+            sd_model.apply_model = sd_model.apply_model_ori
+            del sd_model.apply_model_ori
+
+    # ------------------------------------------------------------------ views
+    def global_split_bboxes(self) -> List[Tuple[int, int]]:
+        """demofusion.py:87-99: the s*s dilated views (x, y), doubled in mixture mode."""
+        s = self.p.current_scale_num
+        views = [(col, row) for row in range(s) for col in range(s)]
+        return views + views if self.p.mixture else views
+
+    @grid_bbox
+    def get_views(self, overlap: int, tile_bs: int, tile_bs_g: int):
+        """demofusion.py:140-162: local window grid (stride = max(4, window - overlap)) + global view batches."""
+        if getattr(self.p, "random_jitter", False):
+            raise NotImplementedError("DemoFusion random jitter is not on the B200 path yet (non-separable window list)")
+        self.enable_grid_bbox = True
+        self.tile_w = self.tile_h = self.window_size
+        self.overlap = max(0, min(overlap, self.window_size - 4))
+        self.stride = max(4, self.window_size - self.overlap)
+        self.jitter_range = 0
+        # split_bboxes_jitter without jitter is split_bboxes on the clamped overlap (demofusion.py:101-115);
+        # init through td_grid_init with tile == window reproduces rows / cols / origins exactly
+        g = engine.make_grid(self.w, self.h, self.window_size, self.window_size, self.overlap, tile_bs)
+        if g.overlap != self.overlap or g.tile_w != self.window_size or g.tile_h != self.window_size:
+            raise ValueError("window larger than the latent: DemoFusion clamps window_size before get_views")
+        self._grid = g
+        bboxes = [BBox(int(x), int(y), int(w), int(h)) for x, y, w, h in engine.grid_bboxes_xywh(g)]
+        self.num_tiles = len(bboxes)
+        self.num_batches = int(g.num_batches)
+        self.tile_bs = int(g.tile_bs)
+        self.batched_bboxes = [bboxes[i * self.tile_bs:(i + 1) * self.tile_bs] for i in range(self.num_batches)]
+        counts = engine.grid_weights(g)   # how many windows cover each pixel (demofusion.py:261)
+        counts[counts == 0] = 1.0         # :262
+        self._counts = torch.from_numpy(counts).to(host.device())
+        self._rcp_counts = torch.from_numpy(engine.exact_reciprocals(counts)).to(host.device())
+
+        global_bboxes = self.global_split_bboxes()
+        self.global_num_tiles = len(global_bboxes)
+        self.global_num_batches = math.ceil(self.global_num_tiles / tile_bs_g)
+        self.global_tile_bs = math.ceil(len(global_bboxes) / self.global_num_batches)
+        self.global_batched_bboxes = [global_bboxes[i * self.global_tile_bs:(i + 1) * self.global_tile_bs]
+                                      for i in range(self.global_num_batches)]
+
+    def repeat_cond_dict(self, cond_in: CondDict, bboxes, mode) -> CondDict:
+        """demofusion.py:60-84: text / vector cond repeated; spatial icond cropped (local) or dilated (global)."""
+        n_rep = len(bboxes)
+        tcond = self.repeat_tensor(self.get_tcond(cond_in), n_rep)
+        icond = self.get_icond(cond_in)
+        if tuple(icond.shape[2:]) == (self.h, self.w):
+            if mode == 0:
+                icond = torch.cat([icond[b.slicer] for b in bboxes], dim=0)
+            else:
+                s = self.p.current_scale_num
+                icond = torch.cat([icond[:, :, b[1]::s, b[0]::s] for b in bboxes], dim=0)
+        else:
+            icond = self.repeat_tensor(icond, n_rep)
+        vcond = self.get_vcond(cond_in)
+        if vcond is not None:
+            vcond = self.repeat_tensor(vcond, n_rep)
+        return self.make_cond_dict(cond_in, tcond, icond, vcond)
+
+    # ------------------------------------------------------------------ gaussian filter
+    def gaussian_kernel(self, kernel_size=3, sigma=1.0, channels=3):
+        """demofusion.py:164-171 (fp32, host)."""
+        x_coord = torch.arange(kernel_size)
+        g1 = torch.exp(-(x_coord - (kernel_size - 1) / 2) ** 2 / (2 * sigma ** 2))
+        g1 = g1 / g1.sum()
+        g2 = g1[:, None] * g1[None, :]
+        return g2[None, None, :, :].repeat(channels, 1, 1, 1)
+
+    def gaussian_filter(self, latents: Tensor, kernel_size=3, sigma=1.0) -> Tensor:
+        """demofusion.py:173-178 as one depthwise stencil launch (weights rounded to the latent dtype like `.to(dtype)`)."""
+        k2 = self.gaussian_kernel(kernel_size, sigma, 1)[0, 0].to(latents.dtype).float().contiguous().numpy()
+        x = latents.contiguous()
+        out = torch.empty_like(x)
+        n, c, hh, ww = x.shape
+        with torch.cuda.device(x.device):
+            check(lib.td_depthwise_conv2d(x.data_ptr(), out.data_ptr(), n * c, hh, ww, k2.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                          int(kernel_size), dtype_code(x.dtype), current_stream_ptr(x.device)))
+        return out
+
+    def _renormalise(self, g_: Tensor, x_in: Tensor) -> Tensor:
+        """(g - g.mean()) / g.std() * x.std() + x.mean() (demofusion.py:269,273), statistics in fp32, ops rounded in dtype."""
+        dev = x_in.device
+
+        def mean_std(t):
+            var, mean = tilevae._segment_stats(t.contiguous(), 1, t.numel(), unbiased=True)
+            return mean.to(t.dtype).float(), var.sqrt().to(t.dtype).float()   # the reference's 0-dim stats are dtype tensors
+        mean_g, std_g = mean_std(g_)
+        mean_x, std_x = mean_std(x_in)
+        lo = torch.full((1,), -float("inf"), device=dev)
+        hi = torch.full((1,), float("inf"), device=dev)
+        n, c, hh, ww = g_.shape
+        with torch.cuda.device(dev):
+            check(lib.td_affine_clamp(g_.data_ptr(), n * c, 1, hh * ww, dtype_code(g_.dtype), mean_g.data_ptr(), std_g.data_ptr(),
+                                      mean_x.data_ptr(), std_x.data_ptr(), lo.data_ptr(), hi.data_ptr(), current_stream_ptr(dev)))
+        return g_
+
+    # ------------------------------------------------------------------ kernel hijacks
+    @torch.no_grad()
+    @keep_signature
+    def forward_one_step(self, x_in, sigma, **kwarg):
+        """demofusion.py:185-214: skip-residual mix (c1), then the CFG forward with inner_model.forward patched."""
+        p = self.p
+        if self.is_kdiff:
+            x_noisy = p.x + p.noise * sigma[0]
+        else:
+            a = p.sd_model.alphas_cumprod[self.timesteps[self.t_enc - p.current_step]]
+            x_noisy = p.x * torch.sqrt(a) + p.noise * torch.sqrt(1 - a)
+        self.cosine_factor = 0.5 * (1 + torch.cos(torch.pi * torch.tensor(((p.current_step + 1) / (self.t_enc + 1)))))
+        c1 = self.cosine_factor ** p.cosine_scale_1
+        x_in = x_in * (1 - c1) + x_noisy * c1
+        cfg = self.sampler.model_wrap_cfg
+        cfg.inner_model.forward = self.sample_one_step
+        self.repeat_3 = False
+        try:
+            x_out = cfg.forward_ori(x_in, sigma, **kwarg)
+        finally:
+            cfg.inner_model.forward = self.sampler_forward
+        return x_out
+
+    @torch.no_grad()
+    @keep_signature
+    def sample_one_step(self, x_in: Tensor, sigma: Tensor, cond):
+        """demofusion.py:219-324 (jitter off)."""
+        p = self.p
+        sd_model = getattr(p, "sd_model", None) or self._sd_model()
+
+        use_apply_model, self.repeat_3 = self.repeat_3, False   # demofusion.py:241-243
+
+        def repeat_func(x_tile: Tensor, bboxes, mode=0) -> Tensor:
+            n_rep = len(bboxes)
+            if use_apply_model:
+                return sd_model.apply_model(x_tile, sigma.repeat(n_rep), cond=self.repeat_cond_dict(cond, bboxes, mode))
+            s_tile = self.repeat_tensor(sigma, n_rep)
+            c_tile = self.repeat_cond_dict(cond, bboxes, mode) if isinstance(cond, dict) else self.repeat_tensor(cond, n_rep)
+            return self.sampler_forward(x_tile, s_tile, cond=c_tile)
+
+        x = self._check_input(x_in)
+        N, C, H, W = x.shape
+        if (H, W) != (self.h, self.w):
+            raise ValueError(f"latent {(H, W)} does not match the views built for {(self.h, self.w)}")
+        dt, dev = x.dtype, x.device
+        s = int(p.current_scale_num)
+        if self._counts.device != dev:
+            self._counts, self._rcp_counts = self._counts.to(dev), self._rcp_counts.to(dev)
+
+        # ---- local windows: count-normalised blend (buffer / count, both in x.dtype) ----------------------------
+        tiles = self._scatter_all(x)
+        outs = []
+        for batch_id, bboxes in enumerate(self.batched_bboxes):
+            if host.interrupted():
+                return x_in
+            outs.append(repeat_func(self._tile_batch(tiles, batch_id, N), bboxes))
+        rcp = self._rcp_counts if dt in (torch.float16, torch.bfloat16) else None
+        x_local = engine.blend_multidiffusion(self._grid, outs, N, C, self.tile_bs, self._counts, dt, flags=self._blend_flags,
+                                              rcp_weights=rcp).to(dt)
+
+        # ---- blurred + renormalised latent for the global path ------------------------------------------------------
+        c3 = 0.99 * self.cosine_factor ** p.cosine_scale_3 + 1e-2
+        x_in_g = None
+        if p.gaussian_filter:
+            x_in_g = self._renormalise(self.gaussian_filter(x, kernel_size=2 * s - 1, sigma=self.sig * c3), x)
+        elif not p.mixture:
+            raise ValueError("DemoFusion without mixture needs gaussian_filter=True (the reference reads x_in_g unconditionally)")
+
+        # ---- global dilated views ------------------------------------------------------------------------------------
+        end = W   # the reference's slice bound `end = shape[3] - jitter_range` is used on both axes
+        end_y, end_x = min(H, end), end
+        oh, ow = len(range(0, end_y, s)), len(range(0, end_x, s))
+        if any(len(range(b, end_y, s)) != oh for b in range(s)) or any(len(range(b, end_x, s)) != ow for b in range(s)):
+            raise ValueError("latent size must be a multiple of the scale (the reference's torch.cat needs equal views)")
+        half = self.global_num_tiles // 2
+        g_outs, seen = [], 0
+        for bboxes in self.global_batched_bboxes:
+            n = len(bboxes)
+            second = [1 if not (p.mixture and (seen + i) < half) else 0 for i in range(n)]
+            seen += n
+            view = torch.empty((n * N, C, oh, ow), dtype=dt, device=dev)
+            arr = lambda v: (ctypes.c_int32 * n)(*v)
+            with torch.cuda.device(dev):
+                check(lib.td_dilated_gather(x.data_ptr(), x_in_g.data_ptr() if x_in_g is not None else None, view.data_ptr(), N, C, H, W,
+                                            s, oh, ow, arr([b[0] for b in bboxes]), arr([b[1] for b in bboxes]), arr(second), n,
+                                            dtype_code(dt), current_stream_ptr(dev)))
+            g_outs.append(repeat_func(view, bboxes, mode=1).to(dt).contiguous())
+
+        # ---- add-back, /2, and the c2 mix: one launch ------------------------------------------------------------------
+        c2 = float(self.cosine_factor ** p.cosine_scale_2)
+        one_minus_c2 = float(1 - self.cosine_factor ** p.cosine_scale_2)
+        out = torch.empty_like(x_local)
+        ptrs = (ctypes.c_void_p * len(g_outs))(*[t.data_ptr() for t in g_outs])
+        with torch.cuda.device(dev):
+            check(lib.td_demofusion_combine(x_local.data_ptr(), ptrs, len(g_outs), self.global_tile_bs, self.global_num_tiles,
+                                            out.data_ptr(), N, C, H, W, s, oh, ow, end_y, end_x, int(bool(p.mixture)), c2, one_minus_c2,
+                                            dtype_code(dt), current_stream_ptr(dev)))
+        self.x_buffer = out
+        return out
+
+    def get_noise(self, x_in: Tensor, sigma_in: Tensor, cond_in: Dict[str, Tensor], step: int) -> Tensor:
+        """demofusion.py:345-353 (jitter off)."""
+        self.repeat_3 = True
+        self.cosine_factor = 0.5 * (1 + torch.cos(torch.pi * torch.tensor(((self.p.current_step + 1) / (self.t_enc + 1)))))
+        return self.sample_one_step(x_in, sigma_in, cond_in.copy())

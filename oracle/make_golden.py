@@ -60,6 +60,39 @@ VAE_CASES = [  # name, is_decoder, fast_mode, color_fix, H, W, tile_size
 ]
 
 
+DEMO_CASES = [("f32_mixture", "f32", True), ("f32_plain", "f32", False), ("f16_mixture", "f16", True), ("f16_plain", "f16", False)]
+DEMO_CFG = dict(N=2, C=4, H=48, W=64, scale=2, window=24, overlap=12, tile_bs=4, tile_bs_g=2, sig=0.6, cs1=3.0, cs2=1.0, cs3=1.0,
+                current_step=3, t_enc=14)
+
+
+def demo_denoise(x_tile, *_a, **_k):
+    """Deterministic stand-in for the UNet in the DemoFusion fixtures (exact: scale by 0.5)."""
+    return (x_tile.float() * 0.5).to(x_tile.dtype)
+
+
+def demofusion_reference_case(ref, dtype, mixture):
+    """The reference's DemoFusion delegate set up like tileglobal.py does, without a WebUI."""
+    import types
+    from . import demofusion as odf
+    c = DEMO_CFG
+    sys.modules['modules.sd_samplers_common'].setup_img2img_steps = lambda p, steps=None: (p.steps, p.t_enc)
+    x = synth.latent(31, (c["N"], c["C"], c["H"], c["W"]), dtype)
+    p = ref_shim.make_p(c["W"] * 8, c["H"] * 8)
+    p.current_scale_num, p.mixture, p.gaussian_filter, p.random_jitter = c["scale"], mixture, True, False
+    p.cosine_scale_1, p.cosine_scale_2, p.cosine_scale_3 = c["cs1"], c["cs2"], c["cs3"]
+    p.current_step, p.steps, p.t_enc = c["current_step"], 20, c["t_enc"]
+    p.sd_model = types.SimpleNamespace(apply_model=lambda *a, **k: None)
+    sampler = ref_shim.make_kdiff_sampler(lambda xt, sigma, cond=None: demo_denoise(xt))
+    d = ref.demofusion.DemoFusion(p, sampler)
+    d.window_size, d.sig = c["window"], c["sig"]
+    d.get_views(c["overlap"], c["tile_bs"], c["tile_bs_g"])
+    d.sampler_forward = lambda xt, sigma, cond=None: demo_denoise(xt)
+    d.repeat_3 = False
+    d.cosine_factor = odf.cosine_factor(p.current_step, p.t_enc)
+    cond = {"c_crossattn": [torch.zeros(c["N"], 77, 8)], "c_concat": [torch.zeros(c["N"], 5, 1, 1)]}
+    return d, x, cond
+
+
 def vae_case_inputs(is_decoder: bool, H: int, W: int):
     """Tiny ldm-shaped net (4 resolutions, like SD) + platform-stable input for the VAE fixtures."""
     from . import ldm_vae
@@ -229,6 +262,17 @@ def main():
         out[name + "_shape"] = np.array(y.shape, np.int32)
         out[name + "_absmax"] = np.array(float(y.abs().max()), np.float32)
     np.savez_compressed(os.path.join(GOLDEN_DIR, "vae_small.npz"), **out)
+
+    # 8. DemoFusion sample_one_step of the reference (tile_methods/demofusion.py:219-324), jitter off -------
+    out = {}
+    for name, dn, mixture in DEMO_CASES:
+        d, x, cond = demofusion_reference_case(ref, DTYPES[dn], mixture)
+        y = d.sample_one_step(x, torch.ones(x.shape[0]), cond)
+        out[name] = _bits(y)
+        out[name + "_dtype"] = np.array(str(y.dtype))
+        out[name + "_local"] = np.array([(b.x, b.y, b.w, b.h) for bb in d.batched_bboxes for b in bb], np.int32)
+        out[name + "_tile_bs"] = np.array([d.tile_bs, d.global_tile_bs, d.global_num_tiles], np.int32)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "demofusion_small.npz"), **out)
 
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))

@@ -1,0 +1,115 @@
+"""DemoFusion (tile_methods/demofusion.py:219-324, jitter off): oracle vs the reference's fixtures (CPU),
+and the sm_100a class path vs oracle (GPU)."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import DTYPES, bits
+from oracle import demofusion as odf
+from oracle import synth, tiling
+from oracle.make_golden import DEMO_CASES, DEMO_CFG, demo_denoise
+
+
+def _oracle(dtype, mixture):
+    c = DEMO_CFG
+    x = synth.latent(31, (c["N"], c["C"], c["H"], c["W"]), dtype)
+    local, _, _ = tiling.demofusion_views(c["W"], c["H"], c["window"], c["overlap"])
+    nb = -(-len(local) // c["tile_bs"]); tbs = -(-len(local) // nb)
+    lb = [local[i * tbs:(i + 1) * tbs] for i in range(nb)]
+    views = odf.global_views(c["scale"], mixture)
+    gnb = -(-len(views) // c["tile_bs_g"]); gtbs = -(-len(views) // gnb)
+    gb = [views[i * gtbs:(i + 1) * gtbs] for i in range(gnb)]
+    cf = odf.cosine_factor(c["current_step"], c["t_enc"])
+    y = odf.sample_one_step(x, lb, gb, c["scale"], mixture, True, c["sig"], cf, c["cs2"], c["cs3"],
+                            lambda t, b: demo_denoise(t), lambda t, b: demo_denoise(t))
+    return x, y, local, (tbs, gtbs, len(views))
+
+
+@pytest.mark.parametrize("case", DEMO_CASES, ids=[c[0] for c in DEMO_CASES])
+def test_oracle_matches_reference_fixture(golden_dir, case):
+    name, dn, mixture = case
+    g = np.load(os.path.join(golden_dir, "demofusion_small.npz"))
+    _, y, local, sizes = _oracle(DTYPES[dn], mixture)
+    assert np.array_equal(np.array(local, np.int32), g[name + "_local"])
+    assert list(sizes) == list(g[name + "_tile_bs"])
+    assert str(y.dtype) == str(g[name + "_dtype"])
+    want = torch.from_numpy(g[name].view(np.float32 if dn == "f32" else np.float16).copy())
+    tol = 2e-6 if dn == "f32" else 2e-3     # another CPU's conv kernels: round-off only
+    assert (y.float() - want.float()).abs().max().item() <= tol * max(1.0, want.float().abs().max().item())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", DEMO_CASES, ids=[c[0] for c in DEMO_CASES])
+def test_demofusion_class_matches_oracle(case):
+    from multidiffusion_upscaler_for_automatic1111_b200 import DemoFusion
+    name, dn, mixture = case
+    c = DEMO_CFG
+    x, want, local, sizes = _oracle(DTYPES[dn], mixture)
+    p = types.SimpleNamespace(width=c["W"] * 8, height=c["H"] * 8, sampler_name="Euler a", current_scale_num=c["scale"], mixture=mixture,
+                              gaussian_filter=True, random_jitter=False, cosine_scale_1=c["cs1"], cosine_scale_2=c["cs2"],
+                              cosine_scale_3=c["cs3"], current_step=c["current_step"], steps=20, t_enc=c["t_enc"], sd_model=None)
+    calls = []
+
+    def fwd(x_tile, sigma, cond=None):
+        calls.append(tuple(x_tile.shape))
+        assert sigma.shape[0] == x_tile.shape[0] and cond["c_crossattn"][0].shape[0] == x_tile.shape[0]
+        return demo_denoise(x_tile)
+    inner = types.SimpleNamespace(forward=fwd)
+    sampler = types.SimpleNamespace(model_wrap_cfg=types.SimpleNamespace(inner_model=inner, image_cfg_scale=None, forward=None))
+    d = DemoFusion(p, sampler)
+    d.window_size, d.sig = c["window"], c["sig"]
+    d.get_views(c["overlap"], c["tile_bs"], c["tile_bs_g"])
+    assert [(b.x, b.y, b.w, b.h) for bb in d.batched_bboxes for b in bb] == local
+    assert (d.tile_bs, d.global_tile_bs, d.global_num_tiles) == sizes
+    d.sampler_forward = fwd
+    d.cosine_factor = odf.cosine_factor(c["current_step"], c["t_enc"])
+    cond = {"c_crossattn": [torch.zeros(c["N"], 77, 8, device="cuda")], "c_concat": [torch.zeros(c["N"], 5, 1, 1, device="cuda")]}
+    got = d.sample_one_step(x.cuda(), torch.ones(c["N"], device="cuda"), cond)
+    assert got.dtype == DTYPES[dn] and got.shape == want.shape
+    assert len(calls) == d.num_batches + d.global_num_batches
+    tol = 3e-6 if dn == "f32" else 2e-3
+    err = (got.cpu().float() - want.float()).abs().max().item()
+    assert err <= tol * max(1.0, want.float().abs().max().item()), f"{name}: max err {err}"
+
+
+@pytest.mark.gpu
+def test_dilated_gather_and_combine_are_exact():
+    """Index work is bit-exact: gather == strided slices; combine == the eager add-back + mix in fp16."""
+    import ctypes
+    from multidiffusion_upscaler_for_automatic1111_b200._cabi import check, current_stream_ptr, lib
+    N, C, H, W, s = 2, 4, 48, 64, 2
+    x = synth.latent(5, (N, C, H, W), torch.float16).cuda()
+    g_ = synth.latent(6, (N, C, H, W), torch.float16).cuda()
+    views = [(0, 0), (1, 0), (0, 1), (1, 1)] * 2
+    second = [0] * 4 + [1] * 4
+    oh, ow = H // s, W // s
+    out = torch.empty((8 * N, C, oh, ow), dtype=torch.float16, device="cuda")
+    arr = lambda v: (ctypes.c_int32 * len(v))(*v)
+    check(lib.td_dilated_gather(x.data_ptr(), g_.data_ptr(), out.data_ptr(), N, C, H, W, s, oh, ow, arr([v[0] for v in views]),
+                                arr([v[1] for v in views]), arr(second), 8, 0, current_stream_ptr()))
+    want = torch.cat([(g_ if sec else x)[:, :, by::s, bx::s] for (bx, by), sec in zip(views, second)], dim=0)
+    assert torch.equal(out, want)
+    x_local = synth.latent(7, (N, C, H, W), torch.float16).cuda()
+    res = torch.empty_like(x_local)
+    ptrs = (ctypes.c_void_p * 2)(out[:4 * N].data_ptr(), out[4 * N:].data_ptr())
+    c2 = 0.3125
+    check(lib.td_demofusion_combine(x_local.data_ptr(), ptrs, 2, 4, 8, res.data_ptr(), N, C, H, W, s, oh, ow, H, W, 1, c2, 1 - c2, 0,
+                                    current_stream_ptr()))
+    xg = torch.zeros_like(x_local)
+    for idx, (bx, by) in enumerate(views):
+        xg[:, :, by::s, bx::s] += out[idx * N:(idx + 1) * N]
+    want = x_local * (1 - c2) + (xg / 2) * c2
+    assert torch.equal(res, want)
+
+
+def test_random_jitter_is_refused():
+    from multidiffusion_upscaler_for_automatic1111_b200 import DemoFusion
+    p = types.SimpleNamespace(width=512, height=512, sampler_name="Euler a", current_scale_num=2, mixture=True, random_jitter=True)
+    inner = types.SimpleNamespace(forward=None)
+    d = DemoFusion(p, types.SimpleNamespace(model_wrap_cfg=types.SimpleNamespace(inner_model=inner, image_cfg_scale=None)))
+    d.window_size = 32
+    with pytest.raises(NotImplementedError):
+        d.get_views(16, 4, 2)
