@@ -409,7 +409,8 @@ def gpu_arm(args, rank, world, local_rank):
                 tbl = {"empty_1024x128": only(wl.empty)}
                 tbl["blend_async_ieee_div"] = only(lambda s: wl.blend(s, 0x200))
                 wl.blend_mod(0)
-                tbl["blend_mixture_reg"] = only(lambda s: wl.blend_mod(s, 0))
+                tbl["blend_mixture_async"] = only(lambda s: wl.blend_mod(s, 0))
+                tbl["blend_mixture_reg"] = only(lambda s: wl.blend_mod(s, 2))
                 for name, fl in (("async", 0), ("pipe", 8), ("tma", 4), ("reg", 2)):
                     tbl[f"blend_{name}"] = only(lambda s, fl=fl: wl.blend(s, fl))
                     tbl[f"blend_{name}_no_tiles"] = only(lambda s, fl=fl: wl.blend(s, fl | 0x100))

@@ -565,6 +565,146 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
 }
 
 // ---------------------------------------------------------------------------
+// Blend, Mixture of Diffusers, cp.async path: same staging as blend_md_async_kernel; the consume
+// step reproduces mixtureofdiffusers.py:125-126 per element --
+//     w = tile_weights[v, u] * rescale[y, x]      (fp32 product, own rounding)
+//     acc = round_T(float(acc) + float(tile) * w) (separate multiply and add, no FMA)
+// The gaussian tile weights are read with three aligned 128-bit loads per vector (the 4-float shift
+// is uniform over the CTA).  Elements outside the tile are skipped explicitly (see mod_accumulate).
+// ---------------------------------------------------------------------------
+// [jlo, jhi): the elements of this vector that lie inside the tile.  Elements outside must not be touched at all:
+// with gaussian weights the accumulator CAN be -0.0 (a tiny negative sum rounds to -0 in fp16), and -0 + (+0) = +0.
+template <typename T, int O>
+__device__ __forceinline__ void mod_accumulate(float (&acc)[Vec<T>::kElems], const uint4& e, const float4& w0, const float4& w1,
+                                               const float4& w2, const float (&rs)[Vec<T>::kElems], int jlo, int jhi) {
+    constexpr int VEC = Vec<T>::kElems;
+    const float wl[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+    if (jlo == 0 && jhi == VEC) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const float w = __fmul_rn(wl[O + j], rs[j]);
+            const float val = __fmul_rn(Vec<T>::get(e, j), w);
+            acc[j] = round_through<T>(__fadd_rn(acc[j], val));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const float w = __fmul_rn(wl[O + j], rs[j]);
+            const float val = __fmul_rn(Vec<T>::get(e, j), w);
+            const float sum = round_through<T>(__fadd_rn(acc[j], val));
+            acc[j] = (j >= jlo && j < jhi) ? sum : acc[j];
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kAsThreads)
+blend_mod_async_kernel(const __grid_constant__ BlendParams p, const float* __restrict__ tile_weights, const float* __restrict__ rescale,
+                       T* __restrict__ out_buf) {
+    constexpr int VEC = Vec<T>::kElems;
+    constexpr int L2V = Vec<T>::kLog2;
+    constexpr int BX = kAsX * VEC;
+    extern __shared__ __align__(16) unsigned char td_smem[];
+    __shared__ VisitEntry s_visit[kAsMaxVisits];
+    __shared__ int s_shift[kAsMaxVisits];
+    const GeomParams& g = p.g;
+    const int tid = threadIdx.x;
+    const int plane = blockIdx.z;
+    const int x_lo = blockIdx.x * BX, y_lo = blockIdx.y * kAsY;
+    const int r_lo = p.prow_lo[blockIdx.y], c_lo = p.pcol_lo[blockIdx.x];
+    const int nc = p.pcol_n[blockIdx.x];
+    const int nv = (int)p.prow_n[blockIdx.y] * nc;
+
+    const int tx = tid % kAsX, ty = tid / kAsX;
+    const int x0 = x_lo + tx * VEC, y = y_lo + ty;
+    const bool inside = tid < kAsVecThreads && x0 < g.W && y < g.H;
+    float rs[VEC];
+#pragma unroll
+    for (int h = 0; h < VEC / 4; ++h) {
+        const float4 f = inside ? __ldg(reinterpret_cast<const float4*>(rescale + (long long)y * g.W + x0) + h) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rs[4 * h + 0] = f.x; rs[4 * h + 1] = f.y; rs[4 * h + 2] = f.z; rs[4 * h + 3] = f.w;
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)   // 1/0 = inf marks a pixel no tile covers: it receives only zero fill, keep 0 * w finite
+        if (isinf(rs[j])) rs[j] = 0.0f;
+
+    if (tid < nv) {
+        const int ri = tid / nc, ci = tid - ri * nc;
+        const int r = r_lo + ri, c = c_lo + ci;
+        const unsigned t = (unsigned)(r * g.cols + c);
+        const unsigned b = fastdiv(t, p.bs_magic);
+        const int u0 = x_lo - (int)g.xs[c];
+        const int v0 = y_lo - (int)g.ys[r], k0 = u0 >> L2V;
+        const long long elem = (long long)(t - b * (unsigned)p.tile_bs) * p.tile_stride + (long long)plane * g.th * g.tw +
+                               (long long)v0 * g.tw + (long long)k0 * VEC;
+        VisitEntry e;
+        e.origin = (long long)reinterpret_cast<uintptr_t>(p.batch_ptrs[b]) + elem * (long long)sizeof(T);
+        e.v0 = v0;
+        e.k0 = k0;
+        s_visit[tid] = e;
+        s_shift[tid] = u0 & (VEC - 1);
+    }
+    __syncthreads();
+    if (tid < kAsSlots) {
+        const int row = tid / kAsChunks, j = tid - row * kAsChunks;
+        const int th1 = g.th - 1 - row, tw1 = (g.tw >> L2V) - 1 - j;
+        const long long off = ((long long)row * g.tw + (long long)j * VEC) * (long long)sizeof(T);
+        uint32_t dst = smem_u32(td_smem) + (uint32_t)tid * 16u;
+#pragma unroll 4
+        for (int i = 0; i < nv; ++i, dst += kAsStage) {
+            const VisitEntry e = s_visit[i];
+            const int skip = (e.v0 + row) | (th1 - e.v0) | (e.k0 + j) | (tw1 - e.k0);
+            cp_async16_zfill(dst, e.origin + off, skip);
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (!inside) return;
+
+    const unsigned char* mine = td_smem + (ty * kAsChunks + tx) * 16;
+    const int tw4 = g.tw >> 2;   // tile-weight row in float4 chunks (tw % 8 == 0 on this path)
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.0f;
+    for (int i = 0; i < nv; ++i, mine += kAsStage) {
+        const VisitEntry e = s_visit[i];
+        const int s = s_shift[i];
+        const int v = e.v0 + ty;
+        if ((unsigned)v >= (unsigned)g.th) continue;        // this row of the stage is all zero fill: nothing to add
+        const uint4 A = lds128(mine);
+        uint4 ev = A;
+        if (s != 0) ev = Vec<T>::window(A, lds128(mine + 16), s);
+        const int u = e.k0 * VEC + s + tx * VEC;            // tile column of element 0 (may be outside the tile)
+        const int q0 = u >> 2, o = u & 3;                   // o == s & 3: uniform over the CTA
+        const float4* wrow = reinterpret_cast<const float4*>(tile_weights + (long long)v * g.tw);
+        const float4 w0 = __ldg(wrow + min(max(q0, 0), tw4 - 1));
+        const float4 w1 = __ldg(wrow + min(max(q0 + 1, 0), tw4 - 1));
+        const float4 w2 = __ldg(wrow + min(max(q0 + 2, 0), tw4 - 1));
+        const int jlo = max(0, -u), jhi = min(VEC, g.tw - u);
+        if (jhi <= jlo) continue;                           // vector entirely outside this tile
+        switch (o) {
+            case 0: mod_accumulate<T, 0>(acc, ev, w0, w1, w2, rs, jlo, jhi); break;
+            case 1: mod_accumulate<T, 1>(acc, ev, w0, w1, w2, rs, jlo, jhi); break;
+            case 2: mod_accumulate<T, 2>(acc, ev, w0, w1, w2, rs, jlo, jhi); break;
+            default: mod_accumulate<T, 3>(acc, ev, w0, w1, w2, rs, jlo, jhi); break;
+        }
+    }
+
+    const long long o_ = ((long long)plane * g.H + y) * g.W + x0;
+    uint4 pk;
+    if constexpr (sizeof(T) == 2) {
+        uint32_t w32[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+            w32[h] = (uint32_t)Elem<T>::f32_to_bits(acc[2 * h]) | ((uint32_t)Elem<T>::f32_to_bits(acc[2 * h + 1]) << 16);
+        pk = make_uint4(w32[0], w32[1], w32[2], w32[3]);
+    } else {
+        pk = make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]), __float_as_uint(acc[3]));
+    }
+    stg128(out_buf + o_, pk);
+}
+
+// ---------------------------------------------------------------------------
 // Persistent, software-pipelined form of the cp.async blend (TD_FLAG_PIPELINE, opt-in): a CTA walks
 // patches pi = blockIdx.x, += gridDim.x with two stage sets -- the copies of patch n+1
 // are in flight while patch n is consumed, normalised and stored, so DRAM stays busy
@@ -1220,6 +1360,29 @@ int launch_blend_async(const td_grid* g, const BlendParams& bp_in, const float* 
     return launch_blend_async_impl<T, WRITE_BUF, false>(bp, weights, nullptr, out_f32, out_buf, nv_cap, pipelined, st);
 }
 
+// Mixture of Diffusers on the cp.async kernel; 0 launched, 1 not applicable, <0 error
+template <typename T>
+int try_launch_blend_mod_async(const td_grid* g, const BlendParams& bp_in, const float* tile_weights, const float* rescale, void* out_buf,
+                               cudaStream_t st) {
+    constexpr int VEC = Vec<T>::kElems;
+    constexpr int BX = kAsX * VEC;
+    if (bp_in.g.N * bp_in.g.C > 65535 || (bp_in.g.H + kAsY - 1) / kAsY > 65535 || bp_in.tile_stride >= (1ll << 31)) return 1;
+    if ((bp_in.g.H + kAsY - 1) / kAsY > TD_MAX_GRID_DIM || (bp_in.g.W + BX - 1) / BX > TD_MAX_GRID_DIM) return 1;
+    if ((reinterpret_cast<uintptr_t>(tile_weights) & 15u) != 0 || (bp_in.g.tw & 7) != 0) return 1;
+    const int nv_cap = max_union(g->ys, g->rows, g->tile_h, g->H, kAsY) * max_union(g->xs, g->cols, g->tile_w, g->W, BX);
+    if (nv_cap <= 0 || nv_cap > kAsMaxVisits || nv_cap > kAsThreads || nv_cap * kAsStage > 200 * 1024) return 1;
+    BlendParams bp = bp_in;
+    fill_patch_table(g->ys, g->rows, g->tile_h, g->H, kAsY, bp.prow_lo, bp.prow_n);
+    fill_patch_table(g->xs, g->cols, g->tile_w, g->W, BX, bp.pcol_lo, bp.pcol_n);
+    const int smem = nv_cap * kAsStage;
+    static int configured = kNoOptInSmem;
+    int rc = ensure_dyn_smem(blend_mod_async_kernel<T>, smem, &configured);
+    if (rc != TD_OK) return rc;
+    dim3 grid((unsigned)((bp.g.W + BX - 1) / BX), (unsigned)((bp.g.H + kAsY - 1) / kAsY), (unsigned)(bp.g.N * bp.g.C));
+    blend_mod_async_kernel<T><<<grid, kAsThreads, smem, st>>>(bp, tile_weights, rescale, (T*)out_buf);
+    return check_launch("td_blend_mixture (cp.async)");
+}
+
 // returns TD_OK if launched, 1 if the path does not apply (caller falls back), <0 on error
 template <typename T>
 int try_launch_blend_async(const td_grid* g, const BlendParams& bp, const float* weights, const float* rcp_weights, float* out_f32,
@@ -1426,6 +1589,15 @@ extern "C" int td_blend_mixture(const td_grid* g, const void* const* batch_ptrs,
     }
     cudaStream_t s = (cudaStream_t)stream;
     if (!(flags & TD_FLAG_FORCE_GENERIC) && blend_vec_ok(bp, tile_dtype, acc_dtype, {rescale, x_buffer})) {
+        if (!(flags & TD_FLAG_NO_TMA)) {
+            int rc;
+            switch (tile_dtype) {
+                case TD_F16: rc = try_launch_blend_mod_async<__half>(g, bp, tile_weights, rescale, x_buffer, s); break;
+                case TD_BF16: rc = try_launch_blend_mod_async<__nv_bfloat16>(g, bp, tile_weights, rescale, x_buffer, s); break;
+                default: rc = try_launch_blend_mod_async<float>(g, bp, tile_weights, rescale, x_buffer, s); break;
+            }
+            if (rc <= 0) return rc;   // launched or hard error; 1 = not applicable -> register-staged kernel
+        }
         switch (tile_dtype) {
             case TD_F16: return launch_blend_vec<__half, MODE_MOD>(bp, nullptr, tile_weights, rescale, nullptr, x_buffer, s);
             case TD_BF16: return launch_blend_vec<__nv_bfloat16, MODE_MOD>(bp, nullptr, tile_weights, rescale, nullptr, x_buffer, s);
