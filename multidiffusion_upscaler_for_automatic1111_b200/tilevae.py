@@ -251,9 +251,13 @@ class _Norm:
 
 
 class GroupNormParam:
-    """tilevae.py:289-361: collects per-tile statistics of one GroupNorm round and merges them."""
+    """tilevae.py:289-361: collects per-tile statistics of one GroupNorm round and merges them.
 
-    def __init__(self):
+    With `group` set (tile shard over ranks) the pixel-weighted sums are all-reduced, so every rank applies
+    the statistics of ALL tiles (same weights as the reference: p_i = pixels_i / sum(pixels))."""
+
+    def __init__(self, group=None, sharded: bool = False):
+        self.group, self.sharded = group, sharded
         self.var_list = []
         self.mean_list = []
         self.pixel_list = []
@@ -272,8 +276,27 @@ class GroupNormParam:
 
     def summary(self):
         """Pixel-count weighted average of the tile variances and means (tilevae.py:320-335)."""
-        if len(self.var_list) == 0:
+        if len(self.var_list) == 0 and not self.sharded:
             return None
+        if self.sharded:
+            import torch.distributed as dist
+            dev = host.device()
+            if self.var_list:
+                px = torch.tensor(self.pixel_list, dtype=torch.float32, device=self.var_list[0].device).unsqueeze(1)
+                packed = torch.cat([(torch.vstack(self.var_list) * px).sum(0), (torch.vstack(self.mean_list) * px).sum(0), px.sum().view(1)])
+            else:
+                packed = None
+            # ranks may own no tile in this round: agree on the vector length first
+            n = torch.tensor([0 if packed is None else packed.numel()], device=dev)
+            dist.all_reduce(n, op=dist.ReduceOp.MAX, group=self.group)
+            if int(n.item()) == 0:
+                return None
+            if packed is None:
+                packed = torch.zeros(int(n.item()), dtype=torch.float32, device=dev)
+            dist.all_reduce(packed, group=self.group)
+            k = (packed.numel() - 1) // 2
+            var, mean = packed[:k] / packed[-1], packed[k:2 * k] / packed[-1]
+            return _Norm(mean, var, self.layer) if self.layer is not None else _Norm(mean, var, None)
         var = torch.vstack(self.var_list)
         mean = torch.vstack(self.mean_list)
         max_value = max(self.pixel_list)
@@ -300,6 +323,19 @@ class VAEHook:
         self.to_gpu = to_gpu
         self.pad = 11 if is_decoder else 32
         self.verbose = False
+        self._shard_group = None
+        self._shard_world = 1
+        self._shard_rank = 0
+
+    def init_tile_shard(self, group=None):
+        """Shard the VAE tiles over the ranks of `group` (one process per GPU): rank r runs tiles i with
+        i % world == r; GroupNorm statistics (slow mode) are all-reduced per round and the disjoint output
+        regions are combined with one all-reduce of the canvas (x + 0 is exact).  New: the reference is
+        single-device."""
+        import torch.distributed as dist
+        self._shard_group = group
+        self._shard_world = dist.get_world_size(group)
+        self._shard_rank = dist.get_rank(group)
 
     def __call__(self, x):
         original_device = next(self.net.parameters()).device
@@ -383,6 +419,11 @@ class VAEHook:
         in_bboxes, out_bboxes = self.split_tiles(height, width)
 
         # tile crop: straight HBM -> HBM (the reference goes through host RAM)
+        sharded = self._shard_world > 1
+        if sharded:   # this rank's tiles only
+            mine = [i for i in range(len(in_bboxes)) if i % self._shard_world == self._shard_rank]
+            all_out_shape = None
+            in_bboxes, out_bboxes = [in_bboxes[i] for i in mine], [out_bboxes[i] for i in mine]
         tiles: List[Optional[torch.Tensor]] = []
         for b in in_bboxes:
             t = torch.empty((N, z.shape[1], b[3] - b[2], b[1] - b[0]), dtype=dtype, device=device)
@@ -404,7 +445,7 @@ class VAEHook:
         while True:
             if host.interrupted():
                 break
-            group_norm_param = GroupNormParam()
+            group_norm_param = GroupNormParam(self._shard_group, sharded)
             for i in (range(num_tiles) if forward else reversed(range(num_tiles))):
                 if host.interrupted():
                     break
@@ -437,8 +478,9 @@ class VAEHook:
                     tiles[i] = None
                     num_completed += 1
                     if result is None:
-                        result = torch.empty((N, tile.shape[1], height * 8 if is_decoder else height // 8,
-                                              width * 8 if is_decoder else width // 8), dtype=dtype, device=device)
+                        alloc = torch.zeros if sharded else torch.empty   # sharded: the other ranks' regions must read 0
+                        result = alloc((N, tile.shape[1], height * 8 if is_decoder else height // 8,
+                                        width * 8 if is_decoder else width // 8), dtype=dtype, device=device)
                     ob = out_bboxes[i]
                     valid = crop_valid_region(tile.to(dtype).contiguous(), in_bboxes[i], ob, is_decoder)
                     copy_region(valid, result[:, :, ob[2]:ob[3], ob[0]:ob[1]])
@@ -450,14 +492,23 @@ class VAEHook:
                     elif i == 0 and not forward:
                         forward = True
 
-            if num_completed == num_tiles or host.interrupted():
+            if (num_completed == num_tiles and not sharded) or host.interrupted():
                 break
-            norm = group_norm_param.summary()
+            norm = group_norm_param.summary()   # sharded: a collective -- every rank takes part in every round
+            if sharded and norm is None:
+                break
             if norm is not None:
                 for q in task_queues:
                     if len(q) > 0:
                         q.insert(0, ('apply_norm', norm))
 
+        if sharded:
+            import torch.distributed as dist
+            out_c = self.net.conv_out.out_channels
+            if result is None:
+                result = torch.zeros((N, out_c, height * 8 if is_decoder else height // 8, width * 8 if is_decoder else width // 8),
+                                     dtype=dtype, device=device)
+            dist.all_reduce(result, group=self._shard_group)   # disjoint regions + zeros: exact
         if result is None or num_completed != num_tiles:
             raise RuntimeError("[Tiled VAE]: interrupted before any tile finished")
         if torch.isnan(result).any():

@@ -109,6 +109,24 @@ def _gpu_worker(rank, world, port, result_dir):
                 if d._exchange is not None:
                     dist.barrier()
                     d._exchange.close()
+        # tiled VAE, tiles sharded over the ranks: fast mode (no collective until the canvas all-reduce) and slow mode
+        # (GroupNorm statistics all-reduced every round) must both reproduce the single-process oracle on every rank
+        from multidiffusion_upscaler_for_automatic1111_b200 import tilevae
+        from oracle import vae as ovae
+        from oracle.make_golden import vae_case_inputs
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        for fast in (True, False):
+            net, z = vae_case_inputs(True, 40, 52)
+            with torch.no_grad():
+                want = ovae.vae_hook_call(net, z, 16, True, fast, False)
+            net_gpu, _ = vae_case_inputs(True, 40, 52)
+            hook = tilevae.VAEHook(net_gpu.cuda(), 16, True, fast_decoder=fast, fast_encoder=fast, color_fix=False)
+            hook.init_tile_shard(None)
+            with torch.no_grad():
+                got = hook(z.cuda())
+            err = (got.cpu() - want).abs().max().item()
+            assert err <= 3e-4 * max(1.0, want.abs().max().item()), f"rank {rank} sharded VAE fast={fast}: err {err}"
         open(os.path.join(result_dir, f"ok{rank}"), "w").close()
     finally:
         dist.destroy_process_group()
