@@ -13,7 +13,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libtd_b200.so")
+LIB_PATH = os.environ.get("TD_B200_LIB") or os.path.join(_PKG_DIR, "libtd_b200.so")   # env override: tuning builds only
 
 TD_OK = 0
 TD_ERR_INVALID_ARG, TD_ERR_UNSUPPORTED, TD_ERR_CUDA, TD_ERR_CAPACITY = -1, -2, -3, -4
@@ -22,6 +22,7 @@ TD_FLAG_FORCE_GENERIC = 1
 TD_FLAG_NO_TMA = 2
 TD_FLAG_TMA = 4
 TD_FLAG_PIPELINE = 8
+TD_FLAG_PEER_ASYNC = 16
 TD_FLAG_DBG_NO_TILES = 0x100
 TD_MAX_GRID_DIM = 256
 TD_MAX_BATCH_PTRS = 128

@@ -369,11 +369,14 @@ blend_grid_vec_kernel(const __grid_constant__ BlendParams p, const float* __rest
 // td_debug_check_fast_div / tests).
 // ---------------------------------------------------------------------------
 constexpr int kAsX = 8;                          // vectors per patch row
-constexpr int kAsY = 16;                         // patch rows
+#ifndef TD_AS_ROWS
+#define TD_AS_ROWS 16                            // tuning knob (build.py --as-rows): 8 / 16 / 32 measured, 16 kept
+#endif
+constexpr int kAsY = TD_AS_ROWS;                 // patch rows
 constexpr int kAsVecThreads = kAsX * kAsY;       // 128 threads own one output vector each
 constexpr int kAsChunks = kAsX + 1;              // staged chunks per row (aligned superset)
 constexpr int kAsSlots = kAsY * kAsChunks;       // 144 copy slots per tile visit: one per thread
-constexpr int kAsThreads = 160;                  // 5 warps: 144 copy threads (the last half warp idles)
+constexpr int kAsThreads = (kAsSlots + 31) / 32 * 32;   // 160 = 5 warps: 144 copy threads (the last half warp idles)
 constexpr int kAsStage = kAsSlots * 16;          // 2304 bytes per tile visit
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
@@ -1561,7 +1564,7 @@ extern "C" int td_blend_multidiffusion_peer(const td_grid* g, const void* const*
     }
     bp.wait_flags = wait_flags; bp.wait_world = world; bp.wait_value = wait_value;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!(flags & TD_FLAG_NO_TMA)) {   // cp.async-staged kernel (peer pointers are ordinary global addresses to LDGSTS)
+    if (flags & TD_FLAG_PEER_ASYNC) {   // cp.async-staged kernel over peer pointers: measured slower over NVLink than direct loads (opt-in)
         int rc;
         switch (tile_dtype) {
             case TD_F16: rc = try_launch_blend_async<__half>(g, bp, weights, nullptr, x_out, x_buffer, false, s); break;

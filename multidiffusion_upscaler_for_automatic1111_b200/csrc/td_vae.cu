@@ -80,7 +80,6 @@ struct Shifted {
         const float d = x - k;
         s += d;
         ss = fmaf(d, d, ss);
-        ++n;
         if constexpr (MINMAX) { lo = fminf(lo, x); hi = fmaxf(hi, x); }
     }
     __device__ __forceinline__ Moments moments() const {
@@ -120,10 +119,11 @@ gn_stats_partial_kernel(const T* __restrict__ x, long long seg_len, long long ch
                 if (v + (long long)u * kStatThreads < v_hi) {
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) acc.add(Vec<T>::get(q[u], j));
+                    acc.n += VEC;   // counted per vector, not per element
                 }
         }
     } else {
-        for (long long i = lo + threadIdx.x; i < hi; i += kStatThreads) acc.add(Elem<T>::to_f32(base[i]));
+        for (long long i = lo + threadIdx.x; i < hi; i += kStatThreads) { acc.add(Elem<T>::to_f32(base[i])); acc.n += 1; }
     }
     const Moments m = block_merge(acc.moments(), s_part);
     if (threadIdx.x == 0) {
