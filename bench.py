@@ -405,6 +405,8 @@ def gpu_arm(args, rank, world, local_rank):
                 return event_time_ms(r, stream) / reps * 1e-3
             t_blend = only(wl.blend)
             t_scatter = only(wl.scatter)
+            t_blend_ser = only(lambda s: wl.blend(s, 32))      # TD_FLAG_NO_PDL: fully serialised launches
+            t_scatter_ser = only(lambda s: wl.scatter(s, 32))
             if args.variants:
                 tbl = {"empty_1024x128": only(wl.empty)}
                 tbl["blend_async_ieee_div"] = only(lambda s: wl.blend(s, 0x200))
@@ -423,10 +425,14 @@ def gpu_arm(args, rank, world, local_rank):
                 "achieved": wl.bytes_blend / t_blend / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": wl.bytes_blend / t_blend / 1e9 / peak, "traffic": load_traffic("blend"),
                 "peak_source": peak_src, "algorithmic_bytes": wl.bytes_blend, "avg_launch_us": t_blend * 1e6,
+                "avg_launch_us_no_pdl": t_blend_ser * 1e6,
                 "scatter": {"kernel": "scatter_tma_kernel<half> (td_scatter_tiles, TMA-staged)", "achieved": wl.bytes_scatter / t_scatter / 1e9,
                             "frac": wl.bytes_scatter / t_scatter / 1e9 / peak, "algorithmic_bytes": wl.bytes_scatter,
-                            "avg_launch_us": t_scatter * 1e6, "traffic": load_traffic("scatter")},
-                "note": "back-to-back launches inside a CUDA graph; avg includes the inter-kernel dependency gap",
+                            "avg_launch_us": t_scatter * 1e6, "avg_launch_us_no_pdl": t_scatter_ser * 1e6,
+                            "traffic": load_traffic("scatter")},
+                "note": "back-to-back launches inside a CUDA graph, programmatic dependent launch on (the next launch becomes "
+                        "resident while this one drains; every global access still waits for completion); avg includes the "
+                        "inter-kernel gap; *_no_pdl = same loop with plain stream serialisation",
             }
             try:
                 roof["vae"] = vae_kernel_rooflines(dev, stream, peak)

@@ -355,9 +355,9 @@ blend_grid_vec_kernel(const __grid_constant__ BlendParams p, const float* __rest
 // ---------------------------------------------------------------------------
 // Blend + normalise, MultiDiffusion, cp.async path (the default when it applies).
 //
-// A CTA owns a 16-row x 8-vector patch of one canvas plane.  For every tile touching the
+// A CTA owns a 8-row x 8-vector (TD_AS_ROWS) patch of one canvas plane.  For every tile touching the
 // patch (ascending tile index) the threads copy the aligned superset of the intersection
-// (9 chunks x 16 rows) global -> shared with 16-byte cp.async; chunks outside the tile
+// (9 chunks x 8 rows) global -> shared with 16-byte cp.async; chunks outside the tile
 // use src-size 0, i.e. the copy itself zero-fills them (exact: the accumulator starts at
 // +0 and can never become -0).  Every copy of the CTA is in flight before the first wait:
 // memory-level parallelism without staging registers and without the per-box cost of TMA.
@@ -370,14 +370,14 @@ blend_grid_vec_kernel(const __grid_constant__ BlendParams p, const float* __rest
 // ---------------------------------------------------------------------------
 constexpr int kAsX = 8;                          // vectors per patch row
 #ifndef TD_AS_ROWS
-#define TD_AS_ROWS 16                            // tuning knob (build.py --as-rows): 8 / 16 / 32 measured, 16 kept
+#define TD_AS_ROWS 8                             // tuning knob (-DTD_AS_ROWS=): 8 / 16 / 32 measured 8.89 / 9.18 / 10.7 us (cfg2), 8 kept
 #endif
 constexpr int kAsY = TD_AS_ROWS;                 // patch rows
-constexpr int kAsVecThreads = kAsX * kAsY;       // 128 threads own one output vector each
+constexpr int kAsVecThreads = kAsX * kAsY;       // 64 threads own one output vector each
 constexpr int kAsChunks = kAsX + 1;              // staged chunks per row (aligned superset)
-constexpr int kAsSlots = kAsY * kAsChunks;       // 144 copy slots per tile visit: one per thread
-constexpr int kAsThreads = (kAsSlots + 31) / 32 * 32;   // 160 = 5 warps: 144 copy threads (the last half warp idles)
-constexpr int kAsStage = kAsSlots * 16;          // 2304 bytes per tile visit
+constexpr int kAsSlots = kAsY * kAsChunks;       // 72 copy slots per tile visit: one per thread
+constexpr int kAsThreads = (kAsSlots + 31) / 32 * 32;   // 96 = 3 warps: 72 copy threads
+constexpr int kAsStage = kAsSlots * 16;          // 1152 bytes per tile visit
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes) : "memory");
@@ -419,13 +419,12 @@ __device__ __forceinline__ float div_exact_small_int(float a, float w, float rcp
     return __uint_as_float((__float_as_uint(q2) & 0x7fffffffu) | (__float_as_uint(a) & 0x80000000u));
 }
 
-// uniform origin search straight from the (constant-bank) kernel parameters
-__device__ __forceinline__ int last_le_c(const short* a, int n, int val, float inv_d) {
-    int i = min(n - 1, max(0, (int)((float)val * inv_d)));
-    while (i + 1 < n && (int)a[i + 1] <= val) ++i;
-    while (i >= 0 && (int)a[i] > val) --i;
-    return i;
-}
+// Programmatic dependent launch (sm_90+): a kernel launched with the stream-serialisation attribute may become
+// resident while its predecessor in the stream drains.  pdl_wait() blocks until the predecessor has completed and
+// its memory is visible -- it precedes every global read or write below, so stream order is kept; what overlaps
+// is the launch itself, the parameter fetch and the index arithmetic.  Both are no-ops for an ordinary launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 struct __align__(16) VisitEntry {   // per tile visit of a CTA, computed once by one thread
     long long origin;               // byte address of tile element (v0, k0*VEC) of this plane (may lie before the tile)
@@ -447,6 +446,7 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
     const int tid = threadIdx.x;
     const int plane = blockIdx.z;
     const int x_lo = blockIdx.x * BX, y_lo = blockIdx.y * kAsY;
+    pdl_launch_dependents();
 
     // tiles touching this patch: host-computed per patch row / col (uniform constant-bank reads)
     const int r_lo = p.prow_lo[blockIdx.y], c_lo = p.pcol_lo[blockIdx.x];
@@ -459,6 +459,7 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
     const bool inside = tid < kAsVecThreads && x0 < g.W && y < g.H;
     const long long wo = (long long)y * g.W + x0;
     float4 wv[VEC / 4], rv[VEC / 4];
+    pdl_wait();
 #pragma unroll
     for (int h = 0; h < VEC / 4; ++h) {
         wv[h] = inside ? __ldg(reinterpret_cast<const float4*>(weights + wo) + h) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -617,11 +618,13 @@ blend_mod_async_kernel(const __grid_constant__ BlendParams p, const float* __res
     const int r_lo = p.prow_lo[blockIdx.y], c_lo = p.pcol_lo[blockIdx.x];
     const int nc = p.pcol_n[blockIdx.x];
     const int nv = (int)p.prow_n[blockIdx.y] * nc;
+    pdl_launch_dependents();
 
     const int tx = tid % kAsX, ty = tid / kAsX;
     const int x0 = x_lo + tx * VEC, y = y_lo + ty;
     const bool inside = tid < kAsVecThreads && x0 < g.W && y < g.H;
     float rs[VEC];
+    pdl_wait();
 #pragma unroll
     for (int h = 0; h < VEC / 4; ++h) {
         const float4 f = inside ? __ldg(reinterpret_cast<const float4*>(rescale + (long long)y * g.W + x0) + h) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1041,9 +1044,13 @@ scatter_tma_kernel(const __grid_constant__ TmaScatterParams p, T* __restrict__ t
     const int r = t / g.cols, c = t - r * g.cols;
     const int xs = (int)g.xs[c], ys = (int)g.ys[r];
     const int pitch = (g.tw + VEC) * (int)sizeof(T);
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         for (int b = 0; b < nboxes; ++b) mbar_init(&bars[b], 1);
         fence_proxy_async();
+    }
+    pdl_wait();   // x is read (TMA) and tiles are written only after the previous kernel in the stream has completed
+    if (threadIdx.x == 0) {
         for (int b = 0; b < nboxes; ++b) {
             mbar_arrive_expect_tx(&bars[b], (uint32_t)(pitch * rb));
             tma_load_3d(td_smem + (size_t)b * box_bytes, &p.src, (xs >> L2V) * VEC, ys + b * rb, plane, &bars[b]);
@@ -1155,8 +1162,31 @@ int fill_geom(const td_grid* g, int N, int C, GeomParams* o) {
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Launch with the programmatic-stream-serialisation attribute (see pdl_wait): inside a stream or a captured graph
+// the kernel may start while its predecessor drains.  tl_pdl is set per C-ABI call from TD_FLAG_NO_PDL.
+thread_local bool tl_pdl = true;
+thread_local cudaError_t tl_launch_err = cudaSuccess;
+
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr = {};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = tl_pdl ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess) tl_launch_err = e;   // reported by check_launch
+}
+
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = tl_launch_err;
+    tl_launch_err = cudaSuccess;
     if (e != cudaSuccess) {
         td_set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
         return TD_ERR_CUDA;
@@ -1297,7 +1327,7 @@ int try_launch_scatter_tma(GeomParams gp, const void* x, void* tiles, int dtype,
     static int configured = kNoOptInSmem;
     rc = ensure_dyn_smem(scatter_tma_kernel<T>, smem, &configured);
     if (rc != TD_OK) return rc;
-    scatter_tma_kernel<T><<<(unsigned)planes_out, kScThreads, smem, st>>>(tp, (T*)tiles, tile_begin, rb, nboxes, box_bytes);
+    launch_pdl(scatter_tma_kernel<T>, dim3((unsigned)planes_out), dim3(kScThreads), (size_t)smem, st, tp, (T*)tiles, tile_begin, rb, nboxes, box_bytes);
     return check_launch("td_scatter_tiles (tma)");
 }
 
@@ -1345,7 +1375,7 @@ int launch_blend_async_impl(const BlendParams& bp, const float* weights, const f
         int rc = ensure_dyn_smem(blend_md_async_kernel<T, WRITE_BUF, FASTDIV>, smem, &configured);
         if (rc != TD_OK) return rc;
         dim3 grid((unsigned)px, (unsigned)py, (unsigned)planes);
-        blend_md_async_kernel<T, WRITE_BUF, FASTDIV><<<grid, kAsThreads, smem, st>>>(bp, weights, rcp_weights, out_f32, (T*)out_buf);
+        launch_pdl(blend_md_async_kernel<T, WRITE_BUF, FASTDIV>, grid, dim3(kAsThreads), (size_t)smem, st, bp, weights, rcp_weights, out_f32, (T*)out_buf);
     }
     return check_launch("td_blend_multidiffusion (cp.async)");
 }
@@ -1382,7 +1412,7 @@ int try_launch_blend_mod_async(const td_grid* g, const BlendParams& bp_in, const
     int rc = ensure_dyn_smem(blend_mod_async_kernel<T>, smem, &configured);
     if (rc != TD_OK) return rc;
     dim3 grid((unsigned)((bp.g.W + BX - 1) / BX), (unsigned)((bp.g.H + kAsY - 1) / kAsY), (unsigned)(bp.g.N * bp.g.C));
-    blend_mod_async_kernel<T><<<grid, kAsThreads, smem, st>>>(bp, tile_weights, rescale, (T*)out_buf);
+    launch_pdl(blend_mod_async_kernel<T>, grid, dim3(kAsThreads), (size_t)smem, st, bp, tile_weights, rescale, (T*)out_buf);
     return check_launch("td_blend_mixture (cp.async)");
 }
 
@@ -1492,6 +1522,7 @@ extern "C" int td_scatter_tiles(const td_grid* g, const void* x, void* tiles, in
     const int es = td_dtype_size(dtype);
     if (es == 0) { td_set_error("td_scatter_tiles: unknown dtype %d", dtype); return TD_ERR_INVALID_ARG; }
     const int vec = 16 / es;
+    tl_pdl = !(flags & TD_FLAG_NO_PDL);
     const bool vec_ok = !(flags & TD_FLAG_FORCE_GENERIC) && gp.W % vec == 0 && gp.tw % vec == 0 && aligned16(x) && aligned16(tiles);
     cudaStream_t s = (cudaStream_t)stream;
     if (vec_ok && !(flags & TD_FLAG_NO_TMA)) {
@@ -1508,6 +1539,7 @@ extern "C" int td_blend_multidiffusion(const td_grid* g, const void* const* batc
                                        int C, int tile_dtype, int acc_dtype, const float* weights, const float* rcp_weights,
                                        float* x_out, void* x_buffer, uint32_t flags, void* stream) {
     BlendParams bp;
+    tl_pdl = !(flags & TD_FLAG_NO_PDL);
     int st = fill_blend(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, acc_dtype, &bp);
     if (st != TD_OK) return st;
     if (weights == nullptr || x_out == nullptr) { td_set_error("td_blend_multidiffusion: null weights / x_out"); return TD_ERR_INVALID_ARG; }
@@ -1554,6 +1586,7 @@ extern "C" int td_blend_multidiffusion_peer(const td_grid* g, const void* const*
                                             void* x_buffer, const uint32_t* wait_flags, int world, const uint32_t* wait_value,
                                             uint32_t flags, void* stream) {
     BlendParams bp;
+    tl_pdl = !(flags & TD_FLAG_NO_PDL);
     int st = fill_blend(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, acc_dtype, &bp);
     if (st != TD_OK) return st;
     if (weights == nullptr || x_out == nullptr) { td_set_error("td_blend_multidiffusion_peer: null weights / x_out"); return TD_ERR_INVALID_ARG; }
@@ -1584,6 +1617,7 @@ extern "C" int td_blend_mixture(const td_grid* g, const void* const* batch_ptrs,
                                 int tile_dtype, int acc_dtype, const float* tile_weights, const float* rescale,
                                 void* x_buffer, uint32_t flags, void* stream) {
     BlendParams bp;
+    tl_pdl = !(flags & TD_FLAG_NO_PDL);
     int st = fill_blend(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, acc_dtype, &bp);
     if (st != TD_OK) return st;
     if (tile_weights == nullptr || rescale == nullptr || x_buffer == nullptr) {

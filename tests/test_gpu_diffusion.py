@@ -17,8 +17,9 @@ FORCE_GENERIC = 1
 NO_TMA = 2
 TMA = 4
 PIPE = 8
+NO_PDL = 32
 # cp.async-staged (default), persistent pipelined cp.async, TMA-staged, register-staged, scalar kernels
-ALL_PATHS = [0, PIPE, TMA, NO_TMA, FORCE_GENERIC]
+ALL_PATHS = [0, NO_PDL, PIPE, TMA, NO_TMA, FORCE_GENERIC]
 
 
 @pytest.fixture(scope="module")
@@ -328,3 +329,47 @@ def test_bad_arguments_return_status_not_crash(eng):
         eng.blend_multidiffusion(g, [tiles[:-2]], 2, 4, g.num_tiles, w, x.dtype)
     with pytest.raises((_cabi.TdError, ValueError)):
         eng.blend_multidiffusion(g, [tiles], 2, 4, g.num_tiles - 1, w, x.dtype)  # table does not cover the tiles
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_dependent_launch_chain_keeps_stream_order(eng, graph):
+    """The default kernels are launched with programmatic dependent launch.  A chain in which every kernel consumes
+    what its direct predecessor wrote (scatter reads the canvas the blend just wrote, the blend reads the tiles the
+    scatter just wrote, and overwrites the canvas the scatter just read) must equal the plainly serialised run bit for
+    bit, eagerly and when replayed from a CUDA graph."""
+    N, C, W, H, tw, th, ov, bs = 2, 4, 512, 512, 96, 96, 48, 4
+    g = _grid(eng, W, H, tw, th, ov, bs)
+    plan = tiling.GridPlan(W, H, tw, th, ov, bs, True)
+    twt = torch.from_numpy(plan.tile_weights).cuda()
+    rf = torch.from_numpy(plan.rescale_factor).cuda()
+    x0 = synth.latent(31, (N, C, H, W), torch.float16).cuda()
+    iters = 24
+
+    def chain(flags):
+        xb = x0.clone()
+        tiles = torch.empty((g.num_tiles * N, C, th, tw), dtype=torch.float16, device="cuda")
+        # one batch holding every tile: the blend reads the scatter's output buffer in place
+        def run():
+            for _ in range(iters):
+                eng.scatter_tiles(g, xb, out=tiles, flags=flags)
+                eng.blend_mixture(g, [tiles], N, C, g.num_tiles, twt, rf, xb, flags=flags)
+        if not graph:
+            run()
+        else:
+            st = torch.cuda.Stream()
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                run()                                   # warm-up outside capture (sets kernel attributes)
+                xb.copy_(x0)
+                cg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(cg, stream=st):
+                    run()
+                cg.replay()
+            torch.cuda.current_stream().wait_stream(st)
+        torch.cuda.synchronize()
+        return xb.clone()
+
+    want = chain(NO_PDL)
+    got = chain(0)
+    assert torch.isfinite(want.float()).all()
+    assert_bit_equal(got, want.cpu(), "PDL chain")
