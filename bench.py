@@ -409,6 +409,7 @@ def gpu_arm(args, rank, world, local_rank):
             t_scatter_ser = only(lambda s: wl.scatter(s, 32))
             if args.variants:
                 tbl = {"empty_1024x128": only(wl.empty)}
+                tbl["blend_async_one_plane"] = only(lambda s: wl.blend(s, 64))
                 tbl["blend_async_ieee_div"] = only(lambda s: wl.blend(s, 0x200))
                 wl.blend_mod(0)
                 tbl["blend_mixture_async"] = only(lambda s: wl.blend_mod(s, 0))

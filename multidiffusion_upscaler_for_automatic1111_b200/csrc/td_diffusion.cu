@@ -432,7 +432,15 @@ struct __align__(16) VisitEntry {   // per tile visit of a CTA, computed once by
 };
 constexpr int kAsMaxVisits = 64;
 
-template <typename T, bool WRITE_BUF, bool FASTDIV>
+template <typename T, int S, int PPC>
+__device__ __forceinline__ void consume_planes(uint4 (&acc)[PPC], const unsigned char* p) {
+#pragma unroll
+    for (int q = 0; q < PPC; ++q) consume_shifted<T, S>(acc[q], p + q * kAsStage);
+}
+
+// PPC = planes per CTA: the (n, c) planes of a patch share the visit table, the zero-fill predicate, the weights
+// and the shift, so a CTA that blends PPC planes amortises its prologue and runs PPC independent add chains.
+template <typename T, bool WRITE_BUF, bool FASTDIV, int PPC>
 __global__ void __launch_bounds__(kAsThreads)
 blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __restrict__ weights, const float* __restrict__ rcp_weights,
                       float* __restrict__ out_f32, T* __restrict__ out_buf) {
@@ -444,7 +452,7 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
     __shared__ int s_shift[kAsMaxVisits];
     const GeomParams& g = p.g;
     const int tid = threadIdx.x;
-    const int plane = blockIdx.z;
+    const int plane = blockIdx.z * PPC;      // first plane of this CTA (the host launches PPC > 1 only if it divides N*C)
     const int x_lo = blockIdx.x * BX, y_lo = blockIdx.y * kAsY;
     pdl_launch_dependents();
 
@@ -477,6 +485,7 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
     }
 
     // ---- per-visit constants: thread i prepares visit i -------------------------------------------------
+    const long long plane_bytes = (long long)g.th * g.tw * (long long)sizeof(T);
     if (tid < nv) {
         const int ri = tid / nc, ci = tid - ri * nc;
         const int r = r_lo + ri, c = c_lo + ci;
@@ -484,10 +493,9 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
         const unsigned b = fastdiv(t, p.bs_magic);
         const int u0 = x_lo - (int)g.xs[c];
         const int v0 = y_lo - (int)g.ys[r], k0 = u0 >> L2V;
-        const long long elem = (long long)(t - b * (unsigned)p.tile_bs) * p.tile_stride + (long long)plane * g.th * g.tw +
-                               (long long)v0 * g.tw + (long long)k0 * VEC;
+        const long long elem = (long long)(t - b * (unsigned)p.tile_bs) * p.tile_stride + (long long)v0 * g.tw + (long long)k0 * VEC;
         VisitEntry e;
-        e.origin = (long long)reinterpret_cast<uintptr_t>(p.batch_ptrs[b]) + elem * (long long)sizeof(T);
+        e.origin = (long long)reinterpret_cast<uintptr_t>(p.batch_ptrs[b]) + elem * (long long)sizeof(T) + (long long)plane * plane_bytes;
         e.v0 = v0;
         e.k0 = k0;
         s_visit[tid] = e;
@@ -495,18 +503,19 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
     }
     __syncthreads();
 
-    // ---- issue every copy of this CTA: src = origin(visit) + offset(thread), zero-fill outside the tile -----
+    // ---- issue every copy of this CTA: src = origin(visit) + offset(thread) + plane, zero-fill outside the tile -----
     if (tid < kAsSlots) {
         const int row = tid / kAsChunks, j = tid - row * kAsChunks;    // this thread's copy slot (same in every stage)
         const int th1 = g.th - 1 - row, tw1 = (g.tw >> L2V) - 1 - j;   // v0 <= th1 and k0 <= tw1 <=> inside the tile (upper bounds)
         const long long off = ((long long)row * g.tw + (long long)j * VEC) * (long long)sizeof(T);
         uint32_t dst = smem_u32(td_smem) + (uint32_t)tid * 16u;
 #pragma unroll 4
-        for (int i = 0; i < nv; ++i, dst += kAsStage) {
+        for (int i = 0; i < nv; ++i, dst += PPC * kAsStage) {
             const VisitEntry e = s_visit[i];
             // negative (= outside the tile) iff v < 0, v >= th, k < 0 or k >= twv, with v = v0 + row, k = k0 + j
             const int skip = (e.v0 + row) | (th1 - e.v0) | (e.k0 + j) | (tw1 - e.k0);
-            cp_async16_zfill(dst, e.origin + off, skip);
+#pragma unroll
+            for (int q = 0; q < PPC; ++q) cp_async16_zfill(dst + q * kAsStage, e.origin + off + q * plane_bytes, skip);
         }
     }
     cp_async_wait_all();
@@ -515,27 +524,29 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
 
     // ---- consume in tile order ------------------------------------------------------------------------
     const unsigned char* mine = td_smem + (ty * kAsChunks + tx) * 16;
-    uint4 acc = make_uint4(0, 0, 0, 0);
+    uint4 acc[PPC];
+#pragma unroll
+    for (int q = 0; q < PPC; ++q) acc[q] = make_uint4(0, 0, 0, 0);
     {
-        for (int i = 0; i < nv; ++i, mine += kAsStage) {
+        for (int i = 0; i < nv; ++i, mine += PPC * kAsStage) {
             const int s = s_shift[i];   // uniform over the CTA
             if constexpr (VEC == 8) {
                 switch (s) {
-                    case 0: consume_shifted<T, 0>(acc, mine); break;
-                    case 1: consume_shifted<T, 1>(acc, mine); break;
-                    case 2: consume_shifted<T, 2>(acc, mine); break;
-                    case 3: consume_shifted<T, 3>(acc, mine); break;
-                    case 4: consume_shifted<T, 4>(acc, mine); break;
-                    case 5: consume_shifted<T, 5>(acc, mine); break;
-                    case 6: consume_shifted<T, 6>(acc, mine); break;
-                    default: consume_shifted<T, 7>(acc, mine); break;
+                    case 0: consume_planes<T, 0, PPC>(acc, mine); break;
+                    case 1: consume_planes<T, 1, PPC>(acc, mine); break;
+                    case 2: consume_planes<T, 2, PPC>(acc, mine); break;
+                    case 3: consume_planes<T, 3, PPC>(acc, mine); break;
+                    case 4: consume_planes<T, 4, PPC>(acc, mine); break;
+                    case 5: consume_planes<T, 5, PPC>(acc, mine); break;
+                    case 6: consume_planes<T, 6, PPC>(acc, mine); break;
+                    default: consume_planes<T, 7, PPC>(acc, mine); break;
                 }
             } else {
                 switch (s) {
-                    case 0: consume_shifted<T, 0>(acc, mine); break;
-                    case 1: consume_shifted<T, 1>(acc, mine); break;
-                    case 2: consume_shifted<T, 2>(acc, mine); break;
-                    default: consume_shifted<T, 3>(acc, mine); break;
+                    case 0: consume_planes<T, 0, PPC>(acc, mine); break;
+                    case 1: consume_planes<T, 1, PPC>(acc, mine); break;
+                    case 2: consume_planes<T, 2, PPC>(acc, mine); break;
+                    default: consume_planes<T, 3, PPC>(acc, mine); break;
                 }
             }
         }
@@ -543,29 +554,32 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
 
     // ---- normalise + store --------------------------------------------------------------------------
     if (!inside) return;
-    const long long o = ((long long)plane * g.H + y) * g.W + x0;
-    float4* op = reinterpret_cast<float4*>(out_f32 + o);
 #pragma unroll
-    for (int h = 0; h < VEC / 4; ++h) {
-        const float4 w = wv[h];
-        const float a0 = Vec<T>::get(acc, 4 * h + 0), a1 = Vec<T>::get(acc, 4 * h + 1);
-        const float a2 = Vec<T>::get(acc, 4 * h + 2), a3 = Vec<T>::get(acc, 4 * h + 3);
-        float4 f;   // x_out = where(weights > 1, x_buffer / weights, x_buffer)  -- fp32, correctly rounded divide
-        if constexpr (FASTDIV) {
-            const float4 rc = rv[h];
-            f.x = w.x > 1.0f ? div_exact_small_int(a0, w.x, rc.x) : a0;
-            f.y = w.y > 1.0f ? div_exact_small_int(a1, w.y, rc.y) : a1;
-            f.z = w.z > 1.0f ? div_exact_small_int(a2, w.z, rc.z) : a2;
-            f.w = w.w > 1.0f ? div_exact_small_int(a3, w.w, rc.w) : a3;
-        } else {
-            f.x = w.x > 1.0f ? __fdiv_rn(a0, w.x) : a0;
-            f.y = w.y > 1.0f ? __fdiv_rn(a1, w.y) : a1;
-            f.z = w.z > 1.0f ? __fdiv_rn(a2, w.z) : a2;
-            f.w = w.w > 1.0f ? __fdiv_rn(a3, w.w) : a3;
+    for (int q = 0; q < PPC; ++q) {
+        const long long o = ((long long)(plane + q) * g.H + y) * g.W + x0;
+        float4* op = reinterpret_cast<float4*>(out_f32 + o);
+#pragma unroll
+        for (int h = 0; h < VEC / 4; ++h) {
+            const float4 w = wv[h];
+            const float a0 = Vec<T>::get(acc[q], 4 * h + 0), a1 = Vec<T>::get(acc[q], 4 * h + 1);
+            const float a2 = Vec<T>::get(acc[q], 4 * h + 2), a3 = Vec<T>::get(acc[q], 4 * h + 3);
+            float4 f;   // x_out = where(weights > 1, x_buffer / weights, x_buffer)  -- fp32, correctly rounded divide
+            if constexpr (FASTDIV) {
+                const float4 rc = rv[h];
+                f.x = w.x > 1.0f ? div_exact_small_int(a0, w.x, rc.x) : a0;
+                f.y = w.y > 1.0f ? div_exact_small_int(a1, w.y, rc.y) : a1;
+                f.z = w.z > 1.0f ? div_exact_small_int(a2, w.z, rc.z) : a2;
+                f.w = w.w > 1.0f ? div_exact_small_int(a3, w.w, rc.w) : a3;
+            } else {
+                f.x = w.x > 1.0f ? __fdiv_rn(a0, w.x) : a0;
+                f.y = w.y > 1.0f ? __fdiv_rn(a1, w.y) : a1;
+                f.z = w.z > 1.0f ? __fdiv_rn(a2, w.z) : a2;
+                f.w = w.w > 1.0f ? __fdiv_rn(a3, w.w) : a3;
+            }
+            op[h] = f;
         }
-        op[h] = f;
+        if constexpr (WRITE_BUF) stg128(out_buf + o, acc[q]);
     }
-    if constexpr (WRITE_BUF) stg128(out_buf + o, acc);
 }
 
 // ---------------------------------------------------------------------------
@@ -1353,6 +1367,28 @@ int sm_count() {
     return n;
 }
 
+template <typename T, bool WRITE_BUF, bool FASTDIV, int PPC>
+int launch_blend_async_ppc(const BlendParams& bp, const float* weights, const float* rcp_weights, float* out_f32, void* out_buf,
+                           int nv_cap, cudaStream_t st) {
+    constexpr int VEC = Vec<T>::kElems;
+    constexpr int BX = kAsX * VEC;
+    const int px = (bp.g.W + BX - 1) / BX, py = (bp.g.H + kAsY - 1) / kAsY, planes = bp.g.N * bp.g.C;
+    const int smem = nv_cap * PPC * kAsStage;
+    static int configured = kNoOptInSmem;
+    int rc = ensure_dyn_smem(blend_md_async_kernel<T, WRITE_BUF, FASTDIV, PPC>, smem, &configured);
+    if (rc != TD_OK) return rc;
+    dim3 grid((unsigned)px, (unsigned)py, (unsigned)(planes / PPC));
+    launch_pdl(blend_md_async_kernel<T, WRITE_BUF, FASTDIV, PPC>, grid, dim3(kAsThreads), (size_t)smem, st, bp, weights, rcp_weights,
+               out_f32, (T*)out_buf);
+    return TD_OK;
+}
+
+// planes per CTA (tl_ppc_max is set per C-ABI call: TD_FLAG_ONE_PLANE forces 1)
+#ifndef TD_AS_PPC
+#define TD_AS_PPC 2   // tuning knob (-DTD_AS_PPC=): 1 / 2 / 4
+#endif
+thread_local int tl_ppc_max = TD_AS_PPC;
+
 template <typename T, bool WRITE_BUF, bool FASTDIV>
 int launch_blend_async_impl(const BlendParams& bp, const float* weights, const float* rcp_weights, float* out_f32, void* out_buf,
                             int nv_cap, bool pipelined, cudaStream_t st) {
@@ -1370,12 +1406,14 @@ int launch_blend_async_impl(const BlendParams& bp, const float* weights, const f
         blend_md_pipe_kernel<T, WRITE_BUF, FASTDIV><<<grid, kAsThreads, smem, st>>>(bp, weights, rcp_weights, out_f32, (T*)out_buf, nv_cap,
                                                                                    px, py, (int)total);
     } else {
-        const int smem = nv_cap * kAsStage;
-        static int configured = kNoOptInSmem;
-        int rc = ensure_dyn_smem(blend_md_async_kernel<T, WRITE_BUF, FASTDIV>, smem, &configured);
+        int rc;
+        if (tl_ppc_max >= 4 && planes % 4 == 0 && 4 * nv_cap * kAsStage <= 64 * 1024)
+            rc = launch_blend_async_ppc<T, WRITE_BUF, FASTDIV, 4>(bp, weights, rcp_weights, out_f32, out_buf, nv_cap, st);
+        else if (tl_ppc_max >= 2 && planes % 2 == 0 && 2 * nv_cap * kAsStage <= 64 * 1024)
+            rc = launch_blend_async_ppc<T, WRITE_BUF, FASTDIV, 2>(bp, weights, rcp_weights, out_f32, out_buf, nv_cap, st);
+        else
+            rc = launch_blend_async_ppc<T, WRITE_BUF, FASTDIV, 1>(bp, weights, rcp_weights, out_f32, out_buf, nv_cap, st);
         if (rc != TD_OK) return rc;
-        dim3 grid((unsigned)px, (unsigned)py, (unsigned)planes);
-        launch_pdl(blend_md_async_kernel<T, WRITE_BUF, FASTDIV>, grid, dim3(kAsThreads), (size_t)smem, st, bp, weights, rcp_weights, out_f32, (T*)out_buf);
     }
     return check_launch("td_blend_multidiffusion (cp.async)");
 }
@@ -1540,6 +1578,7 @@ extern "C" int td_blend_multidiffusion(const td_grid* g, const void* const* batc
                                        float* x_out, void* x_buffer, uint32_t flags, void* stream) {
     BlendParams bp;
     tl_pdl = !(flags & TD_FLAG_NO_PDL);
+    tl_ppc_max = (flags & TD_FLAG_ONE_PLANE) ? 1 : TD_AS_PPC;
     int st = fill_blend(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, acc_dtype, &bp);
     if (st != TD_OK) return st;
     if (weights == nullptr || x_out == nullptr) { td_set_error("td_blend_multidiffusion: null weights / x_out"); return TD_ERR_INVALID_ARG; }
@@ -1587,6 +1626,7 @@ extern "C" int td_blend_multidiffusion_peer(const td_grid* g, const void* const*
                                             uint32_t flags, void* stream) {
     BlendParams bp;
     tl_pdl = !(flags & TD_FLAG_NO_PDL);
+    tl_ppc_max = (flags & TD_FLAG_ONE_PLANE) ? 1 : TD_AS_PPC;
     int st = fill_blend(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, acc_dtype, &bp);
     if (st != TD_OK) return st;
     if (weights == nullptr || x_out == nullptr) { td_set_error("td_blend_multidiffusion_peer: null weights / x_out"); return TD_ERR_INVALID_ARG; }
@@ -1618,6 +1658,7 @@ extern "C" int td_blend_mixture(const td_grid* g, const void* const* batch_ptrs,
                                 void* x_buffer, uint32_t flags, void* stream) {
     BlendParams bp;
     tl_pdl = !(flags & TD_FLAG_NO_PDL);
+    tl_ppc_max = (flags & TD_FLAG_ONE_PLANE) ? 1 : TD_AS_PPC;
     int st = fill_blend(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, acc_dtype, &bp);
     if (st != TD_OK) return st;
     if (tile_weights == nullptr || rescale == nullptr || x_buffer == nullptr) {

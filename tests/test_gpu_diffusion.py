@@ -18,8 +18,9 @@ NO_TMA = 2
 TMA = 4
 PIPE = 8
 NO_PDL = 32
+ONE_PLANE = 64
 # cp.async-staged (default), persistent pipelined cp.async, TMA-staged, register-staged, scalar kernels
-ALL_PATHS = [0, NO_PDL, PIPE, TMA, NO_TMA, FORCE_GENERIC]
+ALL_PATHS = [0, NO_PDL, ONE_PLANE, PIPE, TMA, NO_TMA, FORCE_GENERIC]
 
 
 @pytest.fixture(scope="module")
