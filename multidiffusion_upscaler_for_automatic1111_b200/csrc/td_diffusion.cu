@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <atomic>
 #include <mutex>
 
 #include "td_b200.h"
@@ -1259,12 +1260,26 @@ int max_union(const int32_t* org, int n, int extent, int size, int patch) {
 // dynamic shared memory a kernel may request without opting in (48 KB minus its static allocation, with margin)
 constexpr int kNoOptInSmem = 40 * 1024;
 
+// The opt-in above 48 KB of dynamic shared memory is a per-device function attribute: remember the size configured
+// for each device ordinal (a host may drive several GPUs from one process), set it under a lock.
+constexpr int kMaxDevices = 64;
+struct SmemOptIn {
+    std::atomic<int> bytes[kMaxDevices];
+    SmemOptIn() { for (auto& b : bytes) b.store(kNoOptInSmem, std::memory_order_relaxed); }
+};
+
 template <typename KernelT>
-int ensure_dyn_smem(KernelT kernel, int bytes, int* configured) {
-    if (bytes <= *configured) return TD_OK;
+int ensure_dyn_smem(KernelT kernel, int bytes, SmemOptIn* configured) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) { td_set_error("cudaGetDevice failed"); return TD_ERR_CUDA; }
+    std::atomic<int>* slot = dev < kMaxDevices ? &configured->bytes[dev] : nullptr;
+    if (slot != nullptr && bytes <= slot->load(std::memory_order_acquire)) return TD_OK;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (slot != nullptr && bytes <= slot->load(std::memory_order_relaxed)) return TD_OK;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) { td_set_error("cudaFuncSetAttribute(%d B smem): %s", bytes, cudaGetErrorString(e)); return TD_ERR_CUDA; }
-    *configured = bytes;
+    if (slot != nullptr) slot->store(bytes, std::memory_order_release);
     return TD_OK;
 }
 
@@ -1286,7 +1301,7 @@ int launch_blend_tma_nb(const td_grid* g, const BlendParams& bp, int tile_dtype,
         if (rc != TD_OK) return rc;
     }
     const int smem = nv_cap * (STAGE + 8);
-    static int configured = kNoOptInSmem;
+    static SmemOptIn configured;
     int rc = ensure_dyn_smem(blend_md_tma_kernel<T, WRITE_BUF, NB>, smem, &configured);
     if (rc != TD_OK) return rc;
     dim3 grid((unsigned)((bp.g.W + BX - 1) / BX), (unsigned)((bp.g.H + kTmaBY - 1) / kTmaBY), (unsigned)NC);
@@ -1338,7 +1353,7 @@ int try_launch_scatter_tma(GeomParams gp, const void* x, void* tiles, int dtype,
     int rc = td_encode_tensor_map_3d(&tp.src, x, dtype, (uint64_t)gp.N * gp.C, (uint64_t)gp.H, (uint64_t)gp.W, (uint32_t)rb,
                                      (uint32_t)(gp.tw + VEC));
     if (rc != TD_OK) return rc;
-    static int configured = kNoOptInSmem;
+    static SmemOptIn configured;
     rc = ensure_dyn_smem(scatter_tma_kernel<T>, smem, &configured);
     if (rc != TD_OK) return rc;
     launch_pdl(scatter_tma_kernel<T>, dim3((unsigned)planes_out), dim3(kScThreads), (size_t)smem, st, tp, (T*)tiles, tile_begin, rb, nboxes, box_bytes);
@@ -1374,7 +1389,7 @@ int launch_blend_async_ppc(const BlendParams& bp, const float* weights, const fl
     constexpr int BX = kAsX * VEC;
     const int px = (bp.g.W + BX - 1) / BX, py = (bp.g.H + kAsY - 1) / kAsY, planes = bp.g.N * bp.g.C;
     const int smem = nv_cap * PPC * kAsStage;
-    static int configured = kNoOptInSmem;
+    static SmemOptIn configured;
     int rc = ensure_dyn_smem(blend_md_async_kernel<T, WRITE_BUF, FASTDIV, PPC>, smem, &configured);
     if (rc != TD_OK) return rc;
     dim3 grid((unsigned)px, (unsigned)py, (unsigned)(planes / PPC));
@@ -1397,7 +1412,7 @@ int launch_blend_async_impl(const BlendParams& bp, const float* weights, const f
     const int px = (bp.g.W + BX - 1) / BX, py = (bp.g.H + kAsY - 1) / kAsY, planes = bp.g.N * bp.g.C;
     if (pipelined) {
         const int smem = 2 * nv_cap * kAsStage;
-        static int configured = kNoOptInSmem;
+        static SmemOptIn configured;
         int rc = ensure_dyn_smem(blend_md_pipe_kernel<T, WRITE_BUF, FASTDIV>, smem, &configured);
         if (rc != TD_OK) return rc;
         const long long total = (long long)px * py * planes;
@@ -1446,7 +1461,7 @@ int try_launch_blend_mod_async(const td_grid* g, const BlendParams& bp_in, const
     fill_patch_table(g->ys, g->rows, g->tile_h, g->H, kAsY, bp.prow_lo, bp.prow_n);
     fill_patch_table(g->xs, g->cols, g->tile_w, g->W, BX, bp.pcol_lo, bp.pcol_n);
     const int smem = nv_cap * kAsStage;
-    static int configured = kNoOptInSmem;
+    static SmemOptIn configured;
     int rc = ensure_dyn_smem(blend_mod_async_kernel<T>, smem, &configured);
     if (rc != TD_OK) return rc;
     dim3 grid((unsigned)((bp.g.W + BX - 1) / BX), (unsigned)((bp.g.H + kAsY - 1) / kAsY), (unsigned)(bp.g.N * bp.g.C));
