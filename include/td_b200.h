@@ -77,6 +77,15 @@ int td_splitable(int w, int h, int tile_w, int tile_h, int overlap);
 /* gaussian_weights -- tile_utils/utils.py:180-194.  out: fp32 [tile_h*tile_w]. */
 int td_gaussian_weights(int tile_w, int tile_h, float* out);
 
+/* feather_mask -- tile_utils/utils.py:196-214 (region prompt control, FOREGROUND boxes).
+ * out: fp32 [h*w]; 1 inside, (dist/radius)^2 towards the border, radius = int(min(w//2, h//2) * ratio). */
+int td_feather_mask(int w, int h, double ratio, float* out);
+
+/* Region rectangle in latent units from the UI's relative (x, y, w, h) --
+ * tile_methods/abstractdiffusion.py:206-215: x = max(0, int(x*W)), w = min(W - x, ceil(w*W)), same for y / h.
+ * Returns 1 and writes out_xywh, or 0 if the reference skips the box (x > 1, y > 1, w <= 0 or h <= 0). */
+int td_custom_bbox_rect(double x, double y, double w, double h, int canvas_w, int canvas_h, int32_t* out_xywh);
+
 /* Grid plan = what init_grid_bbox leaves on the delegate
  * (tile_methods/abstractdiffusion.py:172-186): clamped tile size and overlap,
  * separable tile origins, tile count and re-balanced tile batch size. */

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
 
 import torch
 
@@ -62,6 +62,8 @@ _SIGNATURES = {
     "td_split_bboxes": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int), POINTER(c_int)]),
     "td_splitable": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "td_gaussian_weights": (c_int, [c_int, c_int, POINTER(c_float)]),
+    "td_feather_mask": (c_int, [c_int, c_int, c_double, POINTER(c_float)]),
+    "td_custom_bbox_rect": (c_int, [c_double, c_double, c_double, c_double, c_int, c_int, POINTER(c_int32)]),
     "td_grid_init": (c_int, [POINTER(TdGrid), c_int, c_int, c_int, c_int, c_int, c_int]),
     "td_grid_weights": (c_int, [POINTER(TdGrid), POINTER(c_float), POINTER(c_float)]),
     "td_rescale_factor": (c_int, [POINTER(c_float), POINTER(c_float), c_int64]),

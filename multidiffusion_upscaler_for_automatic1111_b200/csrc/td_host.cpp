@@ -127,6 +127,47 @@ extern "C" int td_gaussian_weights(int tile_w, int tile_h, float* out) {
     return TD_OK;
 }
 
+extern "C" int td_feather_mask(int w, int h, double ratio, float* out) {
+    if (w <= 0 || h <= 0 || out == nullptr) {
+        td_set_error("feather_mask: bad args");
+        return TD_ERR_INVALID_ARG;
+    }
+    for (size_t i = 0; i < (size_t)w * h; ++i) out[i] = 1.0f;
+    // feather_radius = int(min(w//2, h//2) * ratio): float64 product, truncation (utils.py:200)
+    const int radius = (int)((double)std::min(w / 2, h / 2) * ratio);
+    for (int i = 0; i < h / 2; ++i)
+        for (int j = 0; j < w / 2; ++j) {
+            const int dist = std::min(i, j);
+            if (dist >= radius) continue;
+            // (dist / radius) ** 2 in float64, stored into a float32 array (utils.py:208)
+            const float wt = (float)std::pow((double)dist / (double)radius, 2.0);
+            out[(size_t)i * w + j] = wt;
+            out[(size_t)i * w + (w - j - 1)] = wt;
+            out[(size_t)(h - i - 1) * w + j] = wt;
+            out[(size_t)(h - i - 1) * w + (w - j - 1)] = wt;
+        }
+    return TD_OK;
+}
+
+extern "C" int td_custom_bbox_rect(double x, double y, double w, double h, int canvas_w, int canvas_h, int32_t* out_xywh) {
+    if (out_xywh == nullptr || canvas_w <= 0 || canvas_h <= 0) {
+        td_set_error("custom_bbox_rect: bad args");
+        return TD_ERR_INVALID_ARG;
+    }
+    if (x > 1.0 || y > 1.0 || w <= 0.0 || h <= 0.0) return 0;   // skipped by the reference (abstractdiffusion.py:207)
+    // int(x * W), math.ceil(w * W) on float64 products; then clamps (abstractdiffusion.py:208-215)
+    int xi = (int)(x * (double)canvas_w);
+    int yi = (int)(y * (double)canvas_h);
+    int wi = (int)std::ceil(w * (double)canvas_w);
+    int hi = (int)std::ceil(h * (double)canvas_h);
+    xi = std::max(0, xi);
+    yi = std::max(0, yi);
+    wi = std::min(canvas_w - xi, wi);
+    hi = std::min(canvas_h - yi, hi);
+    out_xywh[0] = xi; out_xywh[1] = yi; out_xywh[2] = wi; out_xywh[3] = hi;
+    return 1;
+}
+
 extern "C" int td_grid_init(td_grid* g, int w, int h, int tile_w, int tile_h, int overlap, int tile_bs) {
     if (g == nullptr || tile_bs <= 0) {
         td_set_error("grid_init: bad args");

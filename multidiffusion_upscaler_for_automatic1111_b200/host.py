@@ -46,6 +46,11 @@ def _a1111(name: str):
     return _a1111_cache[name]
 
 
+def a1111_module(name: str):
+    """Public form of `_a1111` for the region-prompt helpers (prompt_parser, extra_networks)."""
+    return _a1111(name)
+
+
 def _a1111_shared():
     m = _a1111("shared")
     return m if m is not None and hasattr(m, "state") else None
@@ -112,3 +117,31 @@ def is_ddim_sampler(sampler) -> bool:
     if m is not None and hasattr(m, "CompVisSampler") and isinstance(sampler, m.CompVisSampler):
         return True
     return bool(_mro_names(sampler) & {"CompVisSampler", "VanillaStableDiffusionSampler"})
+
+
+def batch_cond_uncond() -> bool:
+    """`shared.batch_cond_uncond` (abstractdiffusion.py:276); True outside the WebUI."""
+    return bool(getattr(get_shared(), "batch_cond_uncond", True))
+
+
+def extra_networks_activate(p, data) -> None:
+    """extra_networks.activate under autocast (multidiffusion.py:178-180); no-op outside the WebUI."""
+    m, d = _a1111("extra_networks"), _a1111("devices")
+    if m is None or not hasattr(m, "activate"):
+        return
+    if d is not None and hasattr(d, "autocast"):
+        with d.autocast():
+            m.activate(p, data)
+    else:
+        m.activate(p, data)
+
+
+def extra_networks_deactivate(p, data) -> None:
+    m, d = _a1111("extra_networks"), _a1111("devices")
+    if m is None or not hasattr(m, "deactivate"):
+        return
+    if d is not None and hasattr(d, "autocast"):
+        with d.autocast():
+            m.deactivate(p, data)
+    else:
+        m.deactivate(p, data)

@@ -7,21 +7,24 @@ What differs from the reference by design:
     UNet receives views of that buffer (180 GB of HBM: no need to re-cat).
   * `reset_buffer` only (re)allocates: the fused gather-form blend writes every
     canvas pixel, so the per-step `zero_()` pass of the reference is not needed.
-  * Region prompt control, ControlNet / StableSR tile caches and noise inversion
-    are later rows of the scope table: their `init_*`
-    raise NotImplementedError instead of silently doing something else.
+  * Region prompt control is built on the same kernels: the grid tiles go through the
+    fused blend (which then also returns the un-normalised `x_buffer`), the handful of custom regions are cropped,
+    added and feather-composited with the reference's own tensor expressions.
+  * ControlNet / StableSR tile caches and noise inversion are later rows of the scope table (section 8(f)-2/3):
+    their `init_*` raise NotImplementedError instead of silently doing something else.
 """
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Union
+from typing import Callable, Dict, List, Optional, Tuple, Union
 
 import torch
 from torch import Tensor
 
 from .. import engine, host
 from ..host import opt_f
-from ..tile_utils.utils import BBox, custom_bbox, grid_bbox, noise_inverse, controlnet, stablesr
+from ..tile_utils.utils import (BBox, BlendMode, Condition, CustomBBox, Prompt, custom_bbox, custom_bbox_rect, grid_bbox,
+                                noise_inverse, controlnet, stablesr)
 
 CondDict = Dict[str, Union[Tensor, List[Tensor]]]
 
@@ -65,9 +68,11 @@ class AbstractDiffusion:
         self.num_batches: Optional[int] = None
         self.batched_bboxes: List[List[BBox]] = []
 
-        # region prompt control (not on this path yet)
+        # region prompt control (abstractdiffusion.py:44-49)
         self.enable_custom_bbox: bool = False
-        self.custom_bboxes: list = []
+        self.custom_bboxes: List[CustomBBox] = []
+        self.cond_basis = None
+        self.uncond_basis = None
         self.draw_background: bool = True
         self.causal_layers: Optional[bool] = None
 
@@ -252,11 +257,212 @@ class AbstractDiffusion:
         return engine.blend_multidiffusion(g, chunks, N, C, sh.chunk, self.weights, x.dtype, x_buffer=None, flags=self._blend_flags,
                                            rcp_weights=self._rcp_weights)
 
-    # ------------------------------------------- later rows of the scope table
+    # ------------------------------------------------- region prompt control
     @custom_bbox
-    def init_custom_bbox(self, bbox_settings, draw_background: bool, causal_layers: bool):
-        raise NotImplementedError("Region prompt control is not on the B200 hot path yet (SURVEY.md section 8(f)-1)")
+    def init_custom_bbox(self, bbox_settings: Dict[int, tuple], draw_background: bool, causal_layers: bool):
+        """abstractdiffusion.py:193-229: region rectangles in latent units (td_custom_bbox_rect, bit-exact with the
+        reference's float64 arithmetic) and their prompt conditionings (host application's prompt parser)."""
+        self.enable_custom_bbox = True
+        self.causal_layers = causal_layers
+        self.draw_background = draw_background
+        if not draw_background:
+            self.enable_grid_bbox = False
+            self.weights.zero_()
 
+        self.custom_bboxes = []
+        for setting in bbox_settings.values():
+            e, x, y, w, h, prompt, neg_prompt, blend_mode, feather_ratio, seed = setting
+            if not e:
+                continue
+            rect = custom_bbox_rect(x, y, w, h, self.w, self.h)
+            if rect is None:
+                continue
+            self.custom_bboxes.append(CustomBBox(*rect, prompt, neg_prompt, blend_mode, feather_ratio, seed))
+
+        if len(self.custom_bboxes) == 0:
+            self.enable_custom_bbox = False
+            return
+
+        if host.a1111_module("prompt_parser") is None:
+            # no text encoder outside the WebUI: the caller's `custom_func` owns the conditioning
+            return
+        p = self.p
+        prompts = p.all_prompts[:p.batch_size]
+        neg_prompts = p.all_negative_prompts[:p.batch_size]
+        for bbox in self.custom_bboxes:
+            bbox.cond, bbox.extra_network_data = Condition.get_custom_cond(prompts, bbox.prompt, p.steps, p.styles)
+            bbox.uncond = Condition.get_uncond(Prompt.append_prompt(neg_prompts, bbox.neg_prompt), p.steps, p.styles)
+        self.cond_basis = Condition.get_cond(prompts, p.steps)
+        self.uncond_basis = Condition.get_uncond(neg_prompts, p.steps)
+
+    @custom_bbox
+    def reconstruct_custom_cond(self, org_cond: CondDict, custom_cond, custom_uncond, bbox: CustomBBox):
+        """abstractdiffusion.py:231-243: the region's text cond / uncond at the sampler's current step, and the
+        image cond cropped to the region when it is spatial (img2img)."""
+        image_conditioning = None
+        if isinstance(org_cond, dict):
+            icond = self.get_icond(org_cond)
+            if tuple(icond.shape[2:]) == (self.h, self.w):
+                icond = icond[bbox.slicer]
+            image_conditioning = icond
+        step = self.sampler.model_wrap_cfg.step
+        return Condition.reconstruct_cond(custom_cond, step), Condition.reconstruct_uncond(custom_uncond, step), image_conditioning
+
+    def set_custom_controlnet_tensors(self, bbox_id: int, repeat_size: int):
+        pass
+
+    def set_custom_stablesr_tensors(self, bbox_id: int):
+        pass
+
+    def _forward_region(self, bbox_id: int, forward_func: Callable, x: Tensor, sigma: Tensor, original_cond: CondDict,
+                        tcond: Tensor, icond) -> Tensor:
+        self.set_custom_controlnet_tensors(bbox_id, x.shape[0])
+        self.set_custom_stablesr_tensors(bbox_id)
+        return forward_func(x, sigma, cond=self.make_cond_dict(original_cond, tcond, icond))
+
+    def _forward_region_split(self, bbox_id: int, forward_func: Callable, x_tile: Tensor, sigma_in: Tensor, original_cond: CondDict,
+                              first: Tensor, second: Tensor, icond_first, icond_second, pad_with_second: bool = False) -> Tensor:
+        """Two UNet calls when the cond and uncond token counts differ (they cannot share a batch):
+        rows [0, n1) with `first`, the next n2 rows with `second` (abstractdiffusion.py:288-311, :376-395)."""
+        x_out = torch.zeros_like(x_tile)
+        n1, n2 = first.shape[0], second.shape[0]
+        out1 = self._forward_region(bbox_id, forward_func, x_tile[:n1], sigma_in[:n1], original_cond, first, icond_first)
+        hi = n1 + n2 if pad_with_second else x_tile.shape[0]
+        out2 = self._forward_region(bbox_id, forward_func, x_tile[n1:hi], sigma_in[n1:hi], original_cond, second, icond_second)
+        x_out[:n1] = out1
+        x_out[n1:hi] = out2
+        if pad_with_second and self.is_edit_model:
+            x_out[hi:] = out2
+        return x_out
+
+    @custom_bbox
+    def kdiff_custom_forward(self, x_tile: Tensor, sigma_in: Tensor, original_cond: CondDict, bbox_id: int, bbox: CustomBBox,
+                             forward_func: Callable) -> Tensor:
+        """Denoise one custom region the way the k-diffusion CFG wrapper batches the whole image
+        (abstractdiffusion.py:245-427).  The wrapper feeds [cond rows, uncond rows(, uncond rows for edit models)]
+        either in one batch or -- low-VRAM mode, or prompts of different token length -- in slices; the region's
+        own cond / uncond have to be fed in the same row layout."""
+        step = self.sampler.model_wrap_cfg.step
+        if self.kdiff_step != step:                       # a new sampler step: forget per-step state
+            self.kdiff_step = step
+            self.kdiff_step_bbox = [-1] * len(self.custom_bboxes)
+            self.tensor, self.uncond, self.image_cond_in = {}, {}, {}
+            # the global prompts tell how the wrapper batches this step
+            self.real_tensor = Condition.reconstruct_cond(self.cond_basis, step)
+            self.real_uncond = Condition.reconstruct_uncond(self.uncond_basis, step)
+            self.a = [0] * len(self.custom_bboxes)        # rows of the virtual batch already served, per region
+        same_len_global = self.real_tensor.shape[1] == self.real_uncond.shape[1]
+
+        if self.kdiff_step_bbox[bbox_id] != step:         # first call for this region in this step
+            self.kdiff_step_bbox[bbox_id] = step
+            tensor, uncond, icond = self.reconstruct_custom_cond(original_cond, bbox.cond, bbox.uncond, bbox)
+            if same_len_global and host.batch_cond_uncond():
+                # x_tile holds the complete virtual batch
+                if tensor.shape[1] == uncond.shape[1]:
+                    parts = [tensor, uncond, uncond] if self.is_edit_model else [tensor, uncond]
+                    return self._forward_region(bbox_id, forward_func, x_tile, sigma_in, original_cond, torch.cat(parts), icond)
+                n1, n2 = tensor.shape[0], uncond.shape[0]
+                return self._forward_region_split(bbox_id, forward_func, x_tile, sigma_in, original_cond, tensor, uncond,
+                                                  icond[:n1], icond[n1:n1 + n2], pad_with_second=True)
+            # x_tile is a slice of the virtual batch: keep the region's tensors for the following calls
+            self.tensor[bbox_id], self.uncond[bbox_id], self.image_cond_in[bbox_id] = tensor, uncond, icond
+
+        tensor, uncond, icond = self.tensor[bbox_id], self.uncond[bbox_id], self.image_cond_in[bbox_id]
+        a = self.a[bbox_id]
+        b = a + x_tile.shape[0]
+        self.a[bbox_id] = b
+        T, U = tensor.shape[0], uncond.shape[0]
+
+        if same_len_global:
+            # rows [a, b) of the virtual batch [tensor | uncond (| uncond)]
+            segments = [(tensor, 0)] + [(uncond, T + k * U) for k in range(2 if self.is_edit_model else 1)]
+            cond_rows, uncond_rows = [], []
+            for seg, lo in segments:
+                s, e = max(a, lo) - lo, min(b, lo + seg.shape[0]) - lo
+                if e > s:
+                    (cond_rows if seg is tensor else uncond_rows).append(seg[s:e])
+            if not cond_rows:                              # the slice lies entirely in the uncond rows
+                return self._forward_region(bbox_id, forward_func, x_tile, sigma_in, original_cond,
+                                            uncond_rows[0] if len(uncond_rows) == 1 else torch.cat(uncond_rows), icond)
+            cond_in = cond_rows[0]
+            if not uncond_rows:
+                return self._forward_region(bbox_id, forward_func, x_tile, sigma_in, original_cond, cond_in, icond)
+            uncond_in = uncond_rows[0] if len(uncond_rows) == 1 else torch.cat(uncond_rows)
+            if tensor.shape[1] == uncond.shape[1]:
+                return self._forward_region(bbox_id, forward_func, x_tile, sigma_in, original_cond,
+                                            torch.cat([cond_in, uncond_in]), icond)
+            return self._forward_region_split(bbox_id, forward_func, x_tile, sigma_in, original_cond, cond_in, uncond_in, icond, icond)
+
+        # global prompts of different token length: the wrapper runs cond and uncond separately
+        if a < T:
+            tcond = tensor[a:b]
+            if self.is_edit_model:
+                tcond = torch.cat([tcond, uncond])
+            return self._forward_region(bbox_id, forward_func, x_tile, sigma_in, original_cond, tcond, icond)
+        self.set_custom_controlnet_tensors(bbox_id, U)
+        self.set_custom_stablesr_tensors(bbox_id)
+        return forward_func(x_tile, sigma_in, cond=self.make_cond_dict(original_cond, uncond, icond))
+
+    @custom_bbox
+    def ddim_custom_forward(self, x: Tensor, cond_in: CondDict, bbox: CustomBBox, ts: Tensor, forward_func: Callable,
+                            *args, **kwargs) -> Tensor:
+        """abstractdiffusion.py:429-451: DDIM takes cond and uncond side by side, so only their token counts have
+        to agree -- the uncond is padded with its last vector or truncated."""
+        tensor, uncond, image_conditioning = self.reconstruct_custom_cond(cond_in, bbox.cond, bbox.uncond, bbox)
+        cond = tensor
+        if uncond.shape[1] < cond.shape[1]:
+            pad = uncond[:, -1:].repeat([1, cond.shape[1] - uncond.shape[1], 1])
+            uncond = torch.hstack([uncond, pad])
+        elif uncond.shape[1] > cond.shape[1]:
+            uncond = uncond[:, :cond.shape[1]]
+        if image_conditioning is not None:
+            cond = self.make_cond_dict(cond_in, cond, image_conditioning)
+            uncond = self.make_cond_dict(cond_in, uncond, image_conditioning)
+        return forward_func(x, cond, ts, unconditional_conditioning=uncond, *args, **kwargs)
+
+    _INTERRUPTED = object()
+
+    def _custom_region_pass(self, x: Tensor, custom_func: Callable, add_background: Callable, poll_interrupt: bool):
+        """Second half of a tiled step (multidiffusion.py:170-204, mixtureofdiffusers.py:128-165): every custom region is
+        cropped from the latent, denoised by `custom_func`, and either added to `x_buffer` (BACKGROUND, through
+        `add_background`) or collected into the feather buffers (FOREGROUND).
+
+        Returns None, the feather triple (buffer, mask, count), or `_INTERRUPTED`."""
+        N, C, H, W = x.shape
+        feather = None
+        use_networks = not getattr(self.p, "disable_extra_networks", False)
+        for bbox_id, bbox in enumerate(self.custom_bboxes):
+            if poll_interrupt and host.interrupted():
+                return self._INTERRUPTED
+            if use_networks:
+                host.extra_networks_activate(self.p, bbox.extra_network_data)
+            x_tile_out = custom_func(x[bbox.slicer], bbox_id, bbox)
+            if bbox.blend_mode == BlendMode.BACKGROUND:
+                add_background(bbox_id, bbox, x_tile_out)
+            elif bbox.blend_mode == BlendMode.FOREGROUND:
+                if feather is None:
+                    feather = (torch.zeros_like(self.x_buffer), torch.zeros((1, 1, H, W), device=x.device),
+                               torch.zeros((1, 1, H, W), device=x.device))
+                if bbox.feather_mask.device != x.device:
+                    bbox.feather_mask = bbox.feather_mask.to(x.device)
+                feather[0][bbox.slicer] += x_tile_out
+                feather[1][bbox.slicer] += bbox.feather_mask
+                feather[2][bbox.slicer] += 1
+            if use_networks:
+                host.extra_networks_deactivate(self.p, bbox.extra_network_data)
+            self.update_pbar()
+        return feather
+
+    @staticmethod
+    def _feather_composite(x_out: Tensor, feather: Tuple[Tensor, Tensor, Tensor]) -> Tensor:
+        """multidiffusion.py:210-216 / mixtureofdiffusers.py:168-173: average overlapping foreground regions, then
+        lay them over the background with their (averaged) feather masks."""
+        buf, mask, count = feather
+        buf = torch.where(count > 1, buf / count, buf)
+        mask = torch.where(count > 1, mask / count, mask)
+        return torch.where(count > 0, x_out * (1 - mask) + buf * mask, x_out)
+
+    # ------------------------------------------- later rows of the scope table
     @noise_inverse
     def init_noise_inverse(self, *args, **kwargs):
         raise NotImplementedError("Tiled noise inversion is not on the B200 hot path yet (SURVEY.md section 8(f)-3)")
@@ -282,7 +488,7 @@ class AbstractDiffusion:
     def _check_input(self, x_in: Tensor) -> Tensor:
         if not x_in.is_cuda:
             raise RuntimeError(f"{self.method}: latent is on {x_in.device}; the B200 path has no CPU fallback")
-        if self._grid is None:
+        if self.enable_grid_bbox and self._grid is None:
             raise RuntimeError(f"{self.method}: init_grid_bbox() has not been called")
         if self.weights.device != x_in.device:
             self.weights = self.weights.to(x_in.device)

@@ -15,7 +15,7 @@ import torch
 from torch import Tensor
 
 from .. import engine, host
-from ..tile_utils.utils import BBox, custom_bbox, gaussian_weights, grid_bbox, keep_signature
+from ..tile_utils.utils import BBox, BlendMode, Condition, CustomBBox, custom_bbox, gaussian_weights, grid_bbox, keep_signature
 from .abstractdiffusion import AbstractDiffusion, CondDict
 
 
@@ -48,6 +48,10 @@ class MixtureOfDiffusers(AbstractDiffusion):
         w_host = self.weights.detach().to("cpu", torch.float32).numpy().reshape(self.h, self.w)
         rf = engine.rescale_factor(w_host)
         self.rescale_factor = torch.from_numpy(rf).view(1, 1, self.h, self.w).to(self.weights.device)
+        # BACKGROUND regions: their gaussians are pre-multiplied by the rescale factor once (mixtureofdiffusers.py:33-36)
+        for bbox_id, bbox in enumerate(self.custom_bboxes):
+            if bbox.blend_mode == BlendMode.BACKGROUND:
+                self.custom_weights[bbox_id] *= self.rescale_factor[bbox.slicer]
 
     @grid_bbox
     def get_tile_weights(self) -> Tensor:
@@ -58,12 +62,23 @@ class MixtureOfDiffusers(AbstractDiffusion):
 
     @custom_bbox
     def init_custom_bbox(self, *args):
+        """mixtureofdiffusers.py:45-55: a BACKGROUND region brings its own gaussian (sized to the region) into the
+        weight canvas; `init_done` then rescales it like the grid tiles' gaussian."""
         super().init_custom_bbox(*args)
+        self.custom_weights = []
+        for bbox in self.custom_bboxes:
+            if bbox.blend_mode == BlendMode.BACKGROUND:
+                cw = self.get_weight(bbox.w, bbox.h).to(self.weights.device)
+                self.weights[bbox.slicer] += cw
+                self.custom_weights.append(cw.clone().unsqueeze(0).unsqueeze(0))
+            else:
+                self.custom_weights.append(None)
 
     @torch.no_grad()
     @keep_signature
     def apply_model_hijack(self, x_in: Tensor, t_in: Tensor, cond: CondDict, noise_inverse_step: int = -1):
-        """mixtureofdiffusers.py:61-179 (grid part).  Returns `x_buffer` (aliases delegate state, like the reference)."""
+        """mixtureofdiffusers.py:61-179.  Returns `x_buffer` (aliases delegate state, like the reference) unless
+        FOREGROUND regions were composited over it."""
         sd_model = self._sd_model()
         c_in: CondDict = cond
         N, C, H, W = x_in.shape
@@ -72,9 +87,43 @@ class MixtureOfDiffusers(AbstractDiffusion):
             return sd_model.apply_model_original_md(x_in, t_in, c_in)
 
         x = self._check_input(x_in)
-        if not self.draw_background:
-            raise NotImplementedError("draw_background=False needs region prompt control (SURVEY.md section 8(f)-1)")
         self.reset_buffer(x)
+        regions = self.enable_custom_bbox and len(self.custom_bboxes) > 0
+
+        if self.enable_grid_bbox:
+            x_out = self._grid_pass(x_in, x, t_in, c_in, sd_model, N, C)
+            if x_out is None:
+                return x_in            # interrupted
+        else:
+            # draw_background=False: only the custom regions paint (mixtureofdiffusers.py:82 skips the grid loop)
+            self.x_buffer.zero_()
+        if not regions:
+            return self.x_buffer
+
+        def custom_func(x_tile: Tensor, bbox_id: int, bbox: CustomBBox) -> Tensor:
+            if noise_inverse_step < 0:
+                return self.custom_apply_model(x_tile, t_in, c_in, bbox_id, bbox)
+            tcond = Condition.reconstruct_cond(bbox.cond, noise_inverse_step)
+            icond = self.get_icond(c_in)
+            if tuple(icond.shape[2:]) == (self.h, self.w):
+                icond = icond[bbox.slicer]
+            c_out = self.make_cond_dict(c_in, tcond, icond, self.get_vcond(c_in))
+            return sd_model.apply_model(x_tile, t_in, cond=c_out)
+
+        def add_background(bbox_id: int, bbox: CustomBBox, x_tile_out: Tensor):
+            cw = self.custom_weights[bbox_id]
+            if cw.device != x.device:
+                cw = self.custom_weights[bbox_id] = cw.to(x.device)
+            self.x_buffer[bbox.slicer] += x_tile_out * cw
+
+        feather = self._custom_region_pass(x, custom_func, add_background, poll_interrupt=False)
+        if feather is None:
+            return self.x_buffer
+        return self._feather_composite(self.x_buffer, feather)
+
+    def _grid_pass(self, x_in: Tensor, x: Tensor, t_in: Tensor, c_in: CondDict, sd_model, N: int, C: int):
+        """Grid tiles of one UNet call: scatter, denoise per batch, fused gaussian blend into x_buffer.
+        Returns x_buffer, or None when the job was interrupted."""
         if self.rescale_factor.device != x.device:
             self.rescale_factor = self.rescale_factor.to(x.device)
         if self.tile_weights.device != x.device:
@@ -91,7 +140,7 @@ class MixtureOfDiffusers(AbstractDiffusion):
         outs = []
         for batch_id, bboxes in enumerate(self.batched_bboxes):
             if host.interrupted():
-                return x_in
+                return None
             n_rep = len(bboxes)
             x_tile = self._tile_batch(tiles, batch_id, N)
             t_tile = torch.cat([t_in] * n_rep, dim=0) if n_rep > 1 else t_in
@@ -116,6 +165,25 @@ class MixtureOfDiffusers(AbstractDiffusion):
 
         return engine.blend_mixture(self._grid, outs, N, C, self.tile_bs, self.tile_weights, self.rescale_factor,
                                     self.x_buffer, flags=self._blend_flags)
+
+    def custom_apply_model(self, x_in: Tensor, t_in: Tensor, c_in: CondDict, bbox_id: int, bbox: CustomBBox) -> Tensor:
+        """mixtureofdiffusers.py:181-196: a region goes through the un-hijacked `apply_model` with its own prompts."""
+        sd_model = self._sd_model()
+        if self.is_kdiff:
+            return self.kdiff_custom_forward(x_in, t_in, c_in, bbox_id, bbox, forward_func=sd_model.apply_model_original_md)
+
+        def forward_func(x, c, ts, unconditional_conditioning, *args, **kwargs) -> Tensor:
+            # DDIM evaluates [uncond, cond] as one batch (p_sample_ddim)
+            merged: CondDict = {}
+            for k in c:
+                if isinstance(c[k], list):
+                    merged[k] = [torch.cat([unconditional_conditioning[k][i], c[k][i]]) for i in range(len(c[k]))]
+                else:
+                    merged[k] = torch.cat([unconditional_conditioning[k], c[k]])
+            self.set_custom_controlnet_tensors(bbox_id, x.shape[0])
+            self.set_custom_stablesr_tensors(bbox_id)
+            return sd_model.apply_model_original_md(x, ts, merged)
+        return self.ddim_custom_forward(x_in, c_in, bbox, ts=t_in, forward_func=forward_func)
 
     @torch.no_grad()
     def get_noise(self, x_in: Tensor, sigma_in: Tensor, cond_in: CondDict, step: int) -> Tensor:

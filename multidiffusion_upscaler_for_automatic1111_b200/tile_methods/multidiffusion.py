@@ -16,7 +16,7 @@ import torch
 from torch import Tensor
 
 from .. import engine, host
-from ..tile_utils.utils import BBox, custom_bbox, keep_signature
+from ..tile_utils.utils import BBox, BlendMode, CustomBBox, custom_bbox, keep_signature
 from .abstractdiffusion import AbstractDiffusion, CondDict
 
 
@@ -43,7 +43,11 @@ class MultiDiffusion(AbstractDiffusion):
 
     @custom_bbox
     def init_custom_bbox(self, *args):
+        """multidiffusion.py:40-46: a BACKGROUND region counts as one more tile in the weight canvas."""
         super().init_custom_bbox(*args)
+        for bbox in self.custom_bboxes:
+            if bbox.blend_mode == BlendMode.BACKGROUND:
+                self.weights[bbox.slicer] += 1.0
 
     # ------------------------------------------------------- kernel hijacks
     @torch.no_grad()
@@ -57,7 +61,10 @@ class MultiDiffusion(AbstractDiffusion):
             cond_tile = self.repeat_cond_dict(cond, bboxes)
             return self.sampler_forward(x_tile, sigma_tile, cond=cond_tile)
 
-        return self.sample_one_step(x_in, org_func, repeat_func, None)
+        def custom_func(x: Tensor, bbox_id: int, bbox: CustomBBox) -> Tensor:
+            return self.kdiff_custom_forward(x, sigma_in, cond, bbox_id, bbox, self.sampler_forward)
+
+        return self.sample_one_step(x_in, org_func, repeat_func, custom_func)
 
     @torch.no_grad()
     @keep_signature
@@ -74,7 +81,14 @@ class MultiDiffusion(AbstractDiffusion):
                 cond_tile = self.repeat_tensor(cond, n_rep)
             return self.sampler_forward(x_tile, ts_tile, cond=cond_tile)
 
-        return self.sample_one_step(x_in, org_func, repeat_func, None)
+        def custom_func(x: Tensor, bbox_id: int, bbox: CustomBBox) -> Tensor:
+            def forward_func(x, *args, **kwargs):
+                self.set_custom_controlnet_tensors(bbox_id, 2 * x.shape[0])
+                self.set_custom_stablesr_tensors(bbox_id)
+                return self.sampler_forward(x, *args, **kwargs)
+            return self.ddim_custom_forward(x, cond, bbox, ts_in, forward_func)
+
+        return self.sample_one_step(x_in, org_func, repeat_func, custom_func)
 
     def repeat_cond_dict(self, cond_in: CondDict, bboxes: List[BBox]) -> CondDict:
         """Per-batch cond (multidiffusion.py:112-129): text/vector cond repeated, spatial icond cropped per tile."""
@@ -103,7 +117,7 @@ class MultiDiffusion(AbstractDiffusion):
         return r * g.cols + c
 
     def sample_one_step(self, x_in: Tensor, org_func: Callable, repeat_func: Callable, custom_func: Callable) -> Tensor:
-        """One denoiser call over the whole latent, tile by tile (multidiffusion.py:131-218, grid part).
+        """One denoiser call over the whole latent, tile by tile, then region by region (multidiffusion.py:131-218).
 
         Returns a fresh fp32 tensor, as the reference's `torch.where` against the
         fp32 weights does even for fp16 latents.
@@ -115,25 +129,55 @@ class MultiDiffusion(AbstractDiffusion):
             return org_func(x_in)
 
         x = self._check_input(x_in)
-        if not self.draw_background:
-            raise NotImplementedError("draw_background=False needs region prompt control (SURVEY.md section 8(f)-1)")
+        regions = self.enable_custom_bbox and len(self.custom_bboxes) > 0
+        # a BACKGROUND region is added to x_buffer BEFORE the division, so the un-normalised buffer is needed
+        needs_buffer = regions and any(b.blend_mode == BlendMode.BACKGROUND for b in self.custom_bboxes)
 
         if self._shard is not None:
+            if regions:
+                raise NotImplementedError("region prompt control is not combined with the multi-GPU tile shard yet")
             return self._sample_one_step_sharded(x_in, x, repeat_func, N, C)
 
-        tiles = self._scatter_all(x)
-        outs = []
-        for batch_id, bboxes in enumerate(self.batched_bboxes):
-            if host.interrupted():
-                return x_in
-            x_tile = self._tile_batch(tiles, batch_id, N)
-            self.switch_controlnet_tensors(batch_id, N, len(bboxes))
-            self.switch_stablesr_tensors(batch_id)
-            outs.append(repeat_func(x_tile, bboxes))
-            self.update_pbar()
+        x_out = None
+        if self.enable_grid_bbox:
+            tiles = self._scatter_all(x)
+            outs = []
+            for batch_id, bboxes in enumerate(self.batched_bboxes):
+                if host.interrupted():
+                    return x_in
+                x_tile = self._tile_batch(tiles, batch_id, N)
+                self.switch_controlnet_tensors(batch_id, N, len(bboxes))
+                self.switch_stablesr_tensors(batch_id)
+                outs.append(repeat_func(x_tile, bboxes))
+                self.update_pbar()
+            if needs_buffer:
+                self.reset_buffer(x)
+            x_out = engine.blend_multidiffusion(self._grid, outs, N, C, self.tile_bs, self.weights, x.dtype,
+                                                x_buffer=self.x_buffer if needs_buffer else None, flags=self._blend_flags,
+                                                rcp_weights=self._rcp_weights)
+            if not regions:
+                return x_out
+        else:
+            # draw_background=False: only the custom regions paint (multidiffusion.py:146 skips the grid loop)
+            self.reset_buffer(x)
+            self.x_buffer.zero_()
+            needs_buffer = True
 
-        return engine.blend_multidiffusion(self._grid, outs, N, C, self.tile_bs, self.weights, x.dtype,
-                                           x_buffer=None, flags=self._blend_flags, rcp_weights=self._rcp_weights)
+        if not needs_buffer:
+            self.reset_buffer(x)        # shape / dtype template of the feather buffer only
+
+        def add_background(bbox_id: int, bbox: CustomBBox, x_tile_out: Tensor):
+            self.x_buffer[bbox.slicer] += x_tile_out
+
+        feather = self._custom_region_pass(x, custom_func, add_background, poll_interrupt=True)
+        if feather is self._INTERRUPTED:
+            return x_in
+        if needs_buffer:
+            # multidiffusion.py:208 on the buffer that now holds grid tiles + BACKGROUND regions
+            x_out = torch.where(self.weights > 1, self.x_buffer / self.weights, self.x_buffer)
+        if feather is not None:
+            x_out = self._feather_composite(x_out, feather)
+        return x_out
 
     def _sample_one_step_sharded(self, x_in: Tensor, x: Tensor, repeat_func: Callable, N: int, C: int) -> Tensor:
         """This rank's chunk of the tile list, then exchange + deterministic blend (init_tile_shard)."""
@@ -153,7 +197,8 @@ class MultiDiffusion(AbstractDiffusion):
         return self._exchange_and_blend_md(outs, x, N, C)
 
     def get_noise(self, x_in: Tensor, sigma_in: Tensor, cond_in: CondDict, step: int) -> Tensor:
-        """Tiled eps prediction used by noise inversion (multidiffusion.py:220-243, grid part)."""
+        """Tiled eps prediction used by noise inversion (multidiffusion.py:220-243)."""
+        from ..tile_utils.utils import Condition
         cond_orig = cond_in.copy()
         sd_model = self._sd_model()
 
@@ -165,4 +210,12 @@ class MultiDiffusion(AbstractDiffusion):
             cond_out = self.repeat_cond_dict(cond_orig, bboxes)
             return sd_model.apply_model(x_tile, sigma_tile, cond=cond_out)
 
-        return self.sample_one_step(x_in, org_func, repeat_func, None)
+        def custom_func(x: Tensor, bbox_id: int, bbox: CustomBBox):
+            # the region's negative prompt is deliberately not used for noise inversion (multidiffusion.py:233-235)
+            tcond = Condition.reconstruct_cond(bbox.cond, step).unsqueeze_(0)
+            icond = self.get_icond(cond_orig)
+            if tuple(icond.shape[2:]) == (self.h, self.w):
+                icond = icond[bbox.slicer]
+            return sd_model.apply_model(x, sigma_in, cond=self.make_cond_dict(cond_in, tcond, icond))
+
+        return self.sample_one_step(x_in, org_func, repeat_func, custom_func)

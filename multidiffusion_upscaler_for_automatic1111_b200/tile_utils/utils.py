@@ -3,14 +3,17 @@ the C-ABI host functions in csrc/td_host.cpp -- integer results are bit-exact wi
 the reference's Python float64 arithmetic.
 
 In scope: `BBox`, `split_bboxes`, `splitable`,
-`gaussian_weights`, the `Method` / `BlendMode` enums.  Region prompts, feather
-masks and the retouch mask are later rows (section 8(f)) and are not here.
+`gaussian_weights`, the `Method` / `BlendMode` enums; and for region prompt control
+(section 8(f)-1): `BBoxSettings`, `build_bbox_settings`, `CustomBBox`, `feather_mask`
+and the `Prompt` / `Condition` helpers (thin calls into the host's prompt parser).
+The retouch mask of noise inversion is a later row and is not here.
 """
 from __future__ import annotations
 
 import ctypes
+from collections import namedtuple
 from enum import Enum
-from typing import Any, List, Tuple, Union
+from typing import Any, Dict, List, Optional, Tuple, Union
 
 import numpy as np
 import torch
@@ -59,6 +62,26 @@ class BBox:
 
     def __repr__(self):
         return f"BBox(x={self.x}, y={self.y}, w={self.w}, h={self.h})"
+
+
+# one row of the region-control UI (utils.py:41-44)
+BBoxSettings = namedtuple("BBoxSettings", ["enable", "x", "y", "w", "h", "prompt", "neg_prompt", "blend_mode", "feather_ratio", "seed"])
+DEFAULT_BBOX_SETTINGS = BBoxSettings(False, 0.4, 0.4, 0.2, 0.2, "", "", BlendMode.BACKGROUND.value, 0.2, -1)
+NUM_BBOX_PARAMS = len(BBoxSettings._fields)
+
+
+def build_bbox_settings(bbox_control_states: List[Any]) -> Dict[int, BBoxSettings]:
+    """Flat UI state -> {row index: BBoxSettings} (utils.py:47-65): floats rounded to 4 digits, disabled /
+    degenerate rows dropped."""
+    settings: Dict[int, BBoxSettings] = {}
+    for index, lo in enumerate(range(0, len(bbox_control_states), NUM_BBOX_PARAMS)):
+        st = BBoxSettings(*bbox_control_states[lo:lo + NUM_BBOX_PARAMS])
+        st = st._replace(x=round(st.x, 4), y=round(st.y, 4), w=round(st.w, 4), h=round(st.h, 4),
+                         feather_ratio=round(st.feather_ratio, 4), seed=int(st.seed))
+        if not st.enable or st.x > 1.0 or st.y > 1.0 or st.w <= 0.0 or st.h <= 0.0:
+            continue
+        settings[index] = st
+    return settings
 
 
 def _float_ptr(a: np.ndarray):
@@ -117,3 +140,97 @@ stablesr = null_decorator
 grid_bbox = null_decorator
 custom_bbox = null_decorator
 noise_inverse = null_decorator
+
+
+def feather_mask_np(w: int, h: int, ratio: float) -> np.ndarray:
+    out = np.empty((h, w), dtype=np.float32)
+    _cabi.check(_cabi.lib.td_feather_mask(int(w), int(h), float(ratio), _float_ptr(out)))
+    return out
+
+
+def feather_mask(w: int, h: int, ratio: float) -> torch.Tensor:
+    """utils.py:196-214: fp32 [h, w] on the device; 1 inside, (dist/radius)^2 towards the border."""
+    return torch.from_numpy(feather_mask_np(w, h, ratio)).to(host.device())
+
+
+def custom_bbox_rect(x: float, y: float, w: float, h: float, canvas_w: int, canvas_h: int) -> Optional[Tuple[int, int, int, int]]:
+    """Relative UI rectangle -> latent (x, y, w, h) (abstractdiffusion.py:206-215); None if the row is skipped."""
+    out = (ctypes.c_int32 * 4)()
+    if _cabi.check(_cabi.lib.td_custom_bbox_rect(float(x), float(y), float(w), float(h), int(canvas_w), int(canvas_h), out)) == 0:
+        return None
+    return int(out[0]), int(out[1]), int(out[2]), int(out[3])
+
+
+class CustomBBox(BBox):
+    """Region-control bbox (utils.py:84-99): a BBox plus its prompts, layer type, feather mask and seed."""
+
+    __slots__ = ("prompt", "neg_prompt", "blend_mode", "feather_ratio", "seed", "feather_mask", "cond",
+                 "extra_network_data", "uncond")
+
+    def __init__(self, x: int, y: int, w: int, h: int, prompt: str, neg_prompt: str, blend_mode: str,
+                 feather_radio: float, seed: int):
+        super().__init__(x, y, w, h)
+        self.prompt = prompt
+        self.neg_prompt = neg_prompt
+        self.blend_mode = BlendMode(blend_mode)
+        self.feather_ratio = max(min(feather_radio, 1.0), 0.0)
+        self.seed = seed
+        self.feather_mask = feather_mask(self.w, self.h, self.feather_ratio) if self.blend_mode == BlendMode.FOREGROUND else None
+        self.cond = None                  # MulticondLearnedConditioning of (global prompt, region prompt)
+        self.extra_network_data = None    # parsed <lora:...> tags of the region prompt
+        self.uncond = None                # learned conditioning of (global negative, region negative)
+
+
+class Prompt:
+    """utils.py:100-112."""
+
+    @staticmethod
+    def apply_styles(prompts: List[str], styles=None) -> List[str]:
+        if not styles:
+            return prompts
+        shared = host.get_shared()
+        return [shared.prompt_styles.apply_styles_to_prompt(p, styles) for p in prompts]
+
+    @staticmethod
+    def append_prompt(prompts: List[str], prompt: str = "") -> List[str]:
+        if not prompt:
+            return prompts
+        return [f"{p}, {prompt}" for p in prompts]
+
+
+class Condition:
+    """CLIP conditioning through the host application's prompt parser (utils.py:114-147).  Outside the WebUI
+    there is no text encoder: every method raises RuntimeError naming the missing module."""
+
+    @staticmethod
+    def _module(name: str):
+        m = host.a1111_module(name)
+        if m is None:
+            raise RuntimeError(f"region prompts need the WebUI's modules.{name}; it is not importable here")
+        return m
+
+    @staticmethod
+    def get_custom_cond(prompts: List[str], prompt: str, steps: int, styles=None):
+        prompt = Prompt.apply_styles([prompt], styles)[0]
+        _, extra_network_data = Condition._module("extra_networks").parse_prompts([prompt])
+        prompts = Prompt.apply_styles(Prompt.append_prompt(prompts, prompt), styles)
+        return Condition.get_cond(prompts, steps), extra_network_data
+
+    @staticmethod
+    def get_cond(prompts: List[str], steps: int):
+        prompts, _ = Condition._module("extra_networks").parse_prompts(prompts)
+        return Condition._module("prompt_parser").get_multicond_learned_conditioning(host.get_shared().sd_model, prompts, steps)
+
+    @staticmethod
+    def get_uncond(neg_prompts: List[str], steps: int, styles=None):
+        neg_prompts = Prompt.apply_styles(neg_prompts, styles)
+        return Condition._module("prompt_parser").get_learned_conditioning(host.get_shared().sd_model, neg_prompts, steps)
+
+    @staticmethod
+    def reconstruct_cond(cond, step: int) -> torch.Tensor:
+        _, tensor = Condition._module("prompt_parser").reconstruct_multicond_batch(cond, step)
+        return tensor
+
+    @staticmethod
+    def reconstruct_uncond(uncond, step: int) -> torch.Tensor:
+        return Condition._module("prompt_parser").reconstruct_cond_batch(uncond, step)

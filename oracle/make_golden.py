@@ -65,6 +65,91 @@ DEMO_CFG = dict(N=2, C=4, H=48, W=64, scale=2, window=24, overlap=12, tile_bs=4,
                 current_step=3, t_enc=14)
 
 
+# region prompt control: rows of the UI (enable, x, y, w, h, prompt, neg_prompt, blend_mode, feather_ratio, seed)
+_BG, _FG = "Background", "Foreground"
+REGION_GRID = dict(N=2, C=4, W=64, H=48, tw=16, th=16, ov=8, bs=4)
+REGION_CASES = [  # name, draw_background, rows
+    ("bg_fg", True, [(True, 0.1, 0.2, 0.5, 0.4, "a cat", "", _BG, 0.2, -1),
+                     (False, 0.0, 0.0, 0.3, 0.3, "off", "", _BG, 0.2, -1),
+                     (True, 0.4, 0.3, 0.45, 0.6, "a dog", "ugly", _FG, 0.3, 5),
+                     (True, 1.2, 0.3, 0.2, 0.2, "outside", "", _FG, 0.3, 5),
+                     (True, 0.55, 0.05, 0.6, 0.7, "a bird", "", _FG, 0.8, 7)]),
+    ("no_background", False, [(True, 0.0, 0.0, 0.7, 0.8, "left", "", _BG, 0.2, -1),
+                              (True, 0.3, 0.25, 0.7, 0.75, "right", "", _BG, 0.2, -1),
+                              (True, 0.25, 0.3, 0.4, 0.4, "middle", "", _FG, 1.0, 3)]),
+    ("fg_only", True, [(True, 0.2, 0.2, 0.33, 0.5, "one", "", _FG, 0.5, 1),
+                       (True, 0.3, 0.4, 0.5, 0.5, "two", "", _FG, 0.0, 2)]),
+    ("bg_only", True, [(True, 0.05, 0.1, 0.9, 0.3, "strip", "", _BG, 0.2, -1),
+                       (True, 0.5, 0.0, 0.5, 1.0, "half", "", _BG, 0.2, -1)]),
+]
+REGION_DTYPES = ("f16", "f32")
+
+
+def run_reference_region_step(ref, method: str, x: torch.Tensor, draw_background: bool, rows):
+    """One step of the reference WITH custom bboxes; grid UNet = synth.fake_denoise, region UNet = synth.fake_region_denoise."""
+    c = REGION_GRID
+    N = x.shape[0]
+    p = ref_shim.make_p(c["W"] * 8, c["H"] * 8)
+    cond = {"c_crossattn": [torch.zeros(N, 2, 4)], "c_concat": [torch.zeros(N, 5, 1, 1)]}
+    state = {}
+
+    def unet(x_tile, sigma, cond=None):
+        return synth.fake_denoise(x_tile, state["bboxes"], N)
+
+    sampler = ref_shim.make_kdiff_sampler(unet)
+    cls = ref.multidiffusion.MultiDiffusion if method == "md" else ref.mixtureofdiffusers.MixtureOfDiffusers
+    d = cls(p, sampler)
+    d.init_grid_bbox(c["tw"], c["th"], c["ov"], c["bs"])
+    settings = {i: ref.utils.BBoxSettings(*row) for i, row in enumerate(rows)}
+    d.init_custom_bbox(settings, draw_background, False)
+    d.init_done()
+    d.pbar.disable = True
+
+    def custom_func(x_tile, bbox_id, bbox):
+        return synth.fake_region_denoise(x_tile, bbox_id)
+
+    if method == "md":
+        def repeat_func(x_tile, bboxes):
+            state["bboxes"] = bboxes
+            return unet(x_tile, None)
+        out = d.sample_one_step(x, None, repeat_func, custom_func)
+    else:
+        batches = iter(d.batched_bboxes)
+
+        def apply_model(x_tile, t, c_):
+            state["bboxes"] = next(batches)
+            return unet(x_tile, None)
+        ref.shared.sd_model.apply_model = apply_model
+        d.custom_apply_model = lambda x_tile, t, c_, bbox_id, bbox: custom_func(x_tile, bbox_id, bbox)   # instance attribute
+        d.hook()
+        try:
+            out = ref.shared.sd_model.apply_model(x, torch.ones(N), cond)
+        finally:
+            d.unhook()
+    return d, out.clone()
+
+
+def gen_region(ref):
+    """9. region prompt control (custom bboxes): feather masks, rectangles, weights and one full step ------------"""
+    c = REGION_GRID
+    out = {}
+    masks = [(10, 8, 0.5), (29, 29, 0.3), (39, 34, 0.8), (26, 20, 1.0), (33, 24, 0.0), (7, 5, 0.2), (64, 48, 0.2)]
+    for (w, h, r) in masks:
+        out[f"mask_{w}x{h}_{r}"] = ref.utils.feather_mask(w, h, r).numpy()
+    out["mask_cases"] = np.array(masks, np.float64)
+    for name, bg, rows in REGION_CASES:
+        for method in ("md", "mod"):
+            for dn in REGION_DTYPES:
+                x = synth.latent(synth.case_seed("region_" + name, dn), (c["N"], c["C"], c["H"], c["W"]), DTYPES[dn])
+                d, o = run_reference_region_step(ref, method, x, bg, rows)
+                key = f"{name}_{method}_{dn}"
+                out[key] = _bits(o)
+                out[key + "_dtype"] = np.array(str(o.dtype))
+            out[f"{name}_{method}_weights"] = d.weights[0, 0].numpy()
+            out[f"{name}_rects"] = np.array([(b.x, b.y, b.w, b.h) for b in d.custom_bboxes], np.int32)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "region_small.npz"), **out)
+
+
 def demo_denoise(x_tile, *_a, **_k):
     """Deterministic stand-in for the UNet in the DemoFusion fixtures (exact: scale by 0.5)."""
     return (x_tile.float() * 0.5).to(x_tile.dtype)
@@ -162,6 +247,9 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     ref = ref_shim.load()
     torch.set_num_threads(1)
+    if "region" in sys.argv[1:]:      # regenerate only region_small.npz
+        gen_region(ref)
+        return
 
     # 1. split_bboxes sweep (utils.py:160-177) ------------------------------------
     cases, counts, flat = [], [], []
@@ -273,6 +361,8 @@ def main():
         out[name + "_local"] = np.array([(b.x, b.y, b.w, b.h) for bb in d.batched_bboxes for b in bb], np.int32)
         out[name + "_tile_bs"] = np.array([d.tile_bs, d.global_tile_bs, d.global_num_tiles], np.int32)
     np.savez_compressed(os.path.join(GOLDEN_DIR, "demofusion_small.npz"), **out)
+
+    gen_region(ref)
 
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))

@@ -54,6 +54,42 @@ def _mod(name: str, **attrs) -> types.ModuleType:
     return m
 
 
+# --- deterministic stand-in for the WebUI's prompt parser (region prompt control tests) ---------------------------
+# A "conditioning" is just the tuple of prompt strings; reconstructing it at a sampler step yields a tensor
+# [len(prompts), 77 * chunks, 8] whose values depend on the prompt text and the step, chunks = 1 + len(prompt) // 40
+# (so that long prompts have a different token count, like the real CLIP chunking).
+FAKE_TOKEN_DIM = 8
+
+
+def _fake_tokens(prompts, step):
+    import hashlib
+
+    import torch
+    chunks = max(1 + len(p) // 40 for p in prompts)
+    rows = []
+    for p in prompts:
+        h = int.from_bytes(hashlib.sha256(f"{p}|{step}".encode()).digest()[:4], "little")
+        base = (h % 997) / 997.0
+        rows.append(base + torch.arange(77 * chunks * FAKE_TOKEN_DIM, dtype=torch.float32).view(77 * chunks, FAKE_TOKEN_DIM) / 4096.0)
+    return torch.stack(rows)
+
+
+def fake_multicond(model, prompts, steps):
+    return ("multicond", tuple(prompts), steps)
+
+
+def fake_learned(model, prompts, steps):
+    return ("learned", tuple(prompts), steps)
+
+
+def fake_reconstruct_multicond(cond, step):
+    return None, _fake_tokens(cond[1], step)
+
+
+def fake_reconstruct_cond(cond, step):
+    return _fake_tokens(cond[1], step)
+
+
 _installed = False
 
 
@@ -106,8 +142,11 @@ def install(device: str = "cpu"):
     _mod("modules.shared", state=_State(), sd_model=sd_model, opts=_Opts(), cmd_opts=_CmdOpts(),
          batch_cond_uncond=True, State=_State)
     _mod("modules.shared_state", State=_State)
-    _mod("modules.prompt_parser", MulticondLearnedConditioning=_Dummy, ScheduledPromptConditioning=_Dummy)
-    _mod("modules.extra_networks", ExtraNetworkParams=_Dummy)
+    _mod("modules.prompt_parser", MulticondLearnedConditioning=_Dummy, ScheduledPromptConditioning=_Dummy,
+         get_multicond_learned_conditioning=fake_multicond, get_learned_conditioning=fake_learned,
+         reconstruct_multicond_batch=fake_reconstruct_multicond, reconstruct_cond_batch=fake_reconstruct_cond)
+    _mod("modules.extra_networks", ExtraNetworkParams=_Dummy, parse_prompts=lambda prompts: (list(prompts), {}),
+         activate=lambda p, data: None, deactivate=lambda p, data: None)
     _mod("modules.sd_samplers_common")
     _mod("modules.processing", opt_f=8, StableDiffusionProcessing=_Dummy,
          StableDiffusionProcessingImg2Img=_Dummy, Processed=_Dummy)
@@ -161,7 +200,8 @@ def load(device: str = "cpu"):
 def make_p(width: int, height: int, sampler_name: str = "Euler a"):
     """Minimal StableDiffusionProcessing stand-in (abstractdiffusion.py:6-33)."""
     return types.SimpleNamespace(width=width, height=height, sampler_name=sampler_name,
-                                 disable_extra_networks=True, batch_size=1)
+                                 disable_extra_networks=True, batch_size=1, steps=20, styles=None,
+                                 all_prompts=["a photo"], all_negative_prompts=["blurry"])
 
 
 def make_kdiff_sampler(inner_forward):

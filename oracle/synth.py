@@ -43,3 +43,10 @@ def fake_denoise(x_tile: torch.Tensor, bboxes, n_per_tile: int) -> torch.Tensor:
         scales += [tile_scale(int(bx), int(by))] * n_per_tile
     s = torch.tensor(scales, dtype=torch.float32, device=x_tile.device).view(-1, 1, 1, 1)
     return (x_tile.float() * s).to(x_tile.dtype)
+
+
+def fake_region_denoise(x_tile: torch.Tensor, region_id: int) -> torch.Tensor:
+    """Deterministic stand-in for the UNet on a custom region (region prompt control): a per-region power-of-two
+    factor, exact in every dtype on CPU and GPU alike."""
+    scale = (0.5, -1.0, 2.0, 1.0, -0.5)[region_id % 5]
+    return (x_tile.float() * scale).to(x_tile.dtype)

@@ -104,8 +104,8 @@ def test_out_of_scope_inits_raise():
     for fn in (d.init_noise_inverse, d.init_controlnet, d.init_stablesr):
         with pytest.raises(NotImplementedError):
             fn()
-    with pytest.raises(NotImplementedError):
-        d.init_custom_bbox({}, True, False)
+    d.init_custom_bbox({}, True, False)      # region prompt control is on the path: no rows -> switched off again
+    assert d.enable_custom_bbox is False and d.custom_bboxes == []
 
 
 def test_repeat_tensor_semantics():
