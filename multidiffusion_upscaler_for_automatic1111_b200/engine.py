@@ -33,6 +33,20 @@ def grid_bboxes_xywh(g: TdGrid) -> np.ndarray:
     return out.reshape(-1, 4)
 
 
+def scaled_grid(g: TdGrid, scale: int) -> TdGrid:
+    """The same tile plan in a space `scale` times finer: pixel-space side inputs (ControlNet hints, x8) are cropped
+    with the latent tile list multiplied by opt_f (abstractdiffusion.py:499)."""
+    s = TdGrid()
+    s.H, s.W = g.H * scale, g.W * scale
+    s.tile_h, s.tile_w, s.overlap = g.tile_h * scale, g.tile_w * scale, g.overlap * scale
+    s.rows, s.cols, s.num_tiles, s.num_batches, s.tile_bs = g.rows, g.cols, g.num_tiles, g.num_batches, g.tile_bs
+    for i in range(g.rows):
+        s.ys[i] = g.ys[i] * scale
+    for i in range(g.cols):
+        s.xs[i] = g.xs[i] * scale
+    return s
+
+
 def grid_weights(g: TdGrid, tile_weights: Optional[np.ndarray] = None) -> np.ndarray:
     """fp32 [H, W] host weight canvas (utils.py:167,175)."""
     out = np.empty((g.H, g.W), dtype=np.float32)

@@ -10,8 +10,10 @@ What differs from the reference by design:
   * Region prompt control is built on the same kernels: the grid tiles go through the
     fused blend (which then also returns the un-normalised `x_buffer`), the handful of custom regions are cropped,
     added and feather-composited with the reference's own tensor expressions.
-  * ControlNet / StableSR tile caches and noise inversion are later rows of the scope table (section 8(f)-2/3):
-    their `init_*` raise NotImplementedError instead of silently doing something else.
+  * ControlNet / StableSR tile caches (section 8(f)-2) are the scatter kernel applied to the side inputs: one launch
+    per hint on the tile plan scaled to pixel space, the per-batch caches are views of that one tensor.
+  * Noise inversion is a later row of the scope table (section 8(f)-3): `init_noise_inverse` raises
+    NotImplementedError instead of silently doing something else.
 """
 from __future__ import annotations
 
@@ -76,10 +78,21 @@ class AbstractDiffusion:
         self.draw_background: bool = True
         self.causal_layers: Optional[bool] = None
 
-        # noise inversion / controlnet / stablesr (not on this path yet)
+        # noise inversion (not on this path yet)
         self.noise_inverse_enabled: bool = False
+
+        # ext. ControlNet / StableSR side inputs (abstractdiffusion.py:62-75)
         self.enable_controlnet: bool = False
+        self.controlnet_script = None
+        self.control_tensor_batch = None
+        self.control_params = None
+        self.control_tensor_cpu: bool = False
+        self.control_tensor_custom: list = []
         self.enable_stablesr: bool = False
+        self.stablesr_script = None
+        self.stablesr_tensor: Optional[Tensor] = None
+        self.stablesr_tensor_batch = None
+        self.stablesr_tensor_custom: list = []
 
         # B200 engine state
         self._grid = None                     # td_grid plan
@@ -308,12 +321,6 @@ class AbstractDiffusion:
         step = self.sampler.model_wrap_cfg.step
         return Condition.reconstruct_cond(custom_cond, step), Condition.reconstruct_uncond(custom_uncond, step), image_conditioning
 
-    def set_custom_controlnet_tensors(self, bbox_id: int, repeat_size: int):
-        pass
-
-    def set_custom_stablesr_tensors(self, bbox_id: int):
-        pass
-
     def _forward_region(self, bbox_id: int, forward_func: Callable, x: Tensor, sigma: Tensor, original_cond: CondDict,
                         tcond: Tensor, icond) -> Tensor:
         self.set_custom_controlnet_tensors(bbox_id, x.shape[0])
@@ -467,22 +474,143 @@ class AbstractDiffusion:
     def init_noise_inverse(self, *args, **kwargs):
         raise NotImplementedError("Tiled noise inversion is not on the B200 hot path yet (SURVEY.md section 8(f)-3)")
 
+    # ------------------------------------ side-input tile caches (ControlNet, StableSR)
+    def _crop_side_input(self, t: Tensor, scale: int) -> Tensor:
+        """Every grid tile of a side input [B, C, H*scale, W*scale] in one scatter launch: [T*B, C, th*scale, tw*scale],
+        tile-major -- what the reference builds with T slice views and one `cat` per batch (abstractdiffusion.py:494-503)."""
+        dev = host.device()
+        if t.device != dev:
+            t = t.to(dev)
+        g = self._grid if scale == 1 else engine.scaled_grid(self._grid, scale)
+        return engine.scatter_tiles(g, t.contiguous(), flags=self._blend_flags)
+
+    def _batch_rows(self, tiles: Tensor, batch_id: int, rows_per_tile: int) -> Tensor:
+        lo = batch_id * self.tile_bs * rows_per_tile
+        hi = min((batch_id + 1) * self.tile_bs, self.num_tiles) * rows_per_tile
+        return tiles[lo:hi]
+
     @controlnet
-    def init_controlnet(self, *args, **kwargs):
-        raise NotImplementedError("ControlNet tile caches are not on the B200 hot path yet (SURVEY.md section 8(f)-2)")
+    def init_controlnet(self, controlnet_script, control_tensor_cpu: bool):
+        """abstractdiffusion.py:454-464."""
+        self.enable_controlnet = True
+        self.controlnet_script = controlnet_script
+        self.control_tensor_cpu = control_tensor_cpu
+        self.control_tensor_batch = None
+        self.control_params = None
+        self.control_tensor_custom = []
+        self.prepare_controlnet_tensors()
+
+    @controlnet
+    def reset_controlnet_tensors(self):
+        """Give the ControlNet its full-size hints back (abstractdiffusion.py:466-472)."""
+        if not self.enable_controlnet or self.control_tensor_batch is None:
+            return
+        for param_id in range(len(self.control_params)):
+            self.control_params[param_id].hint_cond = self.org_control_tensor_batch[param_id]
+
+    @controlnet
+    def prepare_controlnet_tensors(self, refresh: bool = False):
+        """Crop every ControlNet hint into the tile batches once and cache them (abstractdiffusion.py:474-518).
+        Hints live in pixel space: the tile list is scaled by opt_f.  The tiles of one hint sit in ONE tensor
+        (a scatter launch); `control_tensor_batch[param][batch]` are views of it."""
+        if not refresh and (self.control_tensor_batch is not None or self.control_params is not None):
+            return
+        if not self.enable_controlnet or self.controlnet_script is None:
+            return
+        latest_network = self.controlnet_script.latest_network
+        if latest_network is None or not hasattr(latest_network, "control_params"):
+            return
+        self.control_params = latest_network.control_params
+        tensors = [param.hint_cond for param in latest_network.control_params]
+        self.org_control_tensor_batch = tensors
+        if len(tensors) == 0:
+            return
+
+        self.control_tensor_batch = []
+        self.control_tensor_custom = []                 # (the reference keeps stale entries here on refresh)
+        for control_tensor in tensors:
+            if control_tensor.dim() == 3:
+                control_tensor.unsqueeze_(0)            # in place, like the reference: the param sees 4-d from now on
+            per_batch = []
+            if self.enable_grid_bbox or self.batched_bboxes:
+                tiles = self._crop_side_input(control_tensor, opt_f)
+                rows = control_tensor.shape[0]
+                for batch_id in range(len(self.batched_bboxes)):
+                    tile = self._batch_rows(tiles, batch_id, rows)
+                    per_batch.append(tile.cpu() if self.control_tensor_cpu else tile)
+            self.control_tensor_batch.append(per_batch)
+            if len(self.custom_bboxes) > 0:
+                custom = []
+                for bbox in self.custom_bboxes:
+                    tile = control_tensor[:, :, bbox[1] * opt_f:bbox[3] * opt_f, bbox[0] * opt_f:bbox[2] * opt_f]
+                    custom.append(tile.cpu() if self.control_tensor_cpu else tile)
+                self.control_tensor_custom.append(custom)
+
+    @controlnet
+    def switch_controlnet_tensors(self, batch_id: int, x_batch_size: int, tile_batch_size: int, is_denoise=False):
+        """Point every ControlNet at the hint tiles of this tile batch (abstractdiffusion.py:520-535): k-diffusion
+        wants each tile's hint x_batch_size times in a row, DDIM the whole batch repeated."""
+        if not self.enable_controlnet or self.control_tensor_batch is None:
+            return
+        for param_id in range(len(self.control_params)):
+            control_tile = self.control_tensor_batch[param_id][batch_id]
+            if self.is_kdiff:
+                control_tile = control_tile[:tile_batch_size].repeat_interleave(x_batch_size, dim=0)
+            else:
+                control_tile = control_tile.repeat([x_batch_size if is_denoise else x_batch_size * 2, 1, 1, 1])
+            self.control_params[param_id].hint_cond = control_tile.to(host.device())
+
+    @controlnet
+    def set_custom_controlnet_tensors(self, bbox_id: int, repeat_size: int):
+        """abstractdiffusion.py:537-544."""
+        if not self.enable_controlnet or not len(self.control_tensor_custom):
+            return
+        for param_id in range(len(self.control_params)):
+            control_tensor = self.control_tensor_custom[param_id][bbox_id].to(host.device())
+            self.control_params[param_id].hint_cond = control_tensor.repeat((repeat_size, 1, 1, 1))
 
     @stablesr
-    def init_stablesr(self, *args, **kwargs):
-        raise NotImplementedError("StableSR tile caches are not on the B200 hot path yet (SURVEY.md section 8(f)-2)")
+    def init_stablesr(self, stablesr_script):
+        """abstractdiffusion.py:547-568: StableSR hands over its latent image through a hook; it is cropped into the
+        tile batches (latent space, the grid as is) with one scatter launch."""
+        if stablesr_script.stablesr_model is None:
+            return
+        self.stablesr_script = stablesr_script
 
-    def reset_controlnet_tensors(self):
-        pass
+        def set_image_hook(latent_image):
+            self.enable_stablesr = True
+            self.stablesr_tensor = latent_image
+            self.stablesr_tensor_batch = []
+            if self.batched_bboxes:
+                tiles = self._crop_side_input(latent_image, 1)
+                rows = latent_image.shape[0]
+                self.stablesr_tensor_batch = [self._batch_rows(tiles, b, rows) for b in range(len(self.batched_bboxes))]
+            if len(self.custom_bboxes) > 0:
+                self.stablesr_tensor_custom = [latent_image[:, :, bbox[1]:bbox[3], bbox[0]:bbox[2]] for bbox in self.custom_bboxes]
 
-    def switch_controlnet_tensors(self, batch_id: int, x_batch_size: int, tile_batch_size: int, is_denoise=False):
-        pass
+        stablesr_script.stablesr_model.set_image_hooks["TiledDiffusion"] = set_image_hook
 
+    @stablesr
+    def reset_stablesr_tensors(self):
+        if not self.enable_stablesr or self.stablesr_script.stablesr_model is None:
+            return
+        self.stablesr_script.stablesr_model.latent_image = self.stablesr_tensor
+
+    @stablesr
     def switch_stablesr_tensors(self, batch_id: int):
-        pass
+        if not self.enable_stablesr or self.stablesr_script.stablesr_model is None:
+            return
+        if self.stablesr_tensor_batch is None:
+            return
+        self.stablesr_script.stablesr_model.latent_image = self.stablesr_tensor_batch[batch_id]
+
+    @stablesr
+    def set_custom_stablesr_tensors(self, bbox_id: int):
+        if not self.enable_stablesr or self.stablesr_script.stablesr_model is None:
+            return
+        if not len(getattr(self, "stablesr_tensor_custom", [])):
+            return
+        self.stablesr_script.stablesr_model.latent_image = self.stablesr_tensor_custom[bbox_id]
 
     # ----------------------------------------------------------- engine glue
     def _check_input(self, x_in: Tensor) -> Tensor:

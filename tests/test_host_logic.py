@@ -101,9 +101,8 @@ def test_cpu_tensor_is_refused_not_emulated():
 def test_out_of_scope_inits_raise():
     from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
     d = MultiDiffusion(_p(), _sampler())
-    for fn in (d.init_noise_inverse, d.init_controlnet, d.init_stablesr):
-        with pytest.raises(NotImplementedError):
-            fn()
+    with pytest.raises(NotImplementedError):
+        d.init_noise_inverse()
     d.init_custom_bbox({}, True, False)      # region prompt control is on the path: no rows -> switched off again
     assert d.enable_custom_bbox is False and d.custom_bboxes == []
 
