@@ -145,3 +145,19 @@ def extra_networks_deactivate(p, data) -> None:
             m.deactivate(p, data)
     else:
         m.deactivate(p, data)
+
+
+def setup_img2img_steps(p, steps=None):
+    """modules.sd_samplers_common.setup_img2img_steps; without the WebUI: its plain rule (steps, t_enc)."""
+    m = _a1111("sd_samplers_common")
+    if m is not None and hasattr(m, "setup_img2img_steps"):
+        return m.setup_img2img_steps(p, steps)
+    steps = steps if steps is not None else p.steps
+    return steps, int(min(getattr(p, "denoising_strength", 1.0), 0.999) * steps)
+
+
+def store_latent(x) -> None:
+    """Live-preview hook of the WebUI (sd_samplers_common.store_latent); no-op elsewhere."""
+    m = _a1111("sd_samplers_common")
+    if m is not None and hasattr(m, "store_latent"):
+        m.store_latent(x)

@@ -12,12 +12,12 @@ What differs from the reference by design:
     added and feather-composited with the reference's own tensor expressions.
   * ControlNet / StableSR tile caches (section 8(f)-2) are the scatter kernel applied to the side inputs: one launch
     per hint on the tile plan scaled to pixel space, the per-batch caches are views of that one tensor.
-  * Noise inversion is a later row of the scope table (section 8(f)-3): `init_noise_inverse` raises
-    NotImplementedError instead of silently doing something else.
+  * Tiled noise inversion (section 8(f)-3) is the Euler inversion loop of the reference around our tiled `get_noise`.
 """
 from __future__ import annotations
 
 import math
+from types import MethodType
 from typing import Callable, Dict, List, Optional, Tuple, Union
 
 import torch
@@ -25,8 +25,8 @@ from torch import Tensor
 
 from .. import engine, host
 from ..host import opt_f
-from ..tile_utils.utils import (BBox, BlendMode, Condition, CustomBBox, Prompt, custom_bbox, custom_bbox_rect, grid_bbox,
-                                noise_inverse, controlnet, stablesr)
+from ..tile_utils.utils import (BBox, BlendMode, Condition, CustomBBox, Prompt, custom_bbox, custom_bbox_rect, get_retouch_mask,
+                                grid_bbox, keep_signature, noise_inverse, controlnet, stablesr)
 
 CondDict = Dict[str, Union[Tensor, List[Tensor]]]
 
@@ -78,8 +78,15 @@ class AbstractDiffusion:
         self.draw_background: bool = True
         self.causal_layers: Optional[bool] = None
 
-        # noise inversion (not on this path yet)
+        # tiled noise inversion (abstractdiffusion.py:52-60)
         self.noise_inverse_enabled: bool = False
+        self.noise_inverse_steps: Optional[int] = None
+        self.noise_inverse_retouch: Optional[float] = None
+        self.noise_inverse_renoise_strength: Optional[float] = None
+        self.noise_inverse_renoise_kernel: Optional[int] = None
+        self.noise_inverse_get_cache = None
+        self.noise_inverse_set_cache = None
+        self.sample_img2img_original = None
 
         # ext. ControlNet / StableSR side inputs (abstractdiffusion.py:62-75)
         self.enable_controlnet: bool = False
@@ -469,10 +476,153 @@ class AbstractDiffusion:
         mask = torch.where(count > 1, mask / count, mask)
         return torch.where(count > 0, x_out * (1 - mask) + buf * mask, x_out)
 
-    # ------------------------------------------- later rows of the scope table
+    # -------------------------------------------------- tiled noise inversion
     @noise_inverse
-    def init_noise_inverse(self, *args, **kwargs):
-        raise NotImplementedError("Tiled noise inversion is not on the B200 hot path yet (SURVEY.md section 8(f)-3)")
+    def init_noise_inverse(self, steps: int, retouch: float, get_cache_callback, set_cache_callback, renoise_strength: float,
+                           renoise_kernel: int):
+        """abstractdiffusion.py:591-602: img2img then starts from noise recovered by inverting the input image with the
+        tiled denoiser instead of fresh noise; the sampler's `sample_img2img` is replaced for this job."""
+        self.noise_inverse_enabled = True
+        self.noise_inverse_steps = steps
+        self.noise_inverse_retouch = float(retouch)
+        self.noise_inverse_renoise_strength = float(renoise_strength)
+        self.noise_inverse_renoise_kernel = int(renoise_kernel)
+        if self.sample_img2img_original is None:
+            self.sample_img2img_original = self.sampler_raw.sample_img2img
+        self.sampler_raw.sample_img2img = MethodType(self.sample_img2img, self.sampler_raw)
+        self.noise_inverse_set_cache = set_cache_callback
+        self.noise_inverse_get_cache = get_cache_callback
+
+    def _renoise_mask(self, p, noise: Tensor) -> Optional[Tensor]:
+        """Per-pixel share of fresh noise (abstractdiffusion.py:611-621): 1 - retouch map of the grayscale input,
+        bilinearly resized to the latent, times the strength, clamped to [0, 1]."""
+        if not self.noise_inverse_renoise_strength > 0:
+            return None
+        import numpy as np
+        import torch.nn.functional as F
+        gray = p.init_images[0].convert("L")
+        mask = torch.from_numpy(get_retouch_mask(np.asarray(gray), self.noise_inverse_renoise_kernel)).to(noise.device)
+        mask = 1 - F.interpolate(mask.unsqueeze(0).unsqueeze(0), size=noise.shape[-2:], mode="bilinear").squeeze(0).squeeze(0)
+        mask *= self.noise_inverse_renoise_strength
+        return torch.clamp(mask, 0, 1)
+
+    def _cached_inversion(self, p, prompts: List[str], noise: Tensor) -> Optional[Tensor]:
+        """The previous run's inverted latent when checkpoint, image, prompts and parameters are unchanged
+        (abstractdiffusion.py:625-640)."""
+        c = self.noise_inverse_get_cache()
+        if c is None:
+            return None
+        same = (c.model_hash == p.sd_model.sd_model_hash and c.noise_inversion_steps == self.noise_inverse_steps
+                and len(c.prompts) == len(prompts) and all(c.prompts[i] == prompts[i] for i in range(len(prompts)))
+                and abs(c.retouch - self.noise_inverse_retouch) < 0.01 and c.x0.shape == p.init_latent.shape
+                and torch.abs(c.x0.to(p.init_latent.device) - p.init_latent).sum() < 100)
+        if not same:
+            return None
+        print("[Tiled Diffusion] Noise Inversion reuses the cached noise of the previous run (inputs unchanged).")
+        return c.xt.to(noise.device)
+
+    def _region_only_noise(self, noise: Tensor) -> Tensor:
+        """Without a background layer only the regions are painted: keep the fresh noise under BACKGROUND regions and
+        feather it under FOREGROUND regions (abstractdiffusion.py:657-673)."""
+        shape = (1, 1, noise.shape[2], noise.shape[3])
+        bg_count = torch.zeros(shape, device=noise.device)
+        fg_noise = torch.zeros_like(noise)
+        fg_weight = torch.zeros(shape, device=noise.device)
+        fg_count = torch.zeros(shape, device=noise.device)
+        for bbox in self.custom_bboxes:
+            if bbox.blend_mode == BlendMode.BACKGROUND:
+                bg_count[bbox.slicer] += 1
+            elif bbox.blend_mode == BlendMode.FOREGROUND:
+                fg_noise[bbox.slicer] += noise[bbox.slicer]
+                fg_weight[bbox.slicer] += bbox.feather_mask.to(noise.device)
+                fg_count[bbox.slicer] += 1
+        bg_noise = torch.where(bg_count > 0, noise, 0)
+        fg_noise = torch.where(fg_count > 0, fg_noise / fg_count, 0)
+        fg_weight = torch.where(fg_count > 0, fg_weight / fg_count, 0)
+        return bg_noise * (1 - fg_weight) + fg_noise * fg_weight
+
+    @noise_inverse
+    @keep_signature
+    def sample_img2img(self, sampler, p, x: Tensor, noise: Tensor, conditioning, unconditional_conditioning, steps=None,
+                       image_conditioning=None):
+        """Replacement for `sampler.sample_img2img` (abstractdiffusion.py:604-679): recover (or reuse) the inverted
+        latent, turn it into the noise the sampler expects, blend fresh noise back in where the image has detail,
+        and hand over to the original img2img sampling."""
+        renoise_mask = self._renoise_mask(p, noise)
+        prompts = p.all_prompts[:p.batch_size]
+
+        latent = self._cached_inversion(p, prompts, noise)
+        if latent is None:
+            state = host.get_shared().state
+            state.job_count += 1
+            latent = self.find_noise_for_image_sigma_adjustment(sampler.model_wrap, self.noise_inverse_steps, prompts)
+            state.nextjob()
+            self.noise_inverse_set_cache(p.init_latent.clone().cpu(), latent.clone().cpu(), prompts)
+
+        adjusted_steps, _ = host.setup_img2img_steps(p, steps)
+        sigmas = sampler.get_sigmas(p, adjusted_steps)
+        inverse_noise = latent - (p.init_latent / sigmas[0])
+
+        if renoise_mask is not None:
+            if not self.enable_grid_bbox:
+                noise = self._region_only_noise(noise)
+            combined_noise = ((1 - renoise_mask) * inverse_noise + renoise_mask * noise) / ((renoise_mask ** 2 + (1 - renoise_mask) ** 2) ** 0.5)
+        else:
+            combined_noise = inverse_noise
+        return self.sample_img2img_original(p, x, combined_noise, conditioning, unconditional_conditioning, steps, image_conditioning)
+
+    @noise_inverse
+    @torch.no_grad()
+    def find_noise_for_image_sigma_adjustment(self, dnw, steps: int, prompts: List[str]) -> Tensor:
+        """Euler integration of the probability-flow ODE from the image towards noise, each eps evaluated by the tiled
+        denoiser `get_noise` (abstractdiffusion.py:681-742, after the WebUI's img2imgalt script)."""
+        assert self.p.sampler_name == "Euler"
+        shared = host.get_shared()
+        state = shared.state
+
+        x = self.p.init_latent
+        s_in = x.new_ones([x.shape[0]])
+        skip = 1 if shared.sd_model.parameterization == "v" else 0
+        sigmas = dnw.get_sigmas(steps).flip(0)
+
+        cond = self.p.sd_model.get_learned_conditioning(prompts)
+        if isinstance(cond, Tensor):        # SD1 / SD2
+            cond_in = self.make_cond_dict({"c_crossattn": [], "c_concat": []}, cond, self.p.image_conditioning)
+        else:                               # SDXL
+            cond_in = self.make_cond_dict({"crossattn": None, "vector": None, "c_concat": []}, cond["crossattn"],
+                                          self.p.image_conditioning, cond["vector"])
+
+        state.sampling_steps = steps
+        pbar = None
+        if getattr(self.p, "show_tile_progress", True):
+            from tqdm import tqdm
+            pbar = tqdm(total=steps, desc="Noise Inversion")
+        for i in range(1, len(sigmas)):
+            if state.interrupted:
+                return x
+            state.sampling_step += 1
+
+            sigma_in = torch.cat([sigmas[i] * s_in])
+            c_out, c_in = [k[(...,) + (None,) * (x.ndim - k.ndim)] for k in dnw.get_scalings(sigma_in)[skip:]]
+            t = dnw.sigma_to_t(sigma_in) / self.noise_inverse_retouch
+
+            eps = self.get_noise(x * c_in, t, cond_in, steps - i)
+            denoised = x + eps * c_out
+
+            d = (x - denoised) / sigmas[i]          # Euler step towards the next (larger) sigma
+            x = x + d * (sigmas[i] - sigmas[i - 1])
+            host.store_latent(x)
+            del sigma_in, c_out, c_in, t, eps, denoised, d
+            if pbar is not None:
+                pbar.update(1)
+        if pbar is not None:
+            pbar.close()
+        return x / sigmas[-1]
+
+    @noise_inverse
+    @torch.no_grad()
+    def get_noise(self, x_in: Tensor, sigma_in: Tensor, cond_in: CondDict, step: int) -> Tensor:
+        raise NotImplementedError
 
     # ------------------------------------ side-input tile caches (ControlNet, StableSR)
     def _crop_side_input(self, t: Tensor, scale: int) -> Tensor:

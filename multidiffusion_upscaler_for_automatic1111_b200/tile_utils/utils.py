@@ -6,7 +6,7 @@ In scope: `BBox`, `split_bboxes`, `splitable`,
 `gaussian_weights`, the `Method` / `BlendMode` enums; and for region prompt control
 (section 8(f)-1): `BBoxSettings`, `build_bbox_settings`, `CustomBBox`, `feather_mask`
 and the `Prompt` / `Condition` helpers (thin calls into the host's prompt parser).
-The retouch mask of noise inversion is a later row and is not here.
+`get_retouch_mask` / `NoiseInverseCache` serve tiled noise inversion (section 8(f)-3).
 """
 from __future__ import annotations
 
@@ -68,6 +68,7 @@ class BBox:
 BBoxSettings = namedtuple("BBoxSettings", ["enable", "x", "y", "w", "h", "prompt", "neg_prompt", "blend_mode", "feather_ratio", "seed"])
 DEFAULT_BBOX_SETTINGS = BBoxSettings(False, 0.4, 0.4, 0.2, 0.2, "", "", BlendMode.BACKGROUND.value, 0.2, -1)
 NUM_BBOX_PARAMS = len(BBoxSettings._fields)
+NoiseInverseCache = namedtuple("NoiseInversionCache", ["model_hash", "x0", "xt", "noise_inversion_steps", "retouch", "prompts"])
 
 
 def build_bbox_settings(bbox_control_states: List[Any]) -> Dict[int, BBoxSettings]:
@@ -234,3 +235,25 @@ class Condition:
     @staticmethod
     def reconstruct_uncond(uncond, step: int) -> torch.Tensor:
         return Condition._module("prompt_parser").reconstruct_cond_batch(uncond, step)
+
+
+def get_retouch_mask(img_input: np.ndarray, kernel_size: int) -> np.ndarray:
+    """Where a self-guided box filter changes a grayscale image (utils.py:216-247): the high-frequency map noise
+    inversion uses to decide where fresh noise is injected.  uint8-quantised, in [0, 1], float32 [H, W].
+
+    Guided filter with guide == input: a = var / (var + 0.01), b = mean - a * mean over kernel x kernel boxes
+    (OpenCV's normalised box blur, reflect-101 borders), out = mean_box(a) * I + mean_box(b)... the reference resizes
+    a and b to the input size instead of blurring them, which at its fixed step of 1 is the identity."""
+    import cv2
+    img = img_input.astype(np.float32) / 255.0
+    box = (int(round(kernel_size)), int(round(kernel_size)))
+    mean_i = cv2.blur(img, box)
+    mean_ii = cv2.blur(img * img, box)
+    var_i = mean_ii - mean_i * mean_i
+    a = var_i / (var_i + 0.01)                 # cov(I, p) == var(I) because p is I
+    b = mean_i - a * mean_i
+    gf = a * img + b
+    gf -= img
+    gf *= 255
+    gf = gf.astype(np.uint8).clip(0, 255)
+    return gf.astype(np.float32) / 255.0

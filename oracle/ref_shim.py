@@ -31,6 +31,10 @@ class _State:
     interrupted = False
     sampling_step = 0
     sampling_steps = 1
+    job_count = 0
+
+    def nextjob(self):
+        pass
 
 
 class _Opts:
@@ -137,7 +141,7 @@ def install(device: str = "cpu"):
     _mod("modules.devices", device=dev, cpu=torch.device("cpu"), autocast=autocast,
          torch_gc=lambda: None, test_for_nans=test_for_nans,
          get_optimal_device=lambda: dev, get_optimal_device_name=lambda: str(dev))
-    sd_model = types.SimpleNamespace(cond_stage_key="txt",
+    sd_model = types.SimpleNamespace(cond_stage_key="txt", parameterization="eps",
                                      model=types.SimpleNamespace(conditioning_key="crossattn"))
     _mod("modules.shared", state=_State(), sd_model=sd_model, opts=_Opts(), cmd_opts=_CmdOpts(),
          batch_cond_uncond=True, State=_State)
@@ -147,7 +151,8 @@ def install(device: str = "cpu"):
          reconstruct_multicond_batch=fake_reconstruct_multicond, reconstruct_cond_batch=fake_reconstruct_cond)
     _mod("modules.extra_networks", ExtraNetworkParams=_Dummy, parse_prompts=lambda prompts: (list(prompts), {}),
          activate=lambda p, data: None, deactivate=lambda p, data: None)
-    _mod("modules.sd_samplers_common")
+    _mod("modules.sd_samplers_common", setup_img2img_steps=lambda p, steps=None: (steps if steps is not None else p.steps, p.steps - 1),
+         store_latent=lambda x: None)
     _mod("modules.processing", opt_f=8, StableDiffusionProcessing=_Dummy,
          StableDiffusionProcessingImg2Img=_Dummy, Processed=_Dummy)
     _mod("modules.sd_samplers_kdiffusion", KDiffusionSampler=KDiffusionSampler, CFGDenoiser=_Dummy,
@@ -163,6 +168,7 @@ def install(device: str = "cpu"):
     _mod("gradio")
     _mod("gradio.components", Component=_Dummy)
     _mod("k_diffusion")
+    _mod("k_diffusion.utils", append_dims=lambda x, target_dims: x[(...,) + (None,) * (target_dims - x.ndim)])
     _mod("k_diffusion.external", CompVisDenoiser=CompVisDenoiser, CompVisVDenoiser=CompVisVDenoiser)
     _mod("ldm")
     _mod("ldm.models")

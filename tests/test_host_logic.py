@@ -98,13 +98,13 @@ def test_cpu_tensor_is_refused_not_emulated():
         d.sample_one_step(torch.zeros(2, 4, 128, 128), None, lambda t, b: t, None)
 
 
-def test_out_of_scope_inits_raise():
-    from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
+def test_empty_region_table_switches_region_control_off_again():
+    from multidiffusion_upscaler_for_automatic1111_b200 import AbstractDiffusion, MultiDiffusion
     d = MultiDiffusion(_p(), _sampler())
-    with pytest.raises(NotImplementedError):
-        d.init_noise_inverse()
-    d.init_custom_bbox({}, True, False)      # region prompt control is on the path: no rows -> switched off again
+    d.init_custom_bbox({}, True, False)
     assert d.enable_custom_bbox is False and d.custom_bboxes == []
+    with pytest.raises(NotImplementedError):      # abstract in the base class, like the reference (abstractdiffusion.py:746)
+        AbstractDiffusion.get_noise(d, None, None, None, 0)
 
 
 def test_repeat_tensor_semantics():
