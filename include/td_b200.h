@@ -234,7 +234,7 @@ int td_blend_multidiffusion_peer(const td_grid* g, const void* const* batch_ptrs
                                  const uint32_t* wait_value, uint32_t flags, void* stream);
 
 /* ------------------------------------------------------------------------- *
- *  DemoFusion extras (tile_methods/demofusion.py); jitter off.
+ *  DemoFusion extras (tile_methods/demofusion.py).
  * ------------------------------------------------------------------------- */
 
 /* Dilated global views -- demofusion.py:283-308: out[(v*N+n), c, i, j] = src_v[n, c, by_v + i*s, bx_v + j*s],
@@ -252,6 +252,27 @@ int td_demofusion_combine(const void* x_local, const void* const* view_batch_ptr
                           int views_per_batch, int n_views, void* out, int N, int C, int H, int W, int s,
                           int out_h, int out_w, int end_y, int end_x, int mixture, float c2,
                           float one_minus_c2, int dtype, void* stream);
+
+/* Random-jitter mode (demofusion.py:101-139): the local windows carry individual random offsets on the zero-padded
+ * latent, i.e. an arbitrary window LIST instead of the separable td_grid.  origins_dev: DEVICE int32 [n_tiles][2]
+ * (x, y) in canvas coordinates; origins_host: the same values on the host for bounds validation (may be NULL).
+ *
+ * td_scatter_bboxes: tiles[(t*N+n), c, v, u] = x[n, c, y_t+v, x_t+u]                       (demofusion.py:256)
+ * td_blend_bboxes:   out fp32 [N,C,H,W] = acc / max(count, 1): the windows covering a pixel are added in list
+ *   order, each add rounded through dtype; count = number of covering windows           (demofusion.py:259-264).
+ *   batch_ptrs as in td_blend_multidiffusion (batch b holds windows [b*tile_bs, ...)). */
+int td_scatter_bboxes(const void* x, void* tiles, const int32_t* origins_dev, const int32_t* origins_host, int n_tiles,
+                      int N, int C, int H, int W, int tile_h, int tile_w, int dtype, void* stream);
+int td_blend_bboxes(const void* const* batch_ptrs, int num_batches, int tile_bs, const int32_t* origins_dev,
+                    const int32_t* origins_host, int n_tiles, int N, int C, int H, int W, int tile_h, int tile_w,
+                    int dtype, float* out, void* stream);
+
+/* td_demofusion_combine with the dilated views starting at offset + (by, bx) (offset = jitter_range,
+ * demofusion.py:279-310): pixels with y < offset, x < offset, y >= end_y or x >= end_x get x_global = 0. */
+int td_demofusion_combine_offset(const void* x_local, const void* const* view_batch_ptrs, int num_batches,
+                                 int views_per_batch, int n_views, void* out, int N, int C, int H, int W, int s,
+                                 int out_h, int out_w, int offset, int end_y, int end_x, int mixture, float c2,
+                                 float one_minus_c2, int dtype, void* stream);
 
 /* gaussian_filter -- demofusion.py:173-178: depthwise k x k convolution, zero padding k/2, fp32
  * accumulate, result rounded to dtype.  kernel_host: k*k fp32 values (already rounded through dtype). */

@@ -92,6 +92,12 @@ _SIGNATURES = {
                                   POINTER(c_int32), POINTER(c_int32), c_int, c_int, c_void_p]),
     "td_demofusion_combine": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
+    "td_scatter_bboxes": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int32), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_void_p]),
+    "td_blend_bboxes": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, POINTER(c_int32), c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_int, c_void_p, c_void_p]),
+    "td_demofusion_combine_offset": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                             c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
     "td_depthwise_conv2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_float), c_int, c_int, c_void_p]),
     "td_blend_mixture": (c_int, [POINTER(TdGrid), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),

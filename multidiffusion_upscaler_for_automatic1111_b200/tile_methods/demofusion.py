@@ -7,13 +7,15 @@
     global views    td_dilated_gather                                                  demofusion.py:283-308
     add-back + mix  td_demofusion_combine (one launch)                                 demofusion.py:296-322
 
-Random jitter (demofusion.py:116-134, Python's unseeded `random`) makes the window list non-separable
-and is not on this path yet: `p.random_jitter=True` raises NotImplementedError.
+Random jitter (demofusion.py:116-134, offsets from Python's `random`) makes the window list non-separable: the
+local windows then go through the list-driven td_scatter_bboxes / td_blend_bboxes on the zero-padded latent and the
+add-back through td_demofusion_combine_offset (csrc/td_jitter.cu).
 """
 from __future__ import annotations
 
 import ctypes
 import math
+import random
 from typing import Dict, List, Tuple
 
 import numpy as np
@@ -34,6 +36,18 @@ class DemoFusion(AbstractDiffusion):
         assert p.sampler_name != 'UniPC', 'Demofusion is not compatible with UniPC!'
         self.jitter_range = 0
         self.repeat_3 = False
+        self._jitter = False                 # window LIST (random jitter) instead of the separable grid
+        self._origins_host = None
+        self._origins_dev = None
+
+    def _check_input(self, x_in: Tensor) -> Tensor:
+        if not self._jitter:
+            return super()._check_input(x_in)
+        if not x_in.is_cuda:
+            raise RuntimeError(f"{self.method}: latent is on {x_in.device}; the B200 path has no CPU fallback")
+        if self._origins_dev is None:
+            raise RuntimeError(f"{self.method}: get_views() has not been called")
+        return x_in.contiguous()
 
     # ------------------------------------------------------------------ hooks
     def hook(self):
@@ -64,31 +78,71 @@ class DemoFusion(AbstractDiffusion):
         views = [(col, row) for row in range(s) for col in range(s)]
         return views + views if self.p.mixture else views
 
+    def split_bboxes_jitter(self, w_l: int, h_l: int, tile_w: int, tile_h: int, overlap: int = 16) -> List[BBox]:
+        """demofusion.py:101-139 with random_jitter on: the regular window grid, every window moved by a random offset
+        of at most jitter_range towards the inside (border windows only inwards), in coordinates of the latent
+        zero-padded by jitter_range.  Offsets come from Python's global `random`, x before y, row-major -- the same
+        draws as the reference, so a seeded run reproduces its windows."""
+        cols = math.ceil((w_l - overlap) / (tile_w - overlap)) or 1
+        rows = math.ceil((h_l - overlap) / (tile_h - overlap)) or 1
+        dx = (w_l - tile_w) / (cols - 1) if cols > 1 else 0
+        dy = (h_l - tile_h) / (rows - 1) if rows > 1 else 0
+        jr = min(max((min(self.w, self.h) - self.stride) // 4, 0), min(int(self.window_size / 2), int(self.overlap / 2)))
+        self.jitter_range = jr
+
+        def draw(pos: int, size: int, extent: int) -> int:
+            at_start, at_end = pos == 0, pos + size == extent
+            if not at_start and not at_end:
+                return random.randint(-jr, jr)
+            if at_start and not at_end:
+                return random.randint(-jr, 0)
+            if at_end and not at_start:
+                return random.randint(0, jr)
+            return 0
+        out = []
+        for row in range(rows):
+            for col in range(cols):
+                y = min(int(row * dy), h_l - tile_h)
+                x = min(int(col * dx), w_l - tile_w)
+                xj = draw(x, tile_w, w_l)
+                yj = draw(y, tile_h, h_l)
+                out.append(BBox(x + xj + jr, y + yj + jr, tile_w, tile_h))
+        return out
+
     @grid_bbox
     def get_views(self, overlap: int, tile_bs: int, tile_bs_g: int):
         """demofusion.py:140-162: local window grid (stride = max(4, window - overlap)) + global view batches."""
-        if getattr(self.p, "random_jitter", False):
-            raise NotImplementedError("DemoFusion random jitter is not on the B200 path yet (non-separable window list)")
         self.enable_grid_bbox = True
         self.tile_w = self.tile_h = self.window_size
         self.overlap = max(0, min(overlap, self.window_size - 4))
         self.stride = max(4, self.window_size - self.overlap)
         self.jitter_range = 0
-        # split_bboxes_jitter without jitter is split_bboxes on the clamped overlap (demofusion.py:101-115);
-        # init through td_grid_init with tile == window reproduces rows / cols / origins exactly
-        g = engine.make_grid(self.w, self.h, self.window_size, self.window_size, self.overlap, tile_bs)
-        if g.overlap != self.overlap or g.tile_w != self.window_size or g.tile_h != self.window_size:
-            raise ValueError("window larger than the latent: DemoFusion clamps window_size before get_views")
-        self._grid = g
-        bboxes = [BBox(int(x), int(y), int(w), int(h)) for x, y, w, h in engine.grid_bboxes_xywh(g)]
-        self.num_tiles = len(bboxes)
-        self.num_batches = int(g.num_batches)
-        self.tile_bs = int(g.tile_bs)
+        self._jitter = bool(getattr(self.p, "random_jitter", False))
+        if self._jitter:
+            bboxes = self.split_bboxes_jitter(self.w, self.h, self.tile_w, self.tile_h, self.overlap)
+            self._grid = None
+            flat = [v for b in bboxes for v in (b.x, b.y)]
+            self._origins_host = (ctypes.c_int32 * len(flat))(*flat)
+            self._origins_dev = torch.tensor(flat, dtype=torch.int32, device=host.device())
+            self.num_tiles = len(bboxes)
+            self.num_batches = math.ceil(self.num_tiles / tile_bs)
+            self.tile_bs = math.ceil(self.num_tiles / self.num_batches)
+        else:
+            # split_bboxes_jitter without jitter is split_bboxes on the clamped overlap (demofusion.py:101-115);
+            # init through td_grid_init with tile == window reproduces rows / cols / origins exactly
+            g = engine.make_grid(self.w, self.h, self.window_size, self.window_size, self.overlap, tile_bs)
+            if g.overlap != self.overlap or g.tile_w != self.window_size or g.tile_h != self.window_size:
+                raise ValueError("window larger than the latent: DemoFusion clamps window_size before get_views")
+            self._grid = g
+            bboxes = [BBox(int(x), int(y), int(w), int(h)) for x, y, w, h in engine.grid_bboxes_xywh(g)]
+            self.num_tiles = len(bboxes)
+            self.num_batches = int(g.num_batches)
+            self.tile_bs = int(g.tile_bs)
+            counts = engine.grid_weights(g)   # how many windows cover each pixel (demofusion.py:261)
+            counts[counts == 0] = 1.0         # :262
+            self._counts = torch.from_numpy(counts).to(host.device())
+            self._rcp_counts = torch.from_numpy(engine.exact_reciprocals(counts)).to(host.device())
         self.batched_bboxes = [bboxes[i * self.tile_bs:(i + 1) * self.tile_bs] for i in range(self.num_batches)]
-        counts = engine.grid_weights(g)   # how many windows cover each pixel (demofusion.py:261)
-        counts[counts == 0] = 1.0         # :262
-        self._counts = torch.from_numpy(counts).to(host.device())
-        self._rcp_counts = torch.from_numpy(engine.exact_reciprocals(counts)).to(host.device())
 
         global_bboxes = self.global_split_bboxes()
         self.global_num_tiles = len(global_bboxes)
@@ -104,6 +158,9 @@ class DemoFusion(AbstractDiffusion):
         icond = self.get_icond(cond_in)
         if tuple(icond.shape[2:]) == (self.h, self.w):
             if mode == 0:
+                if self._jitter:          # the windows live on the padded latent (demofusion.py:71-73)
+                    jr = self.jitter_range
+                    icond = F.pad(icond, (jr, jr, jr, jr), "constant", value=0)
                 icond = torch.cat([icond[b.slicer] for b in bboxes], dim=0)
             else:
                 s = self.p.current_scale_num
@@ -166,19 +223,23 @@ class DemoFusion(AbstractDiffusion):
         self.cosine_factor = 0.5 * (1 + torch.cos(torch.pi * torch.tensor(((p.current_step + 1) / (self.t_enc + 1)))))
         c1 = self.cosine_factor ** p.cosine_scale_1
         x_in = x_in * (1 - c1) + x_noisy * c1
+        jr = self.jitter_range if getattr(p, "random_jitter", False) else 0
+        H, W = x_in.shape[2:]
+        x_in_ = F.pad(x_in, (jr, jr, jr, jr), "constant", value=0) if jr else x_in      # demofusion.py:200-204
         cfg = self.sampler.model_wrap_cfg
         cfg.inner_model.forward = self.sample_one_step
         self.repeat_3 = False
         try:
-            x_out = cfg.forward_ori(x_in, sigma, **kwarg)
+            x_out = cfg.forward_ori(x_in_, sigma, **kwarg)
         finally:
             cfg.inner_model.forward = self.sampler_forward
-        return x_out
+        return x_out[:, :, jr:jr + H, jr:jr + W] if jr else x_out
 
     @torch.no_grad()
     @keep_signature
     def sample_one_step(self, x_in: Tensor, sigma: Tensor, cond):
-        """demofusion.py:219-324 (jitter off)."""
+        """demofusion.py:219-324.  With random jitter `x_in` is the latent zero-padded by jitter_range (the callers
+        pad and crop: forward_one_step, get_noise)."""
         p = self.p
         sd_model = getattr(p, "sd_model", None) or self._sd_model()
 
@@ -194,23 +255,29 @@ class DemoFusion(AbstractDiffusion):
 
         x = self._check_input(x_in)
         N, C, H, W = x.shape
-        if (H, W) != (self.h, self.w):
-            raise ValueError(f"latent {(H, W)} does not match the views built for {(self.h, self.w)}")
+        jr = self.jitter_range if self._jitter else 0
+        if (H, W) != (self.h + 2 * jr, self.w + 2 * jr):
+            raise ValueError(f"latent {(H, W)} does not match the views built for {(self.h, self.w)} (+ 2 x jitter {jr})")
         dt, dev = x.dtype, x.device
         s = int(p.current_scale_num)
-        if self._counts.device != dev:
-            self._counts, self._rcp_counts = self._counts.to(dev), self._rcp_counts.to(dev)
 
         # ---- local windows: count-normalised blend (buffer / count, both in x.dtype) ----------------------------
-        tiles = self._scatter_all(x)
-        outs = []
-        for batch_id, bboxes in enumerate(self.batched_bboxes):
-            if host.interrupted():
+        if self._jitter:
+            x_local = self._local_pass_window_list(x_in, x, repeat_func)
+            if x_local is None:
                 return x_in
-            outs.append(repeat_func(self._tile_batch(tiles, batch_id, N), bboxes))
-        rcp = self._rcp_counts if dt in (torch.float16, torch.bfloat16) else None
-        x_local = engine.blend_multidiffusion(self._grid, outs, N, C, self.tile_bs, self._counts, dt, flags=self._blend_flags,
-                                              rcp_weights=rcp).to(dt)
+        else:
+            if self._counts.device != dev:
+                self._counts, self._rcp_counts = self._counts.to(dev), self._rcp_counts.to(dev)
+            tiles = self._scatter_all(x)
+            outs = []
+            for batch_id, bboxes in enumerate(self.batched_bboxes):
+                if host.interrupted():
+                    return x_in
+                outs.append(repeat_func(self._tile_batch(tiles, batch_id, N), bboxes))
+            rcp = self._rcp_counts if dt in (torch.float16, torch.bfloat16) else None
+            x_local = engine.blend_multidiffusion(self._grid, outs, N, C, self.tile_bs, self._counts, dt, flags=self._blend_flags,
+                                                  rcp_weights=rcp).to(dt)
 
         # ---- blurred + renormalised latent for the global path ------------------------------------------------------
         c3 = 0.99 * self.cosine_factor ** p.cosine_scale_3 + 1e-2
@@ -221,10 +288,10 @@ class DemoFusion(AbstractDiffusion):
             raise ValueError("DemoFusion without mixture needs gaussian_filter=True (the reference reads x_in_g unconditionally)")
 
         # ---- global dilated views ------------------------------------------------------------------------------------
-        end = W   # the reference's slice bound `end = shape[3] - jitter_range` is used on both axes
+        end = W - jr   # the reference's slice bound `end = shape[3] - jitter_range` is used on both axes
         end_y, end_x = min(H, end), end
-        oh, ow = len(range(0, end_y, s)), len(range(0, end_x, s))
-        if any(len(range(b, end_y, s)) != oh for b in range(s)) or any(len(range(b, end_x, s)) != ow for b in range(s)):
+        oh, ow = len(range(jr, end_y, s)), len(range(jr, end_x, s))
+        if any(len(range(jr + b, end_y, s)) != oh for b in range(s)) or any(len(range(jr + b, end_x, s)) != ow for b in range(s)):
             raise ValueError("latent size must be a multiple of the scale (the reference's torch.cat needs equal views)")
         half = self.global_num_tiles // 2
         g_outs, seen = [], 0
@@ -236,7 +303,7 @@ class DemoFusion(AbstractDiffusion):
             arr = lambda v: (ctypes.c_int32 * n)(*v)
             with torch.cuda.device(dev):
                 check(lib.td_dilated_gather(x.data_ptr(), x_in_g.data_ptr() if x_in_g is not None else None, view.data_ptr(), N, C, H, W,
-                                            s, oh, ow, arr([b[0] for b in bboxes]), arr([b[1] for b in bboxes]), arr(second), n,
+                                            s, oh, ow, arr([b[0] + jr for b in bboxes]), arr([b[1] + jr for b in bboxes]), arr(second), n,
                                             dtype_code(dt), current_stream_ptr(dev)))
             g_outs.append(repeat_func(view, bboxes, mode=1).to(dt).contiguous())
 
@@ -246,14 +313,49 @@ class DemoFusion(AbstractDiffusion):
         out = torch.empty_like(x_local)
         ptrs = (ctypes.c_void_p * len(g_outs))(*[t.data_ptr() for t in g_outs])
         with torch.cuda.device(dev):
-            check(lib.td_demofusion_combine(x_local.data_ptr(), ptrs, len(g_outs), self.global_tile_bs, self.global_num_tiles,
-                                            out.data_ptr(), N, C, H, W, s, oh, ow, end_y, end_x, int(bool(p.mixture)), c2, one_minus_c2,
-                                            dtype_code(dt), current_stream_ptr(dev)))
+            if jr:
+                check(lib.td_demofusion_combine_offset(x_local.data_ptr(), ptrs, len(g_outs), self.global_tile_bs, self.global_num_tiles,
+                                                       out.data_ptr(), N, C, H, W, s, oh, ow, jr, end_y, end_x, int(bool(p.mixture)), c2,
+                                                       one_minus_c2, dtype_code(dt), current_stream_ptr(dev)))
+            else:
+                check(lib.td_demofusion_combine(x_local.data_ptr(), ptrs, len(g_outs), self.global_tile_bs, self.global_num_tiles,
+                                                out.data_ptr(), N, C, H, W, s, oh, ow, end_y, end_x, int(bool(p.mixture)), c2, one_minus_c2,
+                                                dtype_code(dt), current_stream_ptr(dev)))
         self.x_buffer = out
         return out
 
+    def _local_pass_window_list(self, x_in: Tensor, x: Tensor, repeat_func):
+        """Local windows in random-jitter mode (demofusion.py:254-264): one list-driven scatter, the UNet per batch, one
+        list-driven count-normalised blend.  Returns x_local (x.dtype) or None when interrupted."""
+        N, C, H, W = x.shape
+        dt, dev, ws, T = x.dtype, x.device, self.window_size, self.num_tiles
+        if self._origins_dev.device != dev:
+            self._origins_dev = self._origins_dev.to(dev)
+        shape = (T * N, C, ws, ws)
+        if self._tiles is None or tuple(self._tiles.shape) != shape or self._tiles.dtype != dt or self._tiles.device != dev:
+            self._tiles = torch.empty(shape, dtype=dt, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.td_scatter_bboxes(x.data_ptr(), self._tiles.data_ptr(), self._origins_dev.data_ptr(), self._origins_host, T, N, C, H, W,
+                                        ws, ws, dtype_code(dt), current_stream_ptr(dev)))
+        outs = []
+        for batch_id, bboxes in enumerate(self.batched_bboxes):
+            if host.interrupted():
+                return None
+            outs.append(repeat_func(self._tile_batch(self._tiles, batch_id, N), bboxes).to(dt).contiguous())
+        ptrs = (ctypes.c_void_p * len(outs))(*[t.data_ptr() for t in outs])
+        x_local = torch.empty((N, C, H, W), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.td_blend_bboxes(ptrs, len(outs), self.tile_bs, self._origins_dev.data_ptr(), self._origins_host, T, N, C, H, W, ws, ws,
+                                      dtype_code(dt), x_local.data_ptr(), current_stream_ptr(dev)))
+        return x_local.to(dt)
+
     def get_noise(self, x_in: Tensor, sigma_in: Tensor, cond_in: Dict[str, Tensor], step: int) -> Tensor:
-        """demofusion.py:345-353 (jitter off)."""
+        """demofusion.py:345-353: the tiled eps on the latent padded by jitter_range, cropped back."""
         self.repeat_3 = True
         self.cosine_factor = 0.5 * (1 + torch.cos(torch.pi * torch.tensor(((self.p.current_step + 1) / (self.t_enc + 1)))))
-        return self.sample_one_step(x_in, sigma_in, cond_in.copy())
+        jr = self.jitter_range
+        if not jr:
+            return self.sample_one_step(x_in, sigma_in, cond_in.copy())
+        H, W = x_in.shape[2:]
+        x_in_ = F.pad(x_in, (jr, jr, jr, jr), "constant", value=0)
+        return self.sample_one_step(x_in_, sigma_in, cond_in.copy())[:, :, jr:jr + H, jr:jr + W]

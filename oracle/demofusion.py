@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE -- oracle for DemoFusion's per-step tile path (torch-CPU restatement of
-tile_methods/demofusion.py:219-324, jitter off).
+tile_methods/demofusion.py:219-324; `jitter_range` > 0 = random-jitter mode on the zero-padded latent).
 
   local windows   :254-264   scatter, per-tile add and COUNT (both in x.dtype), x_local = buffer / count
   gaussian filter :164-178   depthwise conv, kernel 2s-1, sigma = sig * c3, kernel cast to x.dtype
@@ -7,6 +7,8 @@ tile_methods/demofusion.py:219-324, jitter off).
   global views    :283-310   s*s dilated views x[:, :, by::s, bx::s] (mixture: raw views then blurred views, /2)
   mix             :312-324   x_local * (1 - c2) + x_global * c2
 Quirk kept: the strided slices stop at `end = W - jitter_range` for BOTH axes (:280).
+Random jitter: the caller pads x_in by jitter_range (:204), the local windows come in padded coordinates
+(tiling.demofusion_views_jitter), the dilated views start at jitter_range + (bx, by) and the caller crops.
 """
 from __future__ import annotations
 
@@ -50,8 +52,8 @@ def global_views(scale: int, mixture: bool) -> List[Tuple[int, int]]:
 
 def sample_one_step(x_in: torch.Tensor, local_batches: Sequence[Sequence[BBox]], global_batches: Sequence[Sequence[Tuple[int, int]]],
                     scale: int, mixture: bool, use_gaussian: bool, sig: float, cos_factor: torch.Tensor, cs2: float, cs3: float,
-                    denoise_local: Callable, denoise_global: Callable) -> torch.Tensor:
-    """demofusion.py:219-324 with jitter off.  denoise_*(x_tile, views) stand for the UNet."""
+                    denoise_local: Callable, denoise_global: Callable, jitter_range: int = 0) -> torch.Tensor:
+    """demofusion.py:219-324.  denoise_*(x_tile, views) stand for the UNet."""
     N = x_in.shape[0]
     dt = x_in.dtype
     x_buffer = torch.zeros_like(x_in)
@@ -75,18 +77,19 @@ def sample_one_step(x_in: torch.Tensor, local_batches: Sequence[Sequence[BBox]],
         x_in_g = (x_in_g - x_in_g.mean()) / x_in_g.std() * std_ + mean_
 
     x_global = torch.zeros_like(x_local)
-    end = x_global.shape[3]
+    jr = jitter_range
+    end = x_global.shape[3] - jr
     total = sum(len(b) for b in global_batches)
     seen = 0
     for views in global_batches:
         srcs = []
         for (bx, by) in views:
             src = x_in if (mixture and seen < total // 2) else x_in_g
-            srcs.append(src[:, :, by:end:scale, bx:end:scale])
+            srcs.append(src[:, :, by + jr:end:scale, bx + jr:end:scale])
             seen += 1
         out = denoise_global(torch.cat(srcs, dim=0), views)
         for idx, (bx, by) in enumerate(views):
-            x_global[:, :, by:end:scale, bx:end:scale] += out[idx * N:(idx + 1) * N]
+            x_global[:, :, by + jr:end:scale, bx + jr:end:scale] += out[idx * N:(idx + 1) * N]
     if mixture:
         x_buffer += x_global / 2
     else:

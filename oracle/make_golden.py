@@ -150,28 +150,69 @@ def gen_region(ref):
     np.savez_compressed(os.path.join(GOLDEN_DIR, "region_small.npz"), **out)
 
 
+def gen_demofusion_jitter(ref):
+    """10. DemoFusion with random jitter (demofusion.py:101-139, :204, :279-310): seeded windows, padded latent ------"""
+    import torch.nn.functional as F
+    out = {}
+    for name, dn, mixture in DEMO_JITTER_CASES:
+        d, x, cond = demofusion_reference_case(ref, DTYPES[dn], mixture, jitter_seed=DEMO_JITTER_SEED)
+        jr = d.jitter_range
+        y = d.sample_one_step(F.pad(x, (jr, jr, jr, jr), "constant", value=0), torch.ones(x.shape[0]), cond)
+        out[name] = _bits(y)
+        out[name + "_dtype"] = np.array(str(y.dtype))
+        out[name + "_local"] = np.array([(b.x, b.y, b.w, b.h) for bb in d.batched_bboxes for b in bb], np.int32)
+        out[name + "_sizes"] = np.array([d.tile_bs, d.global_tile_bs, d.global_num_tiles, jr], np.int32)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "demofusion_jitter.npz"), **out)
+
+
 def demo_denoise(x_tile, *_a, **_k):
     """Deterministic stand-in for the UNet in the DemoFusion fixtures (exact: scale by 0.5)."""
     return (x_tile.float() * 0.5).to(x_tile.dtype)
 
 
-def demofusion_reference_case(ref, dtype, mixture):
+DEMO_JITTER_SEED = 20240922
+DEMO_JITTER_CASES = [("f32_mixture_jitter", "f32", True), ("f16_plain_jitter", "f16", False)]
+
+
+def position_aware_denoise(delegate):
+    """UNet stand-in for the jitter fixtures: local windows are scaled by their (jittered) position, global views by
+    0.5.  The delegate hands the window list to `repeat_cond_dict` right before every UNet call; wrapping that
+    (an instance attribute, the class is untouched) tells the stand-in which windows it is looking at."""
+    state = {}
+    orig = delegate.repeat_cond_dict
+
+    def spy(cond_in, bboxes, mode):
+        state["bboxes"], state["mode"] = bboxes, mode
+        return orig(cond_in, bboxes, mode)
+    delegate.repeat_cond_dict = spy
+
+    def unet(xt, sigma, cond=None):
+        if state["mode"] == 0:
+            return synth.fake_denoise(xt, state["bboxes"], xt.shape[0] // len(state["bboxes"]))
+        return demo_denoise(xt)
+    return unet
+
+
+def demofusion_reference_case(ref, dtype, mixture, jitter_seed=None):
     """The reference's DemoFusion delegate set up like tileglobal.py does, without a WebUI."""
+    import random
     import types
     from . import demofusion as odf
     c = DEMO_CFG
     sys.modules['modules.sd_samplers_common'].setup_img2img_steps = lambda p, steps=None: (p.steps, p.t_enc)
     x = synth.latent(31, (c["N"], c["C"], c["H"], c["W"]), dtype)
     p = ref_shim.make_p(c["W"] * 8, c["H"] * 8)
-    p.current_scale_num, p.mixture, p.gaussian_filter, p.random_jitter = c["scale"], mixture, True, False
+    p.current_scale_num, p.mixture, p.gaussian_filter, p.random_jitter = c["scale"], mixture, True, jitter_seed is not None
     p.cosine_scale_1, p.cosine_scale_2, p.cosine_scale_3 = c["cs1"], c["cs2"], c["cs3"]
     p.current_step, p.steps, p.t_enc = c["current_step"], 20, c["t_enc"]
     p.sd_model = types.SimpleNamespace(apply_model=lambda *a, **k: None)
     sampler = ref_shim.make_kdiff_sampler(lambda xt, sigma, cond=None: demo_denoise(xt))
     d = ref.demofusion.DemoFusion(p, sampler)
     d.window_size, d.sig = c["window"], c["sig"]
+    if jitter_seed is not None:
+        random.seed(jitter_seed)       # the reference draws from Python's global `random` (demofusion.py:122-132)
     d.get_views(c["overlap"], c["tile_bs"], c["tile_bs_g"])
-    d.sampler_forward = lambda xt, sigma, cond=None: demo_denoise(xt)
+    d.sampler_forward = position_aware_denoise(d) if jitter_seed is not None else (lambda xt, sigma, cond=None: demo_denoise(xt))
     d.repeat_3 = False
     d.cosine_factor = odf.cosine_factor(p.current_step, p.t_enc)
     cond = {"c_crossattn": [torch.zeros(c["N"], 77, 8)], "c_concat": [torch.zeros(c["N"], 5, 1, 1)]}
@@ -249,6 +290,9 @@ def main():
     torch.set_num_threads(1)
     if "region" in sys.argv[1:]:      # regenerate only region_small.npz
         gen_region(ref)
+        return
+    if "jitter" in sys.argv[1:]:      # regenerate only demofusion_jitter.npz
+        gen_demofusion_jitter(ref)
         return
 
     # 1. split_bboxes sweep (utils.py:160-177) ------------------------------------
@@ -363,6 +407,7 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN_DIR, "demofusion_small.npz"), **out)
 
     gen_region(ref)
+    gen_demofusion_jitter(ref)
 
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))

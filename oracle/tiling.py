@@ -8,7 +8,7 @@ executes), the reference functions:
   gaussian_weights        tile_utils/utils.py:180-194
   init_grid_bbox          tile_methods/abstractdiffusion.py:172-186
   MoD init_done rescale   tile_methods/mixtureofdiffusers.py:29-36
-  DemoFusion get_views    tile_methods/demofusion.py:101-162 (jitter off)
+  DemoFusion get_views    tile_methods/demofusion.py:101-162 (jitter off, and random jitter with Python's `random`)
 """
 from __future__ import annotations
 
@@ -110,3 +110,37 @@ def demofusion_views(w: int, h: int, window_size: int, overlap: int):
             x = min(int(col * dx), w - tile_w)
             out.append((x, y, tile_w, tile_h))
     return out, overlap, stride
+
+
+def demofusion_views_jitter(w: int, h: int, window_size: int, overlap: int, rng):
+    """demofusion.py:101-139 with random_jitter on.  `rng` is Python's `random` module (or a `random.Random`): the
+    reference draws `randint` per window, x before y, row-major, only for the cases listed below.
+    Windows are returned in PADDED canvas coordinates (+ jitter_range); also returns (overlap, stride, jitter_range)."""
+    overlap = max(0, min(overlap, window_size - 4))
+    stride = max(4, window_size - overlap)
+    tile_w = tile_h = window_size
+    cols = math.ceil((w - overlap) / (tile_w - overlap)) or 1
+    rows = math.ceil((h - overlap) / (tile_h - overlap)) or 1
+    dx = (w - tile_w) / (cols - 1) if cols > 1 else 0
+    dy = (h - tile_h) / (rows - 1) if rows > 1 else 0
+    jr = min(max((min(w, h) - stride) // 4, 0), min(int(window_size / 2), int(overlap / 2)))
+    out = []
+    for row in range(rows):
+        for col in range(cols):
+            y = min(int(row * dy), h - tile_h)
+            x = min(int(col * dx), w - tile_w)
+            xj = yj = 0
+            if x != 0 and x + tile_w != w:
+                xj = rng.randint(-jr, jr)
+            elif x == 0 and x + tile_w != w:
+                xj = rng.randint(-jr, 0)
+            elif x != 0 and x + tile_w == w:
+                xj = rng.randint(0, jr)
+            if y != 0 and y + tile_h != h:
+                yj = rng.randint(-jr, jr)
+            elif y == 0 and y + tile_h != h:
+                yj = rng.randint(-jr, 0)
+            elif y != 0 and y + tile_h == h:
+                yj = rng.randint(0, jr)
+            out.append((x + xj + jr, y + yj + jr, tile_w, tile_h))
+    return out, overlap, stride, jr
