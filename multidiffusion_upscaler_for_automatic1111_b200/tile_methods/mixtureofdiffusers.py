@@ -89,6 +89,8 @@ class MixtureOfDiffusers(AbstractDiffusion):
         x = self._check_input(x_in)
         self.reset_buffer(x)
         regions = self.enable_custom_bbox and len(self.custom_bboxes) > 0
+        if regions and self._shard is not None:
+            raise NotImplementedError("region prompt control is not combined with the multi-GPU tile shard yet")
 
         if self.enable_grid_bbox:
             x_out = self._grid_pass(x_in, x, t_in, c_in, sd_model, N, C)
@@ -121,6 +123,26 @@ class MixtureOfDiffusers(AbstractDiffusion):
             return self.x_buffer
         return self._feather_composite(self.x_buffer, feather)
 
+    def _denoise_tile_batch(self, sd_model, x_tile: Tensor, n_rep: int, t_in: Tensor, c_in: CondDict, icond_tile, batch_id: int,
+                            N: int) -> Tensor:
+        """One UNet call on a batch of n_rep tiles: timestep / text / vector cond repeated per tile, spatial image cond
+        already cropped per tile (mixtureofdiffusers.py:89-119)."""
+        t_tile = torch.cat([t_in] * n_rep, dim=0) if n_rep > 1 else t_in
+        if not isinstance(c_in, dict):
+            raise NotImplementedError("non-dict conditioning is not supported by Mixture of Diffusers "
+                                      "(the reference only prints a warning here, mixtureofdiffusers.py:103)")
+        tcond = self.get_tcond(c_in)
+        tcond_tile = torch.cat([tcond] * n_rep, dim=0) if n_rep > 1 else tcond
+        if icond_tile is None:
+            icond = self.get_icond(c_in)
+            icond_tile = torch.cat([icond] * n_rep, dim=0) if n_rep > 1 else icond
+        vcond = self.get_vcond(c_in)
+        vcond_tile = None if vcond is None else (torch.cat([vcond] * n_rep, dim=0) if n_rep > 1 else vcond)
+        c_tile = self.make_cond_dict(c_in, tcond_tile, icond_tile, vcond_tile)
+        self.switch_controlnet_tensors(batch_id, N, n_rep, is_denoise=True)
+        self.switch_stablesr_tensors(batch_id)
+        return sd_model.apply_model_original_md(x_tile, t_tile, c_tile)
+
     def _grid_pass(self, x_in: Tensor, x: Tensor, t_in: Tensor, c_in: CondDict, sd_model, N: int, C: int):
         """Grid tiles of one UNet call: scatter, denoise per batch, fused gaussian blend into x_buffer.
         Returns x_buffer, or None when the job was interrupted."""
@@ -128,6 +150,8 @@ class MixtureOfDiffusers(AbstractDiffusion):
             self.rescale_factor = self.rescale_factor.to(x.device)
         if self.tile_weights.device != x.device:
             self.tile_weights = self.tile_weights.to(x.device)
+        if self._shard is not None:
+            return self._grid_pass_sharded(x, t_in, c_in, sd_model, N, C)
 
         tiles = self._scatter_all(x)
         icond_tiles = None
@@ -143,28 +167,49 @@ class MixtureOfDiffusers(AbstractDiffusion):
                 return None
             n_rep = len(bboxes)
             x_tile = self._tile_batch(tiles, batch_id, N)
-            t_tile = torch.cat([t_in] * n_rep, dim=0) if n_rep > 1 else t_in
-            if isinstance(c_in, dict):
-                tcond = self.get_tcond(c_in)
-                tcond_tile = torch.cat([tcond] * n_rep, dim=0) if n_rep > 1 else tcond
-                if icond_tiles is not None:
-                    icond_tile = self._tile_batch(icond_tiles, batch_id, n_icond)
-                else:
-                    icond = self.get_icond(c_in)
-                    icond_tile = torch.cat([icond] * n_rep, dim=0) if n_rep > 1 else icond
-                vcond = self.get_vcond(c_in)
-                vcond_tile = None if vcond is None else (torch.cat([vcond] * n_rep, dim=0) if n_rep > 1 else vcond)
-                c_tile = self.make_cond_dict(c_in, tcond_tile, icond_tile, vcond_tile)
-            else:
-                raise NotImplementedError("non-dict conditioning is not supported by Mixture of Diffusers "
-                                          "(the reference only prints a warning here, mixtureofdiffusers.py:103)")
-            self.switch_controlnet_tensors(batch_id, N, n_rep, is_denoise=True)
-            self.switch_stablesr_tensors(batch_id)
-            outs.append(sd_model.apply_model_original_md(x_tile, t_tile, c_tile))
+            icond_tile = self._tile_batch(icond_tiles, batch_id, n_icond) if icond_tiles is not None else None
+            outs.append(self._denoise_tile_batch(sd_model, x_tile, n_rep, t_in, c_in, icond_tile, batch_id, N))
             self.update_pbar()
 
         return engine.blend_mixture(self._grid, outs, N, C, self.tile_bs, self.tile_weights, self.rescale_factor,
                                     self.x_buffer, flags=self._blend_flags)
+
+    def _grid_pass_sharded(self, x: Tensor, t_in: Tensor, c_in: CondDict, sd_model, N: int, C: int):
+        """Tile shard (init_tile_shard): this rank denoises its contiguous chunk of the tile list, the eps tiles are
+        all-gathered, and every rank runs the same ordered gaussian blend over all tiles -- bit-identical to the
+        single-GPU result on every rank."""
+        from .. import parallel
+        sh, g = self._shard, self._grid
+        outs = []
+        if sh.num_local > 0:
+            self._tiles = engine.scatter_tiles(g, x, out=self._tiles, tile_begin=sh.begin, tile_end=sh.end, flags=self._blend_flags)
+            icond_tiles, n_icond = None, 0
+            if isinstance(c_in, dict):
+                icond_full = self.get_icond(c_in)
+                if tuple(icond_full.shape[2:]) == (self.h, self.w):
+                    icond_tiles = engine.scatter_tiles(g, icond_full, tile_begin=sh.begin, tile_end=sh.end, flags=self._blend_flags)
+                    n_icond = icond_full.shape[0]
+            off = 0
+            for batch_id, bboxes in enumerate(self.local_batched_bboxes):
+                if host.interrupted():
+                    return None
+                n_rep = len(bboxes)
+                x_tile = self._tiles[off * N:(off + n_rep) * N]
+                icond_tile = icond_tiles[off * n_icond:(off + n_rep) * n_icond] if icond_tiles is not None else None
+                off += n_rep
+                outs.append(self._denoise_tile_batch(sd_model, x_tile, n_rep, t_in, c_in, icond_tile, batch_id, N))
+                self.update_pbar()
+        dt = outs[0].dtype if outs else x.dtype
+        local = torch.zeros((sh.chunk * N, C, g.tile_h, g.tile_w), dtype=dt, device=x.device)
+        if outs:
+            torch.cat(outs, dim=0, out=local[:sh.num_local * N])
+        gathered = parallel.gather_tile_outputs(local, self._shard_group)
+        chunks = []
+        for b in range(sh.num_chunks):
+            nt = min(sh.chunk, sh.num_tiles - b * sh.chunk)
+            chunks.append(gathered[b * sh.chunk * N:(b * sh.chunk + nt) * N])
+        return engine.blend_mixture(g, chunks, N, C, sh.chunk, self.tile_weights, self.rescale_factor, self.x_buffer,
+                                    flags=self._blend_flags)
 
     def custom_apply_model(self, x_in: Tensor, t_in: Tensor, c_in: CondDict, bbox_id: int, bbox: CustomBBox) -> Tensor:
         """mixtureofdiffusers.py:181-196: a region goes through the un-hijacked `apply_model` with its own prompts."""

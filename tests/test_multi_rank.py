@@ -76,6 +76,85 @@ def test_gloo_world2_sharded_step_equals_single(tmp_path):
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
 
 
+def _gloo_delegate_worker(rank, world, port, result_dir):
+    """The tile-sharded DELEGATES (MultiDiffusion all-gather path, Mixture of Diffusers) on CPU tensors over gloo, with the
+    device kernels swapped for the oracle's scatter / blend: every rank must return the single-process result."""
+    from multidiffusion_upscaler_for_automatic1111_b200 import MixtureOfDiffusers, MultiDiffusion, engine, host
+    from multidiffusion_upscaler_for_automatic1111_b200.tile_methods import abstractdiffusion
+
+    def bbs(g):
+        return [tuple(int(v) for v in r) for r in engine.grid_bboxes_xywh(g)]
+
+    def scatter_tiles(g, x, out=None, tile_begin=0, tile_end=None, flags=0):
+        return blend.scatter_tiles(x, bbs(g)[tile_begin:tile_end])
+
+    def blend_multidiffusion(g, outs, N, C, tile_bs, weights, acc_dtype, x_buffer=None, flags=0, out=None, rcp_weights=None):
+        buf = torch.zeros((N, C, g.H, g.W), dtype=acc_dtype)
+        blend.accumulate_md(buf, torch.cat(list(outs), dim=0), bbs(g), N)
+        return blend.normalise_md(buf, weights)
+
+    def blend_mixture(g, outs, N, C, tile_bs, tile_weights, rescale, x_buffer, flags=0):
+        x_buffer.zero_()
+        blend.accumulate_mod(x_buffer, torch.cat(list(outs), dim=0), bbs(g), N, tile_weights, rescale)
+        return x_buffer
+    engine.scatter_tiles, engine.blend_multidiffusion, engine.blend_mixture = scatter_tiles, blend_multidiffusion, blend_mixture
+    abstractdiffusion.AbstractDiffusion._check_input = lambda self, x: x.contiguous()
+
+    _init(rank, world, port, "gloo")
+    try:
+        for c in (CASE, dict(CASE, W=160, H=64, tw=32, th=24, ov=8, bs=2)):
+            N = c["N"]
+            x = synth.latent(19, (N, c["C"], c["H"], c["W"]), torch.float16)
+            p = types.SimpleNamespace(width=c["W"] * 8, height=c["H"] * 8, sampler_name="Euler a")
+            cond = {"c_crossattn": [torch.zeros(N, 77, 8)], "c_concat": [torch.zeros(N, 5, 1, 1)]}
+            state = {"i": 0}
+
+            # MultiDiffusion, all-gather exchange
+            def unet(x_tile, sigma, cond=None):
+                bb = d.local_batched_bboxes[state["i"]]
+                state["i"] += 1
+                return synth.fake_denoise(x_tile, bb, N)
+            sampler = types.SimpleNamespace(model_wrap_cfg=types.SimpleNamespace(inner_model=types.SimpleNamespace(forward=unet), image_cfg_scale=None))
+            d = MultiDiffusion(p, sampler)
+            d.init_grid_bbox(c["tw"], c["th"], c["ov"], c["bs"])
+            d.init_done()
+            sh = d.init_tile_shard(None, fused=False)
+            d.hook()
+            out = sampler.model_wrap_cfg.inner_model.forward(x, torch.ones(N), cond=cond)
+            _, want = _oracle(c, x)
+            assert torch.equal(out, want), f"rank {rank}: sharded MultiDiffusion delegate differs"
+            assert state["i"] == len(d.local_batched_bboxes) and sum(len(b) for b in d.local_batched_bboxes) == sh.num_local
+
+            # Mixture of Diffusers
+            state["i"] = 0
+
+            def apply_model(x_tile, t, c_):
+                bb = m.local_batched_bboxes[state["i"]]
+                state["i"] += 1
+                return synth.fake_denoise(x_tile, bb, N)
+            model = types.SimpleNamespace(apply_model=apply_model, cond_stage_key="txt", model=types.SimpleNamespace(conditioning_key="crossattn"))
+            host.use_shared(types.SimpleNamespace(state=types.SimpleNamespace(interrupted=False, sampling_step=0, sampling_steps=1), sd_model=model))
+            m = MixtureOfDiffusers(p, types.SimpleNamespace(model_wrap_cfg=types.SimpleNamespace(inner_model=types.SimpleNamespace(forward=None), image_cfg_scale=None)))
+            m.init_grid_bbox(c["tw"], c["th"], c["ov"], c["bs"])
+            m.init_done()
+            m.init_tile_shard(None)
+            m.hook()
+            got = model.apply_model(x, torch.ones(N), cond).clone()
+            MixtureOfDiffusers.unhook()
+            plan = tiling.GridPlan(c["W"], c["H"], c["tw"], c["th"], c["ov"], c["bs"], True)
+            want = blend.mixture_step(x, plan.batched_bboxes, plan.tile_weights, plan.rescale_factor, lambda t, bb: synth.fake_denoise(t, bb, N))
+            assert torch.equal(got, want), f"rank {rank}: sharded Mixture of Diffusers delegate differs"
+            host.use_shared(None)
+        open(os.path.join(result_dir, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_delegates_equal_single(tmp_path):
+    mp.spawn(_gloo_delegate_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
 # ------------------------------------------------------------------------------------------- GPU
 def _gpu_worker(rank, world, port, result_dir):
     from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
@@ -137,4 +216,51 @@ def test_two_gpu_sharded_multidiffusion_bit_identical(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     mp.spawn(_gpu_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def _gpu_mod_worker(rank, world, port, result_dir):
+    from multidiffusion_upscaler_for_automatic1111_b200 import MixtureOfDiffusers, host
+    torch.cuda.set_device(rank)
+    _init(rank, world, port, "nccl")
+    try:
+        for c in (CASE, CASE2):
+            N = c["N"]
+            x = synth.latent(29, (N, c["C"], c["H"], c["W"]), torch.float16)
+            plan = tiling.GridPlan(c["W"], c["H"], c["tw"], c["th"], c["ov"], c["bs"], True)
+            want = blend.mixture_step(x, plan.batched_bboxes, plan.tile_weights, plan.rescale_factor, lambda t, bb: synth.fake_denoise(t, bb, N))
+            state = {"i": 0}
+
+            def apply_model(x_tile, t, c_):
+                bb = m.local_batched_bboxes[state["i"]]
+                state["i"] += 1
+                return synth.fake_denoise(x_tile, bb, N)
+            model = types.SimpleNamespace(apply_model=apply_model, cond_stage_key="txt", model=types.SimpleNamespace(conditioning_key="crossattn"))
+            host.use_shared(types.SimpleNamespace(state=types.SimpleNamespace(interrupted=False, sampling_step=0, sampling_steps=1), sd_model=model))
+            p = types.SimpleNamespace(width=c["W"] * 8, height=c["H"] * 8, sampler_name="Euler a")
+            m = MixtureOfDiffusers(p, types.SimpleNamespace(model_wrap_cfg=types.SimpleNamespace(inner_model=types.SimpleNamespace(forward=None), image_cfg_scale=None)))
+            m.init_grid_bbox(c["tw"], c["th"], c["ov"], c["bs"])
+            m.init_done()
+            m.init_tile_shard(None)
+            m.hook()
+            cond = {"c_crossattn": [torch.zeros(N, 77, 8, device="cuda")], "c_concat": [torch.zeros(N, 5, 1, 1, device="cuda")]}
+            for step in range(2):
+                state["i"] = 0
+                got = model.apply_model(x.cuda(), torch.ones(N, device="cuda"), cond)
+                torch.cuda.synchronize()
+                assert torch.equal(got.cpu(), want), f"rank {rank} step {step}: sharded Mixture of Diffusers differs"
+            MixtureOfDiffusers.unhook()
+            host.use_shared(None)
+        open(os.path.join(result_dir, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+# first hardware run pending (written after the round-1 GPU budget was spent)
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="sharded Mixture of Diffusers: first hardware run pending")
+def test_two_gpu_sharded_mixture_bit_identical(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    mp.spawn(_gpu_mod_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
