@@ -1,6 +1,7 @@
+# Debug helper (test infrastructure, run by hand on a GPU box): may use oracle/ as the checker.
 """Debug helper (GPU box): where does a blend path differ from the oracle?"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from multidiffusion_upscaler_for_automatic1111_b200 import engine
 from oracle import blend, synth, tiling
