@@ -148,3 +148,73 @@ def blend_mixture(g: TdGrid, batch_outs: Sequence[torch.Tensor], N: int, C: int,
                                    dtype_code(x_buffer.dtype), tile_weights.data_ptr(), rescale.data_ptr(),
                                    x_buffer.data_ptr(), int(flags), current_stream_ptr(dev)))
     return x_buffer
+
+
+# ---------------------------------------------------------------------------------------------------------
+# DemoFusion (tile_methods/demofusion.py): thin wrappers over the C-ABI, one launch each
+# ---------------------------------------------------------------------------------------------------------
+def dilated_gather(x: torch.Tensor, x_second: Optional[torch.Tensor], view_bx: Sequence[int], view_by: Sequence[int],
+                   view_second: Sequence[int], s: int, out_h: int, out_w: int) -> torch.Tensor:
+    """demofusion.py:283-308: out[(v*N+n), c, i, j] = src_v[n, c, by_v + i*s, bx_v + j*s]; src_v = x_second where
+    view_second[v] else x."""
+    _require_cuda(x, "x")
+    N, C, H, W = x.shape
+    n = len(view_bx)
+    out = torch.empty((n * N, C, out_h, out_w), dtype=x.dtype, device=x.device)
+    arr = lambda v: (ctypes.c_int32 * n)(*[int(i) for i in v])
+    with torch.cuda.device(x.device):
+        check(lib.td_dilated_gather(x.data_ptr(), x_second.data_ptr() if x_second is not None else None, out.data_ptr(), N, C, H, W,
+                                    int(s), int(out_h), int(out_w), arr(view_bx), arr(view_by), arr(view_second), n,
+                                    dtype_code(x.dtype), current_stream_ptr(x.device)))
+    return out
+
+
+def demofusion_combine(x_local: torch.Tensor, view_outs: Sequence[torch.Tensor], views_per_batch: int, n_views: int, s: int,
+                       out_h: int, out_w: int, offset: int, end_y: int, end_x: int, mixture: bool, c2: float,
+                       one_minus_c2: float) -> torch.Tensor:
+    """demofusion.py:296-322 in one launch: strided add-back of the view outputs (in view order, rounded through the
+    dtype), `/ 2` in mixture mode, out = x_local*(1-c2) + x_global*c2.  `offset` = jitter_range (0: td_demofusion_combine)."""
+    _require_cuda(x_local, "x_local")
+    N, C, H, W = x_local.shape
+    dev, dt = x_local.device, x_local.dtype
+    out = torch.empty_like(x_local)
+    ptrs = (ctypes.c_void_p * len(view_outs))(*[t.data_ptr() for t in view_outs])
+    with torch.cuda.device(dev):
+        if offset:
+            check(lib.td_demofusion_combine_offset(x_local.data_ptr(), ptrs, len(view_outs), int(views_per_batch), int(n_views),
+                                                   out.data_ptr(), N, C, H, W, int(s), int(out_h), int(out_w), int(offset), int(end_y),
+                                                   int(end_x), int(bool(mixture)), c2, one_minus_c2, dtype_code(dt),
+                                                   current_stream_ptr(dev)))
+        else:
+            check(lib.td_demofusion_combine(x_local.data_ptr(), ptrs, len(view_outs), int(views_per_batch), int(n_views), out.data_ptr(),
+                                            N, C, H, W, int(s), int(out_h), int(out_w), int(end_y), int(end_x), int(bool(mixture)), c2,
+                                            one_minus_c2, dtype_code(dt), current_stream_ptr(dev)))
+    return out
+
+
+def scatter_bboxes(x: torch.Tensor, origins_dev: torch.Tensor, origins_host, n_tiles: int, tile_h: int, tile_w: int,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Window LIST scatter (DemoFusion random jitter, demofusion.py:256): tiles[(t*N+n), c] = x[n, c, window t]."""
+    _require_cuda(x, "x")
+    N, C, H, W = x.shape
+    shape = (n_tiles * N, C, tile_h, tile_w)
+    if out is None or tuple(out.shape) != shape or out.dtype != x.dtype or out.device != x.device:
+        out = torch.empty(shape, dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.td_scatter_bboxes(x.data_ptr(), out.data_ptr(), origins_dev.data_ptr(), origins_host, int(n_tiles), N, C, H, W,
+                                    int(tile_h), int(tile_w), dtype_code(x.dtype), current_stream_ptr(x.device)))
+    return out
+
+
+def blend_bboxes(batch_outs: Sequence[torch.Tensor], tile_bs: int, origins_dev: torch.Tensor, origins_host, n_tiles: int, N: int, C: int,
+                 H: int, W: int, tile_h: int, tile_w: int) -> torch.Tensor:
+    """Window LIST count-normalised blend (demofusion.py:259-264): fp32 [N,C,H,W] = ordered sum (rounded through the tile
+    dtype per add) / max(count, 1)."""
+    dev, dt = batch_outs[0].device, batch_outs[0].dtype
+    _require_cuda(batch_outs[0], "tile output")
+    ptrs = (ctypes.c_void_p * len(batch_outs))(*[t.data_ptr() for t in batch_outs])
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.td_blend_bboxes(ptrs, len(batch_outs), int(tile_bs), origins_dev.data_ptr(), origins_host, int(n_tiles), N, C, H, W,
+                                  int(tile_h), int(tile_w), dtype_code(dt), out.data_ptr(), current_stream_ptr(dev)))
+    return out

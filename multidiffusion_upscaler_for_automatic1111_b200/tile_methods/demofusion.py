@@ -299,28 +299,14 @@ class DemoFusion(AbstractDiffusion):
             n = len(bboxes)
             second = [1 if not (p.mixture and (seen + i) < half) else 0 for i in range(n)]
             seen += n
-            view = torch.empty((n * N, C, oh, ow), dtype=dt, device=dev)
-            arr = lambda v: (ctypes.c_int32 * n)(*v)
-            with torch.cuda.device(dev):
-                check(lib.td_dilated_gather(x.data_ptr(), x_in_g.data_ptr() if x_in_g is not None else None, view.data_ptr(), N, C, H, W,
-                                            s, oh, ow, arr([b[0] + jr for b in bboxes]), arr([b[1] + jr for b in bboxes]), arr(second), n,
-                                            dtype_code(dt), current_stream_ptr(dev)))
+            view = engine.dilated_gather(x, x_in_g, [b[0] + jr for b in bboxes], [b[1] + jr for b in bboxes], second, s, oh, ow)
             g_outs.append(repeat_func(view, bboxes, mode=1).to(dt).contiguous())
 
         # ---- add-back, /2, and the c2 mix: one launch ------------------------------------------------------------------
         c2 = float(self.cosine_factor ** p.cosine_scale_2)
         one_minus_c2 = float(1 - self.cosine_factor ** p.cosine_scale_2)
-        out = torch.empty_like(x_local)
-        ptrs = (ctypes.c_void_p * len(g_outs))(*[t.data_ptr() for t in g_outs])
-        with torch.cuda.device(dev):
-            if jr:
-                check(lib.td_demofusion_combine_offset(x_local.data_ptr(), ptrs, len(g_outs), self.global_tile_bs, self.global_num_tiles,
-                                                       out.data_ptr(), N, C, H, W, s, oh, ow, jr, end_y, end_x, int(bool(p.mixture)), c2,
-                                                       one_minus_c2, dtype_code(dt), current_stream_ptr(dev)))
-            else:
-                check(lib.td_demofusion_combine(x_local.data_ptr(), ptrs, len(g_outs), self.global_tile_bs, self.global_num_tiles,
-                                                out.data_ptr(), N, C, H, W, s, oh, ow, end_y, end_x, int(bool(p.mixture)), c2, one_minus_c2,
-                                                dtype_code(dt), current_stream_ptr(dev)))
+        out = engine.demofusion_combine(x_local, g_outs, self.global_tile_bs, self.global_num_tiles, s, oh, ow, jr, end_y, end_x,
+                                        bool(p.mixture), c2, one_minus_c2)
         self.x_buffer = out
         return out
 
@@ -331,23 +317,13 @@ class DemoFusion(AbstractDiffusion):
         dt, dev, ws, T = x.dtype, x.device, self.window_size, self.num_tiles
         if self._origins_dev.device != dev:
             self._origins_dev = self._origins_dev.to(dev)
-        shape = (T * N, C, ws, ws)
-        if self._tiles is None or tuple(self._tiles.shape) != shape or self._tiles.dtype != dt or self._tiles.device != dev:
-            self._tiles = torch.empty(shape, dtype=dt, device=dev)
-        with torch.cuda.device(dev):
-            check(lib.td_scatter_bboxes(x.data_ptr(), self._tiles.data_ptr(), self._origins_dev.data_ptr(), self._origins_host, T, N, C, H, W,
-                                        ws, ws, dtype_code(dt), current_stream_ptr(dev)))
+        self._tiles = engine.scatter_bboxes(x, self._origins_dev, self._origins_host, T, ws, ws, out=self._tiles)
         outs = []
         for batch_id, bboxes in enumerate(self.batched_bboxes):
             if host.interrupted():
                 return None
             outs.append(repeat_func(self._tile_batch(self._tiles, batch_id, N), bboxes).to(dt).contiguous())
-        ptrs = (ctypes.c_void_p * len(outs))(*[t.data_ptr() for t in outs])
-        x_local = torch.empty((N, C, H, W), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            check(lib.td_blend_bboxes(ptrs, len(outs), self.tile_bs, self._origins_dev.data_ptr(), self._origins_host, T, N, C, H, W, ws, ws,
-                                      dtype_code(dt), x_local.data_ptr(), current_stream_ptr(dev)))
-        return x_local.to(dt)
+        return engine.blend_bboxes(outs, self.tile_bs, self._origins_dev, self._origins_host, T, N, C, H, W, ws, ws).to(dt)
 
     def get_noise(self, x_in: Tensor, sigma_in: Tensor, cond_in: Dict[str, Tensor], step: int) -> Tensor:
         """demofusion.py:345-353: the tiled eps on the latent padded by jitter_range, cropped back."""
