@@ -39,6 +39,8 @@ class DemoFusion(AbstractDiffusion):
         self._jitter = False                 # window LIST (random jitter) instead of the separable grid
         self._origins_host = None
         self._origins_dev = None
+        self._shard_on = False               # tile shard requested (init_tile_shard); re-derived by every get_views
+        self._view_shard = None
 
     def _check_input(self, x_in: Tensor) -> Tensor:
         if not self._jitter:
@@ -150,6 +152,47 @@ class DemoFusion(AbstractDiffusion):
         self.global_tile_bs = math.ceil(len(global_bboxes) / self.global_num_batches)
         self.global_batched_bboxes = [global_bboxes[i * self.global_tile_bs:(i + 1) * self.global_tile_bs]
                                       for i in range(self.global_num_batches)]
+        if self._shard_on:
+            self._derive_shards()
+
+    # ------------------------------------------------------------------ multi-GPU
+    def init_tile_shard(self, group=None, fused: bool = False):
+        """Shard the local windows AND the s*s global views over the ranks of `group` (one process per GPU): contiguous
+        chunks of both lists; per step two all-gathers (window outputs, view outputs), then every rank runs the same
+        ordered blend / add-back -- bit-identical across ranks and to a single-GPU run.  Survives get_views() (each
+        upscaling phase rebuilds the lists).  With random jitter every rank must draw the same windows: seed Python's
+        `random` identically on all ranks before get_views()."""
+        if fused:
+            raise NotImplementedError("DemoFusion shards through all-gather; the fused peer exchange is MultiDiffusion-only")
+        self._shard_on, self._shard_group = True, group
+        if self.batched_bboxes:
+            self._derive_shards()
+        return self._shard
+
+    def _derive_shards(self):
+        import torch.distributed as dist
+        from .. import parallel
+        rank, world = dist.get_rank(self._shard_group), dist.get_world_size(self._shard_group)
+        self._shard = parallel.TileShard(self.num_tiles, rank, world)
+        self._view_shard = parallel.TileShard(self.global_num_tiles, rank, world)
+        windows = [b for batch in self.batched_bboxes for b in batch][self._shard.begin:self._shard.end]
+        self.local_batched_bboxes = [windows[i:i + self.tile_bs] for i in range(0, len(windows), self.tile_bs)]
+        views = [v for batch in self.global_batched_bboxes for v in batch][self._view_shard.begin:self._view_shard.end]
+        self.local_global_batched_bboxes = [views[i:i + self.global_tile_bs] for i in range(0, len(views), self.global_tile_bs)]
+
+    def _gather_chunks(self, outs, sh, rows_per_unit: int, unit_shape, dt, dev):
+        """Pad this rank's outputs to the chunk size, all-gather, and return one tensor view per rank chunk (exact unit
+        counts) -- the pointer-table form the blend / combine kernels take (`tile_bs` = chunk)."""
+        from .. import parallel
+        local = torch.zeros((sh.chunk * rows_per_unit,) + tuple(unit_shape), dtype=dt, device=dev)
+        if outs:
+            torch.cat(outs, dim=0, out=local[:sh.num_local * rows_per_unit])
+        gathered = parallel.gather_tile_outputs(local, self._shard_group)
+        chunks = []
+        for b in range(sh.num_chunks):
+            n = min(sh.chunk, sh.num_tiles - b * sh.chunk)
+            chunks.append(gathered[b * sh.chunk * rows_per_unit:(b * sh.chunk + n) * rows_per_unit])
+        return chunks
 
     def repeat_cond_dict(self, cond_in: CondDict, bboxes, mode) -> CondDict:
         """demofusion.py:60-84: text / vector cond repeated; spatial icond cropped (local) or dilated (global)."""
@@ -262,7 +305,11 @@ class DemoFusion(AbstractDiffusion):
         s = int(p.current_scale_num)
 
         # ---- local windows: count-normalised blend (buffer / count, both in x.dtype) ----------------------------
-        if self._jitter:
+        if self._shard_on:
+            x_local = self._local_pass_sharded(x, repeat_func)
+            if x_local is None:
+                return x_in
+        elif self._jitter:
             x_local = self._local_pass_window_list(x_in, x, repeat_func)
             if x_local is None:
                 return x_in
@@ -294,21 +341,55 @@ class DemoFusion(AbstractDiffusion):
         if any(len(range(jr + b, end_y, s)) != oh for b in range(s)) or any(len(range(jr + b, end_x, s)) != ow for b in range(s)):
             raise ValueError("latent size must be a multiple of the scale (the reference's torch.cat needs equal views)")
         half = self.global_num_tiles // 2
-        g_outs, seen = [], 0
-        for bboxes in self.global_batched_bboxes:
+        view_batches = self.local_global_batched_bboxes if self._shard_on else self.global_batched_bboxes
+        g_outs, seen = [], (self._view_shard.begin if self._shard_on else 0)
+        for bboxes in view_batches:
             n = len(bboxes)
             second = [1 if not (p.mixture and (seen + i) < half) else 0 for i in range(n)]
             seen += n
             view = engine.dilated_gather(x, x_in_g, [b[0] + jr for b in bboxes], [b[1] + jr for b in bboxes], second, s, oh, ow)
             g_outs.append(repeat_func(view, bboxes, mode=1).to(dt).contiguous())
+        views_per_batch = self.global_tile_bs
+        if self._shard_on:      # every rank needs every view's output: all-gather, one pointer-table entry per rank chunk
+            g_outs = self._gather_chunks(g_outs, self._view_shard, N, (C, oh, ow), dt, dev)
+            views_per_batch = self._view_shard.chunk
 
         # ---- add-back, /2, and the c2 mix: one launch ------------------------------------------------------------------
         c2 = float(self.cosine_factor ** p.cosine_scale_2)
         one_minus_c2 = float(1 - self.cosine_factor ** p.cosine_scale_2)
-        out = engine.demofusion_combine(x_local, g_outs, self.global_tile_bs, self.global_num_tiles, s, oh, ow, jr, end_y, end_x,
+        out = engine.demofusion_combine(x_local, g_outs, views_per_batch, self.global_num_tiles, s, oh, ow, jr, end_y, end_x,
                                         bool(p.mixture), c2, one_minus_c2)
         self.x_buffer = out
         return out
+
+    def _local_pass_sharded(self, x: Tensor, repeat_func):
+        """Local windows with the tile shard: this rank scatters and denoises its chunk of the window list (grid or
+        jittered), the outputs are all-gathered, every rank blends all windows.  None when interrupted."""
+        N, C, H, W = x.shape
+        dt, dev, ws, sh = x.dtype, x.device, self.window_size, self._shard
+        outs = []
+        if sh.num_local > 0:
+            if self._jitter:
+                if self._origins_dev.device != dev:
+                    self._origins_dev = self._origins_dev.to(dev)
+                host_part = (ctypes.c_int32 * (2 * sh.num_local))(*self._origins_host[2 * sh.begin:2 * sh.end])
+                tiles = engine.scatter_bboxes(x, self._origins_dev[2 * sh.begin:2 * sh.end], host_part, sh.num_local, ws, ws)
+            else:
+                tiles = engine.scatter_tiles(self._grid, x, tile_begin=sh.begin, tile_end=sh.end, flags=self._blend_flags)
+            off = 0
+            for bboxes in self.local_batched_bboxes:
+                if host.interrupted():
+                    return None
+                outs.append(repeat_func(tiles[off * N:(off + len(bboxes)) * N], bboxes).to(dt).contiguous())
+                off += len(bboxes)
+        chunks = self._gather_chunks(outs, sh, N, (C, ws, ws), dt, dev)
+        if self._jitter:
+            return engine.blend_bboxes(chunks, sh.chunk, self._origins_dev, self._origins_host, self.num_tiles, N, C, H, W, ws, ws).to(dt)
+        if self._counts.device != dev:
+            self._counts, self._rcp_counts = self._counts.to(dev), self._rcp_counts.to(dev)
+        rcp = self._rcp_counts if dt in (torch.float16, torch.bfloat16) else None
+        return engine.blend_multidiffusion(self._grid, chunks, N, C, sh.chunk, self._counts, dt, flags=self._blend_flags,
+                                           rcp_weights=rcp).to(dt)
 
     def _local_pass_window_list(self, x_in: Tensor, x: Tensor, repeat_func):
         """Local windows in random-jitter mode (demofusion.py:254-264): one list-driven scatter, the UNet per batch, one

@@ -155,6 +155,58 @@ def test_gloo_world2_sharded_delegates_equal_single(tmp_path):
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
 
 
+def _gloo_demofusion_worker(rank, world, port, result_dir):
+    """Tile-sharded DemoFusion (local windows and global views split over the ranks, grid and random jitter) on CPU
+    stand-ins over gloo: every rank must reproduce the single-process oracle."""
+    from helpers import DTYPES, install_demofusion_stand_ins
+    from oracle import demofusion as odf
+    from oracle.make_golden import DEMO_CFG, demo_denoise, position_aware_denoise
+    from test_demofusion import _jitter_delegate, _jitter_oracle, _jitter_p, _oracle
+    from multidiffusion_upscaler_for_automatic1111_b200 import DemoFusion
+    install_demofusion_stand_ins()
+    _init(rank, world, port, "gloo")
+    try:
+        c = DEMO_CFG
+        for jitter, dn, mixture in [(False, "f32", True), (False, "f16", False), (True, "f32", True), (True, "f16", False)]:
+            if jitter:
+                x, x_step, want, local, sizes = _jitter_oracle(DTYPES[dn], mixture)
+                d = _jitter_delegate(mixture)            # same seed on every rank -> same windows
+                unet = position_aware_denoise(d)
+            else:
+                x, want, local, sizes = _oracle(DTYPES[dn], mixture)
+                x_step = x
+                p = _jitter_p(mixture)
+                p.random_jitter = False
+                inner = types.SimpleNamespace(forward=None)
+                d = DemoFusion(p, types.SimpleNamespace(model_wrap_cfg=types.SimpleNamespace(inner_model=inner, image_cfg_scale=None, forward=None)))
+                d.window_size, d.sig = c["window"], c["sig"]
+                d.get_views(c["overlap"], c["tile_bs"], c["tile_bs_g"])
+                unet = lambda xt, sigma, cond=None: demo_denoise(xt)
+            calls = []
+
+            def counted(xt, sigma, cond=None, unet=unet):
+                calls.append(xt.shape[0] // c["N"])
+                return unet(xt, sigma, cond=cond)
+            d.sampler_forward = counted
+            sh = d.init_tile_shard(None)
+            assert sh.num_tiles == len(local) and d._view_shard.num_tiles == sizes[2]
+            d.cosine_factor = odf.cosine_factor(c["current_step"], c["t_enc"])
+            cond = {"c_crossattn": [torch.zeros(c["N"], 77, 8)], "c_concat": [torch.zeros(c["N"], 5, 1, 1)]}
+            got = d.sample_one_step(x_step, torch.ones(c["N"]), cond)
+            tol = 3e-6 if dn == "f32" else 2e-3
+            err = (got.float() - want.float()).abs().max().item()
+            assert got.shape == want.shape and err <= tol * max(1.0, want.float().abs().max().item()), f"rank {rank} jitter={jitter} {dn}: err {err}"
+            assert sum(calls) == sh.num_local + d._view_shard.num_local      # this rank denoised only its own windows and views
+        open(os.path.join(result_dir, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_demofusion_equals_single(tmp_path):
+    mp.spawn(_gloo_demofusion_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
 # ------------------------------------------------------------------------------------------- GPU
 def _gpu_worker(rank, world, port, result_dir):
     from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
@@ -263,4 +315,52 @@ def test_two_gpu_sharded_mixture_bit_identical(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     mp.spawn(_gpu_mod_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def _gpu_demofusion_worker(rank, world, port, result_dir):
+    from helpers import DTYPES
+    from oracle import demofusion as odf
+    from oracle.make_golden import DEMO_CFG, demo_denoise, position_aware_denoise
+    from test_demofusion import _jitter_delegate, _jitter_oracle, _jitter_p, _oracle
+    from multidiffusion_upscaler_for_automatic1111_b200 import DemoFusion
+    torch.cuda.set_device(rank)
+    _init(rank, world, port, "nccl")
+    try:
+        c = DEMO_CFG
+        for jitter, dn, mixture in [(False, "f32", True), (False, "f16", False), (True, "f32", True)]:
+            if jitter:
+                x, x_step, want, local, sizes = _jitter_oracle(DTYPES[dn], mixture)
+                d = _jitter_delegate(mixture)
+                d.sampler_forward = position_aware_denoise(d)
+            else:
+                x, want, local, sizes = _oracle(DTYPES[dn], mixture)
+                x_step = x
+                p = _jitter_p(mixture)
+                p.random_jitter = False
+                inner = types.SimpleNamespace(forward=None)
+                d = DemoFusion(p, types.SimpleNamespace(model_wrap_cfg=types.SimpleNamespace(inner_model=inner, image_cfg_scale=None, forward=None)))
+                d.window_size, d.sig = c["window"], c["sig"]
+                d.get_views(c["overlap"], c["tile_bs"], c["tile_bs_g"])
+                d.sampler_forward = lambda xt, sigma, cond=None: demo_denoise(xt)
+            d.init_tile_shard(None)
+            d.cosine_factor = odf.cosine_factor(c["current_step"], c["t_enc"])
+            cond = {"c_crossattn": [torch.zeros(c["N"], 77, 8, device="cuda")], "c_concat": [torch.zeros(c["N"], 5, 1, 1, device="cuda")]}
+            got = d.sample_one_step(x_step.cuda(), torch.ones(c["N"], device="cuda"), cond)
+            torch.cuda.synchronize()
+            tol = 3e-6 if dn == "f32" else 2e-3
+            err = (got.cpu().float() - want.float()).abs().max().item()
+            assert err <= tol * max(1.0, want.float().abs().max().item()), f"rank {rank} jitter={jitter} {dn}: err {err}"
+        open(os.path.join(result_dir, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+# first hardware run pending (written after the round-1 GPU budget was spent)
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="sharded DemoFusion: first hardware run pending")
+def test_two_gpu_sharded_demofusion_matches_oracle(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    mp.spawn(_gpu_demofusion_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
