@@ -212,17 +212,3 @@ def test_interrupt_during_region_pass_returns_input(monkeypatch):
         assert d.sample_one_step(x, None, lambda t, bb: t, custom) is x
     finally:
         host.use_shared(None)
-
-
-# the device run of the same delegates: first executed on hardware by the round-end driver (the round-1 GPU budget was
-# spent before this row was written), hence non-strict: XPASS = verified, XFAIL = a device-placement bug to fix.
-@pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="region prompt control: first hardware run pending (kernels themselves are pinned elsewhere)")
-@pytest.mark.parametrize("case", REGION_CASES, ids=[c[0] for c in REGION_CASES])
-@pytest.mark.parametrize("method", ["md", "mod"])
-@pytest.mark.parametrize("dn", REGION_DTYPES)
-def test_delegate_region_step_on_gpu(gold, case, method, dn):
-    name, bg, rows = case
-    d, out = _run_delegate(method, _x(name, dn), bg, rows, "cuda")
-    assert out.is_cuda
-    assert_bit_equal(out, _want(gold, f"{name}_{method}_{dn}"), f"{method} delegate, sm_100a kernels")
