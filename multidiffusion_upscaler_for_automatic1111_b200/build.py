@@ -44,6 +44,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in _deps())
 
 
+def build_variant(out_path: str, defines) -> str:
+    """Tuning aid: the same sources with extra -D knobs (TD_AS_ROWS, TD_AS_X, TD_AS_PPC ...) into `out_path`;
+    load it with TD_B200_LIB=<out_path> (bench.py, tests).  Never replaces the default library."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    os.makedirs(os.path.dirname(os.path.abspath(out_path)) or ".", exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")]
+    cmd = [nvcc, *flags, *[f"-D{d}" for d in defines], "-I", INCLUDE, "-I", CSRC, "-o", out_path, *sources()]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + (res.stdout + res.stderr)[-8000:])
+    return out_path
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into libtd_b200.so; returns its path."""
     if not force and not needs_build():
@@ -66,4 +79,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:      # python build.py --variant build/variants/libtd_x16.so TD_AS_X=16 TD_AS_PPC=1
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

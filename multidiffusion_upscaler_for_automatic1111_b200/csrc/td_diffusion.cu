@@ -369,7 +369,10 @@ blend_grid_vec_kernel(const __grid_constant__ BlendParams p, const float* __rest
 // -- correctly rounded for every 16-bit numerator and w <= 4096 (checked exhaustively by
 // td_debug_check_fast_div / tests).
 // ---------------------------------------------------------------------------
-constexpr int kAsX = 8;                          // vectors per patch row
+#ifndef TD_AS_X
+#define TD_AS_X 8                                // tuning knob (-DTD_AS_X=): vectors per patch row
+#endif
+constexpr int kAsX = TD_AS_X;                    // vectors per patch row
 #ifndef TD_AS_ROWS
 #define TD_AS_ROWS 8                             // tuning knob (-DTD_AS_ROWS=): 8 / 16 / 32 measured 8.89 / 9.18 / 10.7 us (cfg2), 8 kept
 #endif
