@@ -24,20 +24,74 @@ namespace {
 
 using namespace td;
 
+// The per-element bodies are __host__ __device__ so that the index arithmetic and the rounding sequence of these
+// kernels can also be executed on a CPU by the test-only harness tests/emul/jitter_host_emul.cu (the product
+// library never runs them on the host: there is no CPU path).
+template <typename T> struct JElem;
+template <> struct JElem<__half> {
+    static __host__ __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+    static __host__ __device__ __forceinline__ __half from_f32(float f) { return __float2half_rn(f); }
+};
+template <> struct JElem<__nv_bfloat16> {
+    static __host__ __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+    static __host__ __device__ __forceinline__ __nv_bfloat16 from_f32(float f) { return __float2bfloat16_rn(f); }
+};
+template <> struct JElem<float> {
+    static __host__ __device__ __forceinline__ float to_f32(float v) { return v; }
+    static __host__ __device__ __forceinline__ float from_f32(float f) { return f; }
+};
+template <typename T> __host__ __device__ __forceinline__ float jround(float f) { return JElem<T>::to_f32(JElem<T>::from_f32(f)); }
+
+// single IEEE roundings, never contracted into an FMA (the host build uses -ffp-contract=off)
+__host__ __device__ __forceinline__ float jadd(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+__host__ __device__ __forceinline__ float jmul(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+__host__ __device__ __forceinline__ float jdiv(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+__host__ __device__ __forceinline__ int jload(const int32_t* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// tiles[e] for the flat tile-batch index e = ((t*NC + plane)*th + v)*tw + u
+template <typename T>
+__host__ __device__ __forceinline__ T scatter_bboxes_elem(const T* __restrict__ x, const int32_t* __restrict__ origins, int NC, int H,
+                                                          int W, int th, int tw, long long e) {
+    const int u = (int)(e % tw);
+    long long r = e / tw;
+    const int v = (int)(r % th);
+    r /= th;
+    const int plane = (int)(r % NC);
+    const int t = (int)(r / NC);
+    const int ox = jload(origins + 2 * t), oy = jload(origins + 2 * t + 1);
+    return x[((long long)plane * H + oy + v) * W + ox + u];
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 scatter_bboxes_kernel(const T* __restrict__ x, T* __restrict__ tiles, const int32_t* __restrict__ origins, int NC, int H, int W,
                       int th, int tw, long long total) {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int u = (int)(e % tw);
-        long long r = e / tw;
-        const int v = (int)(r % th);
-        r /= th;
-        const int plane = (int)(r % NC);
-        const int t = (int)(r / NC);
-        const int ox = __ldg(origins + 2 * t), oy = __ldg(origins + 2 * t + 1);
-        tiles[e] = x[((long long)plane * H + oy + v) * W + ox + u];
-    }
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+        tiles[e] = scatter_bboxes_elem<T>(x, origins, NC, H, W, th, tw, e);
 }
 
 struct BlendListParams {
@@ -47,26 +101,30 @@ struct BlendListParams {
 
 // out[plane, y, x] = acc / max(count, 1); acc = windows covering (y, x) added in list order, each add rounded through T
 template <typename T>
+__host__ __device__ __forceinline__ float blend_bboxes_elem(const BlendListParams& p, const int32_t* __restrict__ origins, long long e) {
+    const int x = (int)(e % p.W);
+    const long long r = e / p.W;
+    const int y = (int)(r % p.H);
+    const int plane = (int)(r / p.H);
+    float acc = 0.0f;
+    int count = 0;
+    for (int t = 0; t < p.n_tiles; ++t) {
+        const int u = x - jload(origins + 2 * t), v = y - jload(origins + 2 * t + 1);
+        if ((unsigned)u >= (unsigned)p.tw || (unsigned)v >= (unsigned)p.th) continue;
+        const int b = t / p.tile_bs, ti = t - b * p.tile_bs;
+        const T* tp = reinterpret_cast<const T*>(p.batch_ptrs[b]) + (((long long)ti * p.NC + plane) * p.th + v) * p.tw + u;
+        acc = jround<T>(jadd(acc, JElem<T>::to_f32(*tp)));
+        ++count;
+    }
+    return count > 1 ? jdiv(acc, (float)count) : acc;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256)
 blend_bboxes_kernel(const __grid_constant__ BlendListParams p, const int32_t* __restrict__ origins, float* __restrict__ out) {
     const long long total = (long long)p.NC * p.H * p.W;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(e % p.W);
-        const long long r = e / p.W;
-        const int y = (int)(r % p.H);
-        const int plane = (int)(r / p.H);
-        float acc = 0.0f;
-        int count = 0;
-        for (int t = 0; t < p.n_tiles; ++t) {
-            const int u = x - __ldg(origins + 2 * t), v = y - __ldg(origins + 2 * t + 1);
-            if ((unsigned)u >= (unsigned)p.tw || (unsigned)v >= (unsigned)p.th) continue;
-            const int b = t / p.tile_bs, ti = t - b * p.tile_bs;
-            const T* tp = reinterpret_cast<const T*>(p.batch_ptrs[b]) + (((long long)ti * p.NC + plane) * p.th + v) * p.tw + u;
-            acc = round_through<T>(__fadd_rn(acc, Elem<T>::to_f32(*tp)));
-            ++count;
-        }
-        out[e] = count > 1 ? __fdiv_rn(acc, (float)count) : acc;
-    }
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+        out[e] = blend_bboxes_elem<T>(p, origins, e);
 }
 
 struct CombineOffsetParams {
@@ -76,35 +134,41 @@ struct CombineOffsetParams {
     const void* batch_ptrs[TD_MAX_BATCH_PTRS];
 };
 
+// out = T(T(x_local * (1-c2)) + T(x_global * c2)),  x_global = (mixture ? T(acc / 2) : acc), acc = the view outputs that
+// land on this pixel added in view order (each add rounded through T); views start at off + (by, bx)
+template <typename T>
+__host__ __device__ __forceinline__ T combine_offset_elem(const CombineOffsetParams& p, const T* __restrict__ x_local, long long e) {
+    const int half = p.mixture ? p.n_views / 2 : p.n_views;
+    const long long view_plane = (long long)p.oh * p.ow;
+    const int x = (int)(e % p.W);
+    const long long r = e / p.W;
+    const int y = (int)(r % p.H);
+    const int plane = (int)(r / p.H);
+    float acc = 0.0f;
+    if (y >= p.off && x >= p.off && y < p.end_y && x < p.end_x) {
+        const int yy = y - p.off, xx = x - p.off;
+        const int by = yy % p.s, bx = xx % p.s, i = yy / p.s, j = xx / p.s;
+        const int v0 = by * p.s + bx;   // views are listed row-major over (by, bx)
+        for (int rep = 0; rep < (p.mixture ? 2 : 1); ++rep) {
+            const int v = v0 + rep * half;
+            const int b = v / p.views_per_batch, vi = v - b * p.views_per_batch;
+            const T* vp = reinterpret_cast<const T*>(p.batch_ptrs[b]) + ((long long)vi * p.NC + plane) * view_plane + (long long)i * p.ow + j;
+            acc = jround<T>(jadd(acc, JElem<T>::to_f32(*vp)));
+        }
+    }
+    float xg = acc;
+    if (p.mixture) xg = jround<T>(jmul(acc, 0.5f));                      // x_global / 2
+    const float a = jround<T>(jmul(JElem<T>::to_f32(x_local[e]), p.one_minus_c2));
+    const float b2 = jround<T>(jmul(xg, p.c2));
+    return JElem<T>::from_f32(jadd(a, b2));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 combine_offset_kernel(const __grid_constant__ CombineOffsetParams p, const T* __restrict__ x_local, T* __restrict__ out) {
     const long long total = (long long)p.NC * p.H * p.W;
-    const int half = p.mixture ? p.n_views / 2 : p.n_views;
-    const long long view_plane = (long long)p.oh * p.ow;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(e % p.W);
-        const long long r = e / p.W;
-        const int y = (int)(r % p.H);
-        const int plane = (int)(r / p.H);
-        float acc = 0.0f;
-        if (y >= p.off && x >= p.off && y < p.end_y && x < p.end_x) {
-            const int yy = y - p.off, xx = x - p.off;
-            const int by = yy % p.s, bx = xx % p.s, i = yy / p.s, j = xx / p.s;
-            const int v0 = by * p.s + bx;   // views are listed row-major over (by, bx)
-            for (int rep = 0; rep < (p.mixture ? 2 : 1); ++rep) {
-                const int v = v0 + rep * half;
-                const int b = v / p.views_per_batch, vi = v - b * p.views_per_batch;
-                const T* vp = reinterpret_cast<const T*>(p.batch_ptrs[b]) + ((long long)vi * p.NC + plane) * view_plane + (long long)i * p.ow + j;
-                acc = round_through<T>(__fadd_rn(acc, Elem<T>::to_f32(*vp)));
-            }
-        }
-        float xg = acc;
-        if (p.mixture) xg = round_through<T>(__fmul_rn(acc, 0.5f));           // x_global / 2
-        const float a = round_through<T>(__fmul_rn(Elem<T>::to_f32(x_local[e]), p.one_minus_c2));
-        const float b2 = round_through<T>(__fmul_rn(xg, p.c2));
-        out[e] = Elem<T>::from_f32(__fadd_rn(a, b2));
-    }
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+        out[e] = combine_offset_elem<T>(p, x_local, e);
 }
 
 int launched(const char* what) {
@@ -204,3 +268,46 @@ extern "C" int td_demofusion_combine_offset(const void* x_local, const void* con
     else { td_set_error("td_demofusion_combine_offset: unknown dtype"); return TD_ERR_INVALID_ARG; }
     return launched("td_demofusion_combine_offset");
 }
+
+#ifdef TD_JITTER_HOST_EMULATION
+// Test-only (tests/emul/jitter_host_emul.cu includes this file with the macro set): run the element bodies on the host.
+extern "C" int td_emul_scatter_bboxes(const void* x, void* tiles, const int32_t* origins, int n_tiles, int N, int C, int H, int W,
+                                      int tile_h, int tile_w, int elem_size) {
+    const long long total = (long long)n_tiles * N * C * tile_h * tile_w;
+    for (long long e = 0; e < total; ++e) {
+        if (elem_size == 2) ((uint16_t*)tiles)[e] = scatter_bboxes_elem<uint16_t>((const uint16_t*)x, origins, N * C, H, W, tile_h, tile_w, e);
+        else ((uint32_t*)tiles)[e] = scatter_bboxes_elem<uint32_t>((const uint32_t*)x, origins, N * C, H, W, tile_h, tile_w, e);
+    }
+    return TD_OK;
+}
+
+extern "C" int td_emul_blend_bboxes(const void* const* batch_ptrs, int num_batches, int tile_bs, const int32_t* origins, int n_tiles,
+                                    int N, int C, int H, int W, int tile_h, int tile_w, int dtype, float* out) {
+    BlendListParams p;
+    p.NC = N * C; p.H = H; p.W = W; p.th = tile_h; p.tw = tile_w; p.n_tiles = n_tiles; p.tile_bs = tile_bs;
+    for (int b = 0; b < num_batches; ++b) p.batch_ptrs[b] = batch_ptrs[b];
+    const long long total = (long long)p.NC * H * W;
+    for (long long e = 0; e < total; ++e) {
+        if (dtype == TD_F16) out[e] = blend_bboxes_elem<__half>(p, origins, e);
+        else if (dtype == TD_BF16) out[e] = blend_bboxes_elem<__nv_bfloat16>(p, origins, e);
+        else out[e] = blend_bboxes_elem<float>(p, origins, e);
+    }
+    return TD_OK;
+}
+
+extern "C" int td_emul_combine_offset(const void* x_local, const void* const* view_batch_ptrs, int num_batches, int views_per_batch,
+                                      int n_views, void* out, int N, int C, int H, int W, int s, int out_h, int out_w, int offset,
+                                      int end_y, int end_x, int mixture, float c2, float one_minus_c2, int dtype) {
+    CombineOffsetParams p;
+    p.NC = N * C; p.H = H; p.W = W; p.s = s; p.oh = out_h; p.ow = out_w; p.end_y = end_y; p.end_x = end_x; p.off = offset;
+    p.views_per_batch = views_per_batch; p.n_views = n_views; p.mixture = mixture; p.c2 = c2; p.one_minus_c2 = one_minus_c2;
+    for (int b = 0; b < num_batches; ++b) p.batch_ptrs[b] = view_batch_ptrs[b];
+    const long long total = (long long)p.NC * H * W;
+    for (long long e = 0; e < total; ++e) {
+        if (dtype == TD_F16) ((__half*)out)[e] = combine_offset_elem<__half>(p, (const __half*)x_local, e);
+        else if (dtype == TD_BF16) ((__nv_bfloat16*)out)[e] = combine_offset_elem<__nv_bfloat16>(p, (const __nv_bfloat16*)x_local, e);
+        else ((float*)out)[e] = combine_offset_elem<float>(p, (const float*)x_local, e);
+    }
+    return TD_OK;
+}
+#endif
