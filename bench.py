@@ -418,6 +418,12 @@ def gpu_arm(args, rank, world, local_rank):
             if args.variants:
                 tbl = {"empty_1024x128": only(wl.empty)}
                 tbl["blend_async_one_plane"] = only(lambda s: wl.blend(s, 64))
+                try:      # strip form (td_strip.cu): opt-in, first timed in round 2
+                    tbl["blend_strip"] = only(lambda s: wl.blend(s, 128))
+                    tbl["blend_strip_L2hot"] = only(lambda s: wl.blend(0, 128))
+                except Exception as e:
+                    tbl["blend_strip_error"] = -1.0
+                    print(f"strip variant failed: {e!r}", file=sys.stderr)
                 tbl["blend_async_ieee_div"] = only(lambda s: wl.blend(s, 0x200))
                 wl.blend_mod(0)
                 tbl["blend_mixture_async"] = only(lambda s: wl.blend_mod(s, 0))

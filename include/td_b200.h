@@ -45,6 +45,7 @@ typedef enum td_dtype { TD_F16 = 0, TD_BF16 = 1, TD_F32 = 2 } td_dtype;
 #define TD_FLAG_PEER_ASYNC 16u   /* peer blend: stage peer tiles with cp.async instead of direct 128-bit loads */
 #define TD_FLAG_NO_PDL 32u       /* launch without the programmatic-dependent-launch attribute (A/B measurement) */
 #define TD_FLAG_ONE_PLANE 64u    /* cp.async blend: one (n, c) plane per CTA instead of two (A/B measurement) */
+#define TD_FLAG_STRIP 128u       /* MultiDiffusion blend: strip CTAs (8 rows x full width), opt-in, see csrc/td_strip.cu */
 #define TD_FLAG_DBG_NO_TILES 0x100u /* measurement aid: skip all tile visits (launch + epilogue floor) */
 
 #define TD_MAX_GRID_DIM 256   /* max tile rows / cols of a grid plan            */

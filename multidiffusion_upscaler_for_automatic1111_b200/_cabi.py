@@ -25,6 +25,7 @@ TD_FLAG_PIPELINE = 8
 TD_FLAG_PEER_ASYNC = 16
 TD_FLAG_NO_PDL = 32
 TD_FLAG_ONE_PLANE = 64
+TD_FLAG_STRIP = 128
 TD_FLAG_DBG_NO_TILES = 0x100
 TD_MAX_GRID_DIM = 256
 TD_MAX_BATCH_PTRS = 128

@@ -1604,6 +1604,10 @@ extern "C" int td_blend_multidiffusion(const td_grid* g, const void* const* batc
     cudaStream_t s = (cudaStream_t)stream;
     if (!(flags & TD_FLAG_FORCE_GENERIC) && blend_vec_ok(bp, tile_dtype, acc_dtype, {weights, rcp_weights, x_out, x_buffer})) {
         int rc = 1;
+        if (flags & TD_FLAG_STRIP) {   // opt-in: strip form (td_strip.cu); falls through to the default when not applicable
+            rc = td_strip_try_launch(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, weights, rcp_weights, x_out, x_buffer, stream);
+            if (rc <= 0) return rc;
+        }
         if (flags & TD_FLAG_TMA) {
             switch (tile_dtype) {
                 case TD_F16: rc = try_launch_blend_tma<__half>(g, bp, tile_dtype, weights, x_out, x_buffer, s); break;

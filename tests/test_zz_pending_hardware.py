@@ -69,6 +69,34 @@ def test_controlnet_tile_caches_on_gpu_equal_plain_slicing(dtype):
     assert cs.latest_network.control_params[0].hint_cond.shape == (1, 3, H * 8, W * 8)
 
 
+# ------------------------------------------------------------------------------- strip form of the MultiDiffusion blend (new kernel)
+STRIP = 128
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="strip blend (TD_FLAG_STRIP): first hardware run pending; host emulation in test_strip_emulation.py")
+@pytest.mark.parametrize("dn", list(DTYPES))
+@pytest.mark.parametrize("use_rcp", [False, True])
+def test_strip_blend_matches_reference_fixtures_on_gpu(golden_dir, dn, use_rcp):
+    from multidiffusion_upscaler_for_automatic1111_b200 import engine
+    from helpers import bits, sha
+    from test_gpu_diffusion import _run_cuda_step
+    if use_rcp and dn == "f32":
+        pytest.skip("the fast exact divide is a 16-bit path")
+    g = np.load(os.path.join(golden_dir, "blend_small.npz"))
+    for name, (N, C, W, H, tw, th, ov, bs) in zip(g["names"], g["cases"]):
+        x = synth.latent(synth.case_seed(str(name), dn), (int(N), int(C), int(H), int(W)), DTYPES[dn])
+        out, xb, plan = _run_cuda_step(engine, "md", x, int(W), int(H), int(tw), int(th), int(ov), int(bs), flags=STRIP, use_rcp=use_rcp)
+        assert np.array_equal(bits(out), g[f"{name}_{dn}_md"]), f"{name}: strip blend differs from the reference's"
+    if dn == "f16":
+        h = np.load(os.path.join(golden_dir, "blend_hashes.npz"))
+        idx = list(h["names"]).index("cfg2_ov48")
+        N, C, W, H, tw, th, ov, bs = (int(v) for v in h["cases"][idx])
+        x = synth.latent(synth.case_seed("cfg2_ov48", dn), (N, C, H, W), DTYPES[dn])
+        out, _, _ = _run_cuda_step(engine, "md", x, W, H, tw, th, ov, bs, flags=STRIP, use_rcp=use_rcp)
+        assert sha(out) == str(h["cfg2_ov48_f16_md"])
+
+
 # ------------------------------------------------------------------------------- DemoFusion random jitter (new kernels: last)
 @pytest.mark.gpu
 @pytest.mark.xfail(strict=False, reason="DemoFusion random jitter: first hardware run pending")
