@@ -1605,7 +1605,8 @@ extern "C" int td_blend_multidiffusion(const td_grid* g, const void* const* batc
     if (!(flags & TD_FLAG_FORCE_GENERIC) && blend_vec_ok(bp, tile_dtype, acc_dtype, {weights, rcp_weights, x_out, x_buffer})) {
         int rc = 1;
         if (flags & TD_FLAG_STRIP) {   // opt-in: strip form (td_strip.cu); falls through to the default when not applicable
-            rc = td_strip_try_launch(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, weights, rcp_weights, x_out, x_buffer, stream);
+            rc = td_strip_try_launch(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, weights, rcp_weights, x_out, x_buffer,
+                                     (flags & TD_FLAG_NO_PDL) ? 0 : 1, stream);
             if (rc <= 0) return rc;
         }
         if (flags & TD_FLAG_TMA) {

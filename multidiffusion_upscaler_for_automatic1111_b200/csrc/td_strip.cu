@@ -206,9 +206,25 @@ template <typename T>
 __host__ __device__ __forceinline__ void strip_phase_copy(const StripParams& p, int strip, int tid, int nthreads, unsigned char* smem) {
     constexpr int VEC = 16 / (int)sizeof(T);
     const int nvis = (int)p.prow_n[strip] * p.cols;
-    const int total = nvis * p.spv;
     const StripVisit* vis = strip_visits(smem);
     unsigned char* stage = strip_stage(smem);
+    if (p.spv <= nthreads) {
+        // a thread keeps ONE slot (strip row, chunk) and walks the visits with a stride of G = nthreads / spv groups:
+        // row / chunk arithmetic once, ~10 instructions per copy
+        const int groups = (int)sdiv((unsigned)nthreads, p.spv_magic);
+        const int grp = (int)sdiv((unsigned)tid, p.spv_magic), q = tid - grp * p.spv;
+        if (grp >= groups) return;
+        const int row = (int)sdiv((unsigned)q, p.cpr_magic), j = q - row * p.cpr;
+        const bool col_ok = j >= 1 && j <= p.twv;
+        const long long off = ((long long)row * p.tw + (long long)(j - 1) * VEC) * (long long)sizeof(T);
+        for (int i = grp; i < nvis; i += groups) {
+            const StripVisit e = vis[i];
+            const bool valid = col_ok && (unsigned)(e.v0 + row) < (unsigned)p.th;
+            s_copy16(stage + ((size_t)i * p.spv + q) * 16, e.origin + off, valid);
+        }
+        return;
+    }
+    const int total = nvis * p.spv;    // a staged row wider than the CTA (single tile column): flat slot loop
     for (int s = tid; s < total; s += nthreads) {
         const int i = (int)sdiv((unsigned)s, p.spv_magic), q = s - i * p.spv;
         const int row = (int)sdiv((unsigned)q, p.cpr_magic), j = q - row * p.cpr;
@@ -284,7 +300,11 @@ strip_blend_kernel(const __grid_constant__ StripParams p, const float* __restric
                    float* __restrict__ out_f32, T* __restrict__ out_buf) {
     extern __shared__ __align__(16) unsigned char td_strip_smem[];
     const int strip = blockIdx.x, plane = blockIdx.y, tid = threadIdx.x;
-    strip_phase_table<T>(p, strip, plane, tid, td_strip_smem);
+    // programmatic dependent launch (as in td_diffusion.cu): the next grid may become resident while this one drains;
+    // every global access of THIS grid waits for its predecessor below.  Both are no-ops for an ordinary launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    strip_phase_table<T>(p, strip, plane, tid, td_strip_smem);     // kernel parameters only
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
     strip_phase_copy<T>(p, strip, tid, (int)blockDim.x, td_strip_smem);
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -336,34 +356,43 @@ int strip_plan(const td_grid* g, const void* const* batch_ptrs, int num_batches,
 
 template <typename T, bool WRITE_BUF, bool FASTDIV>
 int strip_launch(const StripParams& p, int strips, int nthreads, int smem, const float* weights, const float* rcp, float* out_f32,
-                 void* out_buf, cudaStream_t st) {
+                 void* out_buf, bool pdl, cudaStream_t st) {
     if (smem > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(strip_blend_kernel<T, WRITE_BUF, FASTDIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { td_set_error("td_blend_multidiffusion (strip): cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return TD_ERR_CUDA; }
     }
-    dim3 grid((unsigned)strips, (unsigned)p.NC);
-    strip_blend_kernel<T, WRITE_BUF, FASTDIV><<<grid, nthreads, smem, st>>>(p, weights, rcp, out_f32, (T*)out_buf);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)strips, (unsigned)p.NC);
+    cfg.blockDim = dim3((unsigned)nthreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr = {};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, strip_blend_kernel<T, WRITE_BUF, FASTDIV>, p, weights, rcp, out_f32, (T*)out_buf);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { td_set_error("td_blend_multidiffusion (strip): CUDA launch failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
     return TD_OK;
 }
 
 template <typename T>
 int strip_dispatch(const StripParams& p, int strips, int nthreads, int smem, const float* weights, const float* rcp, float* out_f32,
-                   void* out_buf, cudaStream_t st) {
+                   void* out_buf, bool pdl, cudaStream_t st) {
     const bool fast = rcp != nullptr && sizeof(T) == 2;
     if (out_buf != nullptr)
-        return fast ? strip_launch<T, true, true>(p, strips, nthreads, smem, weights, rcp, out_f32, out_buf, st)
-                    : strip_launch<T, true, false>(p, strips, nthreads, smem, weights, nullptr, out_f32, out_buf, st);
-    return fast ? strip_launch<T, false, true>(p, strips, nthreads, smem, weights, rcp, out_f32, out_buf, st)
-                : strip_launch<T, false, false>(p, strips, nthreads, smem, weights, nullptr, out_f32, out_buf, st);
+        return fast ? strip_launch<T, true, true>(p, strips, nthreads, smem, weights, rcp, out_f32, out_buf, pdl, st)
+                    : strip_launch<T, true, false>(p, strips, nthreads, smem, weights, nullptr, out_f32, out_buf, pdl, st);
+    return fast ? strip_launch<T, false, true>(p, strips, nthreads, smem, weights, rcp, out_f32, out_buf, pdl, st)
+                : strip_launch<T, false, false>(p, strips, nthreads, smem, weights, nullptr, out_f32, out_buf, pdl, st);
 }
 
 }  // namespace
 
 // TD_OK launched, 1 not applicable (the caller continues with the default kernels), < 0 error
 int td_strip_try_launch(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N, int C, int dtype,
-                        const float* weights, const float* rcp_weights, float* x_out, void* x_buffer, void* stream) {
+                        const float* weights, const float* rcp_weights, float* x_out, void* x_buffer, int pdl, void* stream) {
     static StripParams p;          // 2.7 KB: filled per launch under a lock (the parameters are copied at launch)
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
@@ -371,9 +400,9 @@ int td_strip_try_launch(const td_grid* g, const void* const* batch_ptrs, int num
     if (strip_plan(g, batch_ptrs, num_batches, tile_bs, N, C, td_dtype_size(dtype), &p, &nthreads, &smem, &strips) != 0) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {
-        case TD_F16: return strip_dispatch<__half>(p, strips, nthreads, smem, weights, rcp_weights, x_out, x_buffer, st);
-        case TD_BF16: return strip_dispatch<__nv_bfloat16>(p, strips, nthreads, smem, weights, rcp_weights, x_out, x_buffer, st);
-        case TD_F32: return strip_dispatch<float>(p, strips, nthreads, smem, weights, nullptr, x_out, x_buffer, st);
+        case TD_F16: return strip_dispatch<__half>(p, strips, nthreads, smem, weights, rcp_weights, x_out, x_buffer, pdl != 0, st);
+        case TD_BF16: return strip_dispatch<__nv_bfloat16>(p, strips, nthreads, smem, weights, rcp_weights, x_out, x_buffer, pdl != 0, st);
+        case TD_F32: return strip_dispatch<float>(p, strips, nthreads, smem, weights, nullptr, x_out, x_buffer, pdl != 0, st);
         default: return 1;
     }
 }
