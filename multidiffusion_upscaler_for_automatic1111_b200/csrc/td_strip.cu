@@ -29,7 +29,10 @@ namespace {
 
 using namespace td;
 
-constexpr int kStripRows = 8;        // canvas rows per CTA
+#ifndef TD_STRIP_ROWS
+#define TD_STRIP_ROWS 8              // tuning knob (-DTD_STRIP_ROWS=): canvas rows per CTA
+#endif
+constexpr int kStripRows = TD_STRIP_ROWS;   // canvas rows per CTA
 constexpr int kStripMaxVisits = 64;  // tile rows touching a strip x tile columns
 
 struct StripParams {

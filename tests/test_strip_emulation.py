@@ -17,6 +17,7 @@ from oracle import blend, synth, tiling
 from oracle.make_golden import BLEND_CASES, HASH_CASES
 
 PKG = os.path.join(ROOT, "multidiffusion_upscaler_for_automatic1111_b200")
+ROWS = int(os.environ.get("TD_STRIP_ROWS", "8"))      # the kernel's tuning knob; run the file with another value to check a variant
 CODE = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}
 
 
@@ -27,12 +28,13 @@ def emul():
         pytest.skip("nvcc not available")
     out_dir = os.path.join(ROOT, "tests", "_build")
     os.makedirs(out_dir, exist_ok=True)
-    so = os.path.join(out_dir, "libtd_strip_emul.so")
+    so = os.path.join(out_dir, f"libtd_strip_emul_r{ROWS}.so")
     srcs = [os.path.join(ROOT, "tests", "emul", "strip_host_emul.cu"), os.path.join(PKG, "csrc", "td_host.cpp")]
     deps = srcs + [os.path.join(PKG, "csrc", "td_strip.cu"), os.path.join(PKG, "csrc", "td_device.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "--shared", "-Xcompiler", "-fPIC,-ffp-contract=off",
-               "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "csrc"), "-o", so, *srcs]
+               "--expt-relaxed-constexpr", f"-DTD_STRIP_ROWS={ROWS}", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "csrc"),
+               "-o", so, *srcs]
         res = subprocess.run(cmd, capture_output=True, text=True)
         assert res.returncode == 0, res.stderr[-3000:]
     return ctypes.CDLL(so)
@@ -98,7 +100,9 @@ def test_emulated_strip_blend_full_size_cfg2(emul, golden_dir):
     rc, x_out, _, info, _ = _strip_step(emul, x, W, H, tw, th, ov, bs, use_rcp=True, want_buffer=False)
     assert rc == 0
     strips, nthreads, smem = info
-    assert (strips, nthreads) == (64, 512) and 50_000 < smem < 57_000
+    assert (strips, nthreads) == (-(-512 // ROWS), ROWS * 64)
+    if ROWS == 8:
+        assert 50_000 < smem < 57_000
     g = np.load(os.path.join(golden_dir, "blend_hashes.npz"))
     assert sha(x_out) == str(g[f"{name}_f16_md"])
 
@@ -109,6 +113,9 @@ def test_emulated_strip_blend_edge_geometries(emul, geom):
     N, C, W, H, tw, th, ov, bs = geom
     x = synth.latent(5, (N, C, H, W), torch.float16)
     rc, x_out, xb, info, plan = _strip_step(emul, x, W, H, tw, th, ov, bs)
+    if ROWS * (W // 8) > 1024:
+        assert rc == 1                                   # more than 1024 threads per strip: not applicable, default kernels run
+        return
     assert rc == 0
     want = blend.multidiffusion_step(x, plan.batched_bboxes, plan.weights, lambda t, bb: synth.fake_denoise(t, bb, N))
     assert_bit_equal(x_out, want, f"strip blend {geom}")
