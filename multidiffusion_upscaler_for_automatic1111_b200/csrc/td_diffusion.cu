@@ -1690,6 +1690,11 @@ extern "C" int td_blend_mixture(const td_grid* g, const void* const* batch_ptrs,
     }
     cudaStream_t s = (cudaStream_t)stream;
     if (!(flags & TD_FLAG_FORCE_GENERIC) && blend_vec_ok(bp, tile_dtype, acc_dtype, {rescale, x_buffer})) {
+        if (flags & TD_FLAG_STRIP) {   // opt-in: strip form (td_strip.cu); falls through to the default when not applicable
+            const int rc = td_strip_try_launch_mod(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, tile_weights, rescale, x_buffer,
+                                                   (flags & TD_FLAG_NO_PDL) ? 0 : 1, stream);
+            if (rc <= 0) return rc;
+        }
         if (!(flags & TD_FLAG_NO_TMA)) {
             int rc;
             switch (tile_dtype) {

@@ -85,6 +85,20 @@ __host__ __device__ __forceinline__ float s_add(float a, float b) {
 #endif
 }
 
+__host__ __device__ __forceinline__ float s_mul(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+
+// fp32 value rounded through T (the store to x_buffer and the load back of the reference)
+template <typename T> __host__ __device__ __forceinline__ float s_round(float f) {
+    if constexpr (sizeof(T) == 4) return f;
+    else return SElem<T>::to_f32(SElem<T>::from_f32(f));
+}
+
 // one 32-bit word of packed T: a (+) b with one rounding per element through T
 template <typename T> __host__ __device__ __forceinline__ uint32_t s_packed_add(uint32_t a, uint32_t b) {
     if constexpr (sizeof(T) == 4) {
@@ -315,6 +329,82 @@ strip_blend_kernel(const __grid_constant__ StripParams p, const float* __restric
     strip_phase_consume<T, WRITE_BUF, FASTDIV>(p, strip, plane, tid, td_strip_smem, weights, rcp_weights, out_f32, out_buf);
 }
 
+// ---- phase 3, Mixture of Diffusers (mixtureofdiffusers.py:122-126): per element of every covering tile, in tile order,
+//      w = tile_weights[v, u] * rescale[y, x]   (fp32 product, its own rounding)
+//      acc = round_T(acc + tile * w)            (separate multiply and add, no FMA)
+// Elements outside the tile are skipped, never added as zeros: with gaussian weights the accumulator can be -0.0 and
+// -0 + (+0) would flip the sign bit the reference keeps.  Returns x_buffer in the latent dtype (no division).
+template <typename T>
+__host__ __device__ __forceinline__ void strip_phase_consume_mod(const StripParams& p, int strip, int plane, int tid, unsigned char* smem,
+                                                                 const float* __restrict__ tile_weights, const float* __restrict__ rescale,
+                                                                 T* __restrict__ out_buf) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int ty = (int)sdiv((unsigned)tid, p.xv_magic), tx = tid - ty * p.xv;
+    const int y = strip * kStripRows + ty;
+    if (ty >= kStripRows || y >= p.H) return;
+    const int nvis = (int)p.prow_n[strip] * p.cols;
+    const StripVisit* vis = strip_visits(smem);
+    const unsigned char* row0 = strip_stage(smem) + (size_t)ty * p.cpr * 16;
+    const int x0 = tx * VEC;
+    const long long wo = (long long)y * p.W + x0;
+    float rs[VEC], acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { rs[j] = rescale[wo + j]; acc[j] = 0.0f; }
+    for (int i = 0; i < nvis; ++i) {
+        const StripVisit e = vis[i];
+        const int v = e.v0 + ty;                           // tile row of this canvas row
+        if ((unsigned)v >= (unsigned)p.th) continue;
+        const int u0 = (tx - e.qx) * VEC - e.s;            // tile column of this vector's first element
+        const int jlo = u0 < 0 ? -u0 : 0, jhi = (p.tw - u0) < VEC ? (p.tw - u0) : VEC;
+        if (jlo >= jhi) continue;
+        const unsigned char* rowp = row0 + (size_t)i * p.spv * 16;
+        uint4 t;
+        if (e.s == 0) {
+            t = s_ld16(rowp + (size_t)(tx - e.qx + 1) * 16);
+        } else {
+            const int idx = tx - e.qx;
+            t = s_window<T>(s_ld16(rowp + (size_t)idx * 16), s_ld16(rowp + (size_t)(idx + 1) * 16), VEC - e.s);
+        }
+        const float* wrow = tile_weights + (long long)v * p.tw + u0;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            if (j < jlo || j >= jhi) continue;
+            const float w = s_mul(wrow[j], rs[j]);
+            acc[j] = s_round<T>(s_add(acc[j], s_mul(s_get<T>(t, j), w)));
+        }
+    }
+    const long long o = ((long long)plane * p.H + y) * p.W + x0;
+    uint4 pk;
+    if constexpr (sizeof(T) == 4) {
+        uint32_t w32[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) memcpy(&w32[j], &acc[j], 4);
+        pk = make_uint4(w32[0], w32[1], w32[2], w32[3]);
+    } else {
+        uint32_t w32[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) w32[h] = (uint32_t)SElem<T>::from_f32(acc[2 * h]) | ((uint32_t)SElem<T>::from_f32(acc[2 * h + 1]) << 16);
+        pk = make_uint4(w32[0], w32[1], w32[2], w32[3]);
+    }
+    s_st16(out_buf + o, pk);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+strip_blend_mod_kernel(const __grid_constant__ StripParams p, const float* __restrict__ tile_weights, const float* __restrict__ rescale,
+                       T* __restrict__ out_buf) {
+    extern __shared__ __align__(16) unsigned char td_strip_smem[];
+    const int strip = blockIdx.x, plane = blockIdx.y, tid = threadIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    strip_phase_table<T>(p, strip, plane, tid, td_strip_smem);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __syncthreads();
+    strip_phase_copy<T>(p, strip, tid, (int)blockDim.x, td_strip_smem);
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    strip_phase_consume_mod<T>(p, strip, plane, tid, td_strip_smem, tile_weights, rescale, out_buf);
+}
+
 unsigned s_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(((1ull << 32) + d - 1) / d); }
 
 // fills p and the launch shape; 0 = applicable, 1 = not applicable
@@ -391,14 +481,55 @@ int strip_dispatch(const StripParams& p, int strips, int nthreads, int smem, con
                 : strip_launch<T, false, false>(p, strips, nthreads, smem, weights, nullptr, out_f32, out_buf, pdl, st);
 }
 
+template <typename T>
+int strip_launch_mod(const StripParams& p, int strips, int nthreads, int smem, const float* tile_weights, const float* rescale, void* out_buf,
+                     bool pdl, cudaStream_t st) {
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(strip_blend_mod_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { td_set_error("td_blend_mixture (strip): cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return TD_ERR_CUDA; }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)strips, (unsigned)p.NC);
+    cfg.blockDim = dim3((unsigned)nthreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr = {};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, strip_blend_mod_kernel<T>, p, tile_weights, rescale, (T*)out_buf);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { td_set_error("td_blend_mixture (strip): CUDA launch failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+    return TD_OK;
+}
+
+std::mutex g_strip_mu;
+StripParams g_strip_params;        // 2.7 KB: filled per launch under the lock (the parameters are copied at launch)
+
 }  // namespace
+
+// Mixture of Diffusers on strips; same return convention as td_strip_try_launch
+int td_strip_try_launch_mod(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N, int C, int dtype,
+                            const float* tile_weights, const float* rescale, void* x_buffer, int pdl, void* stream) {
+    std::lock_guard<std::mutex> lk(g_strip_mu);
+    StripParams& p = g_strip_params;
+    int nthreads = 0, smem = 0, strips = 0;
+    if (strip_plan(g, batch_ptrs, num_batches, tile_bs, N, C, td_dtype_size(dtype), &p, &nthreads, &smem, &strips) != 0) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case TD_F16: return strip_launch_mod<__half>(p, strips, nthreads, smem, tile_weights, rescale, x_buffer, pdl != 0, st);
+        case TD_BF16: return strip_launch_mod<__nv_bfloat16>(p, strips, nthreads, smem, tile_weights, rescale, x_buffer, pdl != 0, st);
+        case TD_F32: return strip_launch_mod<float>(p, strips, nthreads, smem, tile_weights, rescale, x_buffer, pdl != 0, st);
+        default: return 1;
+    }
+}
 
 // TD_OK launched, 1 not applicable (the caller continues with the default kernels), < 0 error
 int td_strip_try_launch(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N, int C, int dtype,
                         const float* weights, const float* rcp_weights, float* x_out, void* x_buffer, int pdl, void* stream) {
-    static StripParams p;          // 2.7 KB: filled per launch under a lock (the parameters are copied at launch)
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lk(mu);
+    std::lock_guard<std::mutex> lk(g_strip_mu);
+    StripParams& p = g_strip_params;
     int nthreads = 0, smem = 0, strips = 0;
     if (strip_plan(g, batch_ptrs, num_batches, tile_bs, N, C, td_dtype_size(dtype), &p, &nthreads, &smem, &strips) != 0) return 1;
     cudaStream_t st = (cudaStream_t)stream;
@@ -432,6 +563,31 @@ static void emul_run(const StripParams& p, int strips, int nthreads, int smem_by
             }
         }
     delete[] smem;
+}
+
+template <typename T>
+static void emul_run_mod(const StripParams& p, int strips, int nthreads, int smem_bytes, const float* tile_weights, const float* rescale,
+                         void* out_buf) {
+    unsigned char* smem = new unsigned char[smem_bytes + 16];
+    for (int plane = 0; plane < p.NC; ++plane)
+        for (int strip = 0; strip < strips; ++strip) {
+            memset(smem, 0xCD, smem_bytes);
+            for (int tid = 0; tid < nthreads; ++tid) strip_phase_table<T>(p, strip, plane, tid, smem);
+            for (int tid = 0; tid < nthreads; ++tid) strip_phase_copy<T>(p, strip, tid, nthreads, smem);
+            for (int tid = 0; tid < nthreads; ++tid) strip_phase_consume_mod<T>(p, strip, plane, tid, smem, tile_weights, rescale, (T*)out_buf);
+        }
+    delete[] smem;
+}
+
+extern "C" int td_emul_strip_blend_mod(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N, int C, int dtype,
+                                       const float* tile_weights, const float* rescale, void* x_buffer) {
+    static StripParams p;
+    int nthreads = 0, smem = 0, strips = 0;
+    if (strip_plan(g, batch_ptrs, num_batches, tile_bs, N, C, td_dtype_size(dtype), &p, &nthreads, &smem, &strips) != 0) return 1;
+    if (dtype == TD_F16) emul_run_mod<__half>(p, strips, nthreads, smem, tile_weights, rescale, x_buffer);
+    else if (dtype == TD_BF16) emul_run_mod<__nv_bfloat16>(p, strips, nthreads, smem, tile_weights, rescale, x_buffer);
+    else emul_run_mod<float>(p, strips, nthreads, smem, tile_weights, rescale, x_buffer);
+    return TD_OK;
 }
 
 extern "C" int td_emul_strip_blend(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N, int C, int dtype,

@@ -119,3 +119,47 @@ def test_emulated_strip_blend_edge_geometries(emul, geom):
     assert rc == 0
     want = blend.multidiffusion_step(x, plan.batched_bboxes, plan.weights, lambda t, bb: synth.fake_denoise(t, bb, N))
     assert_bit_equal(x_out, want, f"strip blend {geom}")
+
+
+# ------------------------------------------------------------------------------------------ Mixture of Diffusers on strips
+def _strip_step_mod(emul, x, W, H, tw, th, ov, bs):
+    from multidiffusion_upscaler_for_automatic1111_b200 import engine
+    N, C = x.shape[:2]
+    g = engine.make_grid(W, H, tw, th, ov, bs)
+    plan = tiling.GridPlan(W, H, tw, th, ov, bs, True)
+    outs = [synth.fake_denoise(blend.scatter_tiles(x, bbs), bbs, N).contiguous() for bbs in plan.batched_bboxes]
+    ptrs = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+    twt = np.ascontiguousarray(plan.tile_weights, dtype=np.float32)
+    rf = np.ascontiguousarray(plan.rescale_factor, dtype=np.float32)
+    xb = torch.empty_like(x)
+    rc = emul.td_emul_strip_blend_mod(ctypes.byref(g), ptrs, len(outs), int(g.tile_bs), N, C, CODE[x.dtype],
+                                      twt.ctypes.data_as(ctypes.c_void_p), rf.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(xb.data_ptr()))
+    return rc, xb
+
+
+@pytest.mark.parametrize("case", BLEND_CASES, ids=[c[0] for c in BLEND_CASES])
+@pytest.mark.parametrize("dn", list(DTYPES))
+def test_emulated_strip_mixture_matches_reference_fixture(emul, golden_dir, case, dn):
+    name, N, C, W, H, tw, th, ov, bs = case
+    x = synth.latent(synth.case_seed(name, dn), (N, C, H, W), DTYPES[dn])
+    vec = 16 // x.element_size()
+    rc, xb = _strip_step_mod(emul, x, W, H, tw, th, ov, bs)
+    if W % vec or min(tw, W) % vec:
+        assert rc == 1
+        return
+    assert rc == 0
+    g = np.load(os.path.join(golden_dir, "blend_small.npz"))
+    raw = g[f"{name}_{dn}_mod"]
+    want = torch.from_numpy(raw.view(np.int16 if raw.dtype == np.uint16 else np.int32).copy()).view(DTYPES[dn])
+    from helpers import bits
+    assert np.array_equal(bits(xb), raw), f"{name} {dn}: strip Mixture of Diffusers differs from the reference's (sign of zero included)"
+    assert_bit_equal(xb, want, "strip mixture vs reference")
+
+
+def test_emulated_strip_mixture_full_size_cfg2(emul, golden_dir):
+    name, N, C, W, H, tw, th, ov, bs = HASH_CASES[0]
+    x = synth.latent(synth.case_seed(name, "f16"), (N, C, H, W), torch.float16)
+    rc, xb = _strip_step_mod(emul, x, W, H, tw, th, ov, bs)
+    assert rc == 0
+    g = np.load(os.path.join(golden_dir, "blend_hashes.npz"))
+    assert sha(xb) == str(g[f"{name}_f16_mod"])

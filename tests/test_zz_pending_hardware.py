@@ -97,6 +97,27 @@ def test_strip_blend_matches_reference_fixtures_on_gpu(golden_dir, dn, use_rcp):
         assert sha(out) == str(h["cfg2_ov48_f16_md"])
 
 
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="strip Mixture of Diffusers (TD_FLAG_STRIP): first hardware run pending; host emulation in test_strip_emulation.py")
+@pytest.mark.parametrize("dn", list(DTYPES))
+def test_strip_mixture_matches_reference_fixtures_on_gpu(golden_dir, dn):
+    from multidiffusion_upscaler_for_automatic1111_b200 import engine
+    from helpers import bits, sha
+    from test_gpu_diffusion import _run_cuda_step
+    g = np.load(os.path.join(golden_dir, "blend_small.npz"))
+    for name, (N, C, W, H, tw, th, ov, bs) in zip(g["names"], g["cases"]):
+        x = synth.latent(synth.case_seed(str(name), dn), (int(N), int(C), int(H), int(W)), DTYPES[dn])
+        out, _, _ = _run_cuda_step(engine, "mod", x, int(W), int(H), int(tw), int(th), int(ov), int(bs), flags=STRIP)
+        assert np.array_equal(bits(out), g[f"{name}_{dn}_mod"]), f"{name}: strip Mixture of Diffusers differs from the reference's"
+    if dn == "f16":
+        h = np.load(os.path.join(golden_dir, "blend_hashes.npz"))
+        idx = list(h["names"]).index("cfg2_ov48")
+        N, C, W, H, tw, th, ov, bs = (int(v) for v in h["cases"][idx])
+        x = synth.latent(synth.case_seed("cfg2_ov48", dn), (N, C, H, W), DTYPES[dn])
+        out, _, _ = _run_cuda_step(engine, "mod", x, W, H, tw, th, ov, bs, flags=STRIP)
+        assert sha(out) == str(h["cfg2_ov48_f16_mod"])
+
+
 # ------------------------------------------------------------------------------- DemoFusion random jitter (new kernels: last)
 @pytest.mark.gpu
 @pytest.mark.xfail(strict=False, reason="DemoFusion random jitter: first hardware run pending")
