@@ -447,13 +447,25 @@ int strip_plan(const td_grid* g, const void* const* batch_ptrs, int num_batches,
     return 0;
 }
 
+// opt-in above 48 KB of dynamic shared memory: once per kernel and device (called under g_strip_mu)
+template <typename KernelT>
+int strip_ensure_smem(KernelT kernel, int smem, int* configured /* [64], zero-initialised */) {
+    if (smem <= 40 * 1024) return TD_OK;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) { td_set_error("cudaGetDevice failed"); return TD_ERR_CUDA; }
+    if (dev < 64 && smem <= configured[dev]) return TD_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { td_set_error("strip blend: cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return TD_ERR_CUDA; }
+    if (dev < 64) configured[dev] = smem;
+    return TD_OK;
+}
+
 template <typename T, bool WRITE_BUF, bool FASTDIV>
 int strip_launch(const StripParams& p, int strips, int nthreads, int smem, const float* weights, const float* rcp, float* out_f32,
                  void* out_buf, bool pdl, cudaStream_t st) {
-    if (smem > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(strip_blend_kernel<T, WRITE_BUF, FASTDIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) { td_set_error("td_blend_multidiffusion (strip): cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return TD_ERR_CUDA; }
-    }
+    static int configured[64] = {0};
+    const int rc = strip_ensure_smem(strip_blend_kernel<T, WRITE_BUF, FASTDIV>, smem, configured);
+    if (rc != TD_OK) return rc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)strips, (unsigned)p.NC);
     cfg.blockDim = dim3((unsigned)nthreads);
@@ -484,10 +496,9 @@ int strip_dispatch(const StripParams& p, int strips, int nthreads, int smem, con
 template <typename T>
 int strip_launch_mod(const StripParams& p, int strips, int nthreads, int smem, const float* tile_weights, const float* rescale, void* out_buf,
                      bool pdl, cudaStream_t st) {
-    if (smem > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(strip_blend_mod_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) { td_set_error("td_blend_mixture (strip): cudaFuncSetAttribute(%d B): %s", smem, cudaGetErrorString(e)); return TD_ERR_CUDA; }
-    }
+    static int configured[64] = {0};
+    const int rc = strip_ensure_smem(strip_blend_mod_kernel<T>, smem, configured);
+    if (rc != TD_OK) return rc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)strips, (unsigned)p.NC);
     cfg.blockDim = dim3((unsigned)nthreads);
