@@ -1606,7 +1606,7 @@ extern "C" int td_blend_multidiffusion(const td_grid* g, const void* const* batc
         int rc = 1;
         if (flags & TD_FLAG_STRIP) {   // opt-in: strip form (td_strip.cu); falls through to the default when not applicable
             rc = td_strip_try_launch(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, weights, rcp_weights, x_out, x_buffer,
-                                     (flags & TD_FLAG_NO_PDL) ? 0 : 1, stream);
+                                     (flags & TD_FLAG_NO_PDL) ? 0 : 1, (flags & TD_FLAG_ONE_PLANE) ? 1 : 2, stream);
             if (rc <= 0) return rc;
         }
         if (flags & TD_FLAG_TMA) {

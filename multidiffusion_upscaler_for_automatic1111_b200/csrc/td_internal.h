@@ -9,6 +9,6 @@ static inline int td_dtype_size(int dtype) { return dtype == 2 /*TD_F32*/ ? 4 : 
 // td_strip.cu: strip form of the MultiDiffusion blend (TD_FLAG_STRIP).  TD_OK launched, 1 not applicable, < 0 error.
 struct td_grid;
 int td_strip_try_launch(const struct td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N, int C, int dtype,
-                        const float* weights, const float* rcp_weights, float* x_out, void* x_buffer, int pdl, void* stream);
+                        const float* weights, const float* rcp_weights, float* x_out, void* x_buffer, int pdl, int max_ppc, void* stream);
 int td_strip_try_launch_mod(const struct td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N, int C, int dtype,
                             const float* tile_weights, const float* rescale, void* x_buffer, int pdl, void* stream);

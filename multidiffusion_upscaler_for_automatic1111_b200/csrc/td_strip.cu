@@ -218,13 +218,15 @@ __host__ __device__ __forceinline__ void strip_phase_table(const StripParams& p,
     strip_visits(smem)[tid] = e;
 }
 
-// ---- phase 2: stage every visit's row segments: slot = (visit, strip row, chunk), chunk 0 and twv+1 are zero pads -------
-template <typename T>
+// ---- phase 2: stage every visit's row segments: slot = (visit, plane, strip row, chunk), chunk 0 and twv+1 are zero pads ---
+// PPC = planes per CTA: the (n, c) planes of a strip share the visit table, the predicates and the shifts.
+template <typename T, int PPC = 1>
 __host__ __device__ __forceinline__ void strip_phase_copy(const StripParams& p, int strip, int tid, int nthreads, unsigned char* smem) {
     constexpr int VEC = 16 / (int)sizeof(T);
     const int nvis = (int)p.prow_n[strip] * p.cols;
     const StripVisit* vis = strip_visits(smem);
     unsigned char* stage = strip_stage(smem);
+    const long long plane_bytes = (long long)p.th * p.tw * (long long)sizeof(T);
     if (p.spv <= nthreads) {
         // a thread keeps ONE slot (strip row, chunk) and walks the visits with a stride of G = nthreads / spv groups:
         // row / chunk arithmetic once, ~10 instructions per copy
@@ -237,7 +239,9 @@ __host__ __device__ __forceinline__ void strip_phase_copy(const StripParams& p, 
         for (int i = grp; i < nvis; i += groups) {
             const StripVisit e = vis[i];
             const bool valid = col_ok && (unsigned)(e.v0 + row) < (unsigned)p.th;
-            s_copy16(stage + ((size_t)i * p.spv + q) * 16, e.origin + off, valid);
+#pragma unroll
+            for (int pl = 0; pl < PPC; ++pl)
+                s_copy16(stage + (((size_t)i * PPC + pl) * p.spv + q) * 16, e.origin + off + pl * plane_bytes, valid);
         }
         return;
     }
@@ -248,12 +252,14 @@ __host__ __device__ __forceinline__ void strip_phase_copy(const StripParams& p, 
         const StripVisit e = vis[i];
         const bool valid = (unsigned)(e.v0 + row) < (unsigned)p.th && j >= 1 && j <= p.twv;
         const long long src = e.origin + ((long long)row * p.tw + (long long)(j - 1) * VEC) * (long long)sizeof(T);
-        s_copy16(stage + (size_t)s * 16, src, valid);
+#pragma unroll
+        for (int pl = 0; pl < PPC; ++pl)
+            s_copy16(stage + (((size_t)i * PPC + pl) * p.spv + q) * 16, src + pl * plane_bytes, valid);
     }
 }
 
-// ---- phase 3: one thread per canvas vector: add the covering tiles in tile order, normalise, store ------------------------
-template <typename T, bool WRITE_BUF, bool FASTDIV>
+// ---- phase 3: one thread per canvas vector (of PPC planes): add the covering tiles in tile order, normalise, store --------
+template <typename T, bool WRITE_BUF, bool FASTDIV, int PPC = 1>
 __host__ __device__ __forceinline__ void strip_phase_consume(const StripParams& p, int strip, int plane, int tid, unsigned char* smem,
                                                              const float* __restrict__ weights, const float* __restrict__ rcp_weights,
                                                              float* __restrict__ out_f32, T* __restrict__ out_buf) {
@@ -264,69 +270,84 @@ __host__ __device__ __forceinline__ void strip_phase_consume(const StripParams& 
     const int nvis = (int)p.prow_n[strip] * p.cols;
     const StripVisit* vis = strip_visits(smem);
     const unsigned char* row0 = strip_stage(smem) + (size_t)ty * p.cpr * 16;
-    uint4 acc = make_uint4(0, 0, 0, 0);
+    const size_t plane_stage = (size_t)p.spv * 16;
+    uint4 acc[PPC];
+#pragma unroll
+    for (int pl = 0; pl < PPC; ++pl) acc[pl] = make_uint4(0, 0, 0, 0);
     for (int i = 0; i < nvis; ++i) {
         const StripVisit e = vis[i];
-        const unsigned char* rowp = row0 + (size_t)i * p.spv * 16;
-        uint4 v;
+        const unsigned char* rowp = row0 + (size_t)i * PPC * plane_stage;
         if (e.s == 0) {
             const int idx = tx - e.qx + 1;                 // staged chunk of tile chunk (tx - qx)
             if ((unsigned)(idx - 1) >= (unsigned)p.twv) continue;
-            v = s_ld16(rowp + (size_t)idx * 16);
+#pragma unroll
+            for (int pl = 0; pl < PPC; ++pl) {
+                const uint4 v = s_ld16(rowp + pl * plane_stage + (size_t)idx * 16);
+                acc[pl].x = s_packed_add<T>(acc[pl].x, v.x); acc[pl].y = s_packed_add<T>(acc[pl].y, v.y);
+                acc[pl].z = s_packed_add<T>(acc[pl].z, v.z); acc[pl].w = s_packed_add<T>(acc[pl].w, v.w);
+            }
         } else {
             const int idx = tx - e.qx;                     // staged chunk of tile chunk (tx - qx - 1); -1 is the left pad
             if ((unsigned)idx > (unsigned)p.twv) continue;
-            const uint4 A = s_ld16(rowp + (size_t)idx * 16), B = s_ld16(rowp + (size_t)(idx + 1) * 16);
-            v = s_window<T>(A, B, VEC - e.s);
+#pragma unroll
+            for (int pl = 0; pl < PPC; ++pl) {
+                const uint4 A = s_ld16(rowp + pl * plane_stage + (size_t)idx * 16), B = s_ld16(rowp + pl * plane_stage + (size_t)(idx + 1) * 16);
+                const uint4 v = s_window<T>(A, B, VEC - e.s);
+                acc[pl].x = s_packed_add<T>(acc[pl].x, v.x); acc[pl].y = s_packed_add<T>(acc[pl].y, v.y);
+                acc[pl].z = s_packed_add<T>(acc[pl].z, v.z); acc[pl].w = s_packed_add<T>(acc[pl].w, v.w);
+            }
         }
-        acc.x = s_packed_add<T>(acc.x, v.x);
-        acc.y = s_packed_add<T>(acc.y, v.y);
-        acc.z = s_packed_add<T>(acc.z, v.z);
-        acc.w = s_packed_add<T>(acc.w, v.w);
     }
     // x_out = where(weights > 1, x_buffer / weights, x_buffer): fp32, correctly rounded divide (multidiffusion.py:208)
     const int x0 = tx * VEC;
     const long long wo = (long long)y * p.W + x0;
-    const long long o = ((long long)plane * p.H + y) * p.W + x0;
 #pragma unroll
     for (int h = 0; h < VEC / 4; ++h) {
         const float4 w = s_ldf4(weights + wo + 4 * h);
         float4 rc = make_float4(1.f, 1.f, 1.f, 1.f);
         if constexpr (FASTDIV) rc = s_ldf4(rcp_weights + wo + 4 * h);
-        const float a0 = s_get<T>(acc, 4 * h + 0), a1 = s_get<T>(acc, 4 * h + 1), a2 = s_get<T>(acc, 4 * h + 2), a3 = s_get<T>(acc, 4 * h + 3);
-        float4 f;
-        if constexpr (FASTDIV) {
-            f.x = w.x > 1.0f ? s_div_exact(a0, w.x, rc.x) : a0;
-            f.y = w.y > 1.0f ? s_div_exact(a1, w.y, rc.y) : a1;
-            f.z = w.z > 1.0f ? s_div_exact(a2, w.z, rc.z) : a2;
-            f.w = w.w > 1.0f ? s_div_exact(a3, w.w, rc.w) : a3;
-        } else {
-            f.x = w.x > 1.0f ? s_div_ieee(a0, w.x) : a0;
-            f.y = w.y > 1.0f ? s_div_ieee(a1, w.y) : a1;
-            f.z = w.z > 1.0f ? s_div_ieee(a2, w.z) : a2;
-            f.w = w.w > 1.0f ? s_div_ieee(a3, w.w) : a3;
+#pragma unroll
+        for (int pl = 0; pl < PPC; ++pl) {
+            const long long o = ((long long)(plane + pl) * p.H + y) * p.W + x0;
+            const float a0 = s_get<T>(acc[pl], 4 * h + 0), a1 = s_get<T>(acc[pl], 4 * h + 1);
+            const float a2 = s_get<T>(acc[pl], 4 * h + 2), a3 = s_get<T>(acc[pl], 4 * h + 3);
+            float4 f;
+            if constexpr (FASTDIV) {
+                f.x = w.x > 1.0f ? s_div_exact(a0, w.x, rc.x) : a0;
+                f.y = w.y > 1.0f ? s_div_exact(a1, w.y, rc.y) : a1;
+                f.z = w.z > 1.0f ? s_div_exact(a2, w.z, rc.z) : a2;
+                f.w = w.w > 1.0f ? s_div_exact(a3, w.w, rc.w) : a3;
+            } else {
+                f.x = w.x > 1.0f ? s_div_ieee(a0, w.x) : a0;
+                f.y = w.y > 1.0f ? s_div_ieee(a1, w.y) : a1;
+                f.z = w.z > 1.0f ? s_div_ieee(a2, w.z) : a2;
+                f.w = w.w > 1.0f ? s_div_ieee(a3, w.w) : a3;
+            }
+            s_stf4(out_f32 + o + 4 * h, f);
         }
-        s_stf4(out_f32 + o + 4 * h, f);
     }
-    if constexpr (WRITE_BUF) s_st16(out_buf + o, acc);
+    if constexpr (WRITE_BUF) {
+#pragma unroll
+        for (int pl = 0; pl < PPC; ++pl) s_st16(out_buf + ((long long)(plane + pl) * p.H + y) * p.W + x0, acc[pl]);
+    }
 }
 
-template <typename T, bool WRITE_BUF, bool FASTDIV>
+template <typename T, bool WRITE_BUF, bool FASTDIV, int PPC>
 __global__ void __launch_bounds__(1024)
 strip_blend_kernel(const __grid_constant__ StripParams p, const float* __restrict__ weights, const float* __restrict__ rcp_weights,
                    float* __restrict__ out_f32, T* __restrict__ out_buf) {
     extern __shared__ __align__(16) unsigned char td_strip_smem[];
-    const int strip = blockIdx.x, plane = blockIdx.y, tid = threadIdx.x;
+    const int strip = blockIdx.x, plane = blockIdx.y * PPC, tid = threadIdx.x;
     // programmatic dependent launch (as in td_diffusion.cu): the next grid may become resident while this one drains;
     // every global access of THIS grid waits for its predecessor below.  Both are no-ops for an ordinary launch.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     strip_phase_table<T>(p, strip, plane, tid, td_strip_smem);     // kernel parameters only
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
-    strip_phase_copy<T>(p, strip, tid, (int)blockDim.x, td_strip_smem);
+    strip_phase_copy<T, PPC>(p, strip, tid, (int)blockDim.x, td_strip_smem);
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    strip_phase_consume<T, WRITE_BUF, FASTDIV>(p, strip, plane, tid, td_strip_smem, weights, rcp_weights, out_f32, out_buf);
+    strip_phase_consume<T, WRITE_BUF, FASTDIV, PPC>(p, strip, plane, tid, td_strip_smem, weights, rcp_weights, out_f32, out_buf);
 }
 
 // ---- phase 3, Mixture of Diffusers (mixtureofdiffusers.py:122-126): per element of every covering tile, in tile order,
@@ -460,14 +481,14 @@ int strip_ensure_smem(KernelT kernel, int smem, int* configured /* [64], zero-in
     return TD_OK;
 }
 
-template <typename T, bool WRITE_BUF, bool FASTDIV>
+template <typename T, bool WRITE_BUF, bool FASTDIV, int PPC>
 int strip_launch(const StripParams& p, int strips, int nthreads, int smem, const float* weights, const float* rcp, float* out_f32,
                  void* out_buf, bool pdl, cudaStream_t st) {
     static int configured[64] = {0};
-    const int rc = strip_ensure_smem(strip_blend_kernel<T, WRITE_BUF, FASTDIV>, smem, configured);
+    const int rc = strip_ensure_smem(strip_blend_kernel<T, WRITE_BUF, FASTDIV, PPC>, smem, configured);
     if (rc != TD_OK) return rc;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)strips, (unsigned)p.NC);
+    cfg.gridDim = dim3((unsigned)strips, (unsigned)(p.NC / PPC));
     cfg.blockDim = dim3((unsigned)nthreads);
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st;
@@ -476,21 +497,30 @@ int strip_launch(const StripParams& p, int strips, int nthreads, int smem, const
     attr.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, strip_blend_kernel<T, WRITE_BUF, FASTDIV>, p, weights, rcp, out_f32, (T*)out_buf);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, strip_blend_kernel<T, WRITE_BUF, FASTDIV, PPC>, p, weights, rcp, out_f32, (T*)out_buf);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { td_set_error("td_blend_multidiffusion (strip): CUDA launch failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
     return TD_OK;
 }
 
-template <typename T>
+template <typename T, int PPC>
 int strip_dispatch(const StripParams& p, int strips, int nthreads, int smem, const float* weights, const float* rcp, float* out_f32,
                    void* out_buf, bool pdl, cudaStream_t st) {
     const bool fast = rcp != nullptr && sizeof(T) == 2;
     if (out_buf != nullptr)
-        return fast ? strip_launch<T, true, true>(p, strips, nthreads, smem, weights, rcp, out_f32, out_buf, pdl, st)
-                    : strip_launch<T, true, false>(p, strips, nthreads, smem, weights, nullptr, out_f32, out_buf, pdl, st);
-    return fast ? strip_launch<T, false, true>(p, strips, nthreads, smem, weights, rcp, out_f32, out_buf, pdl, st)
-                : strip_launch<T, false, false>(p, strips, nthreads, smem, weights, nullptr, out_f32, out_buf, pdl, st);
+        return fast ? strip_launch<T, true, true, PPC>(p, strips, nthreads, smem, weights, rcp, out_f32, out_buf, pdl, st)
+                    : strip_launch<T, true, false, PPC>(p, strips, nthreads, smem, weights, nullptr, out_f32, out_buf, pdl, st);
+    return fast ? strip_launch<T, false, true, PPC>(p, strips, nthreads, smem, weights, rcp, out_f32, out_buf, pdl, st)
+                : strip_launch<T, false, false, PPC>(p, strips, nthreads, smem, weights, nullptr, out_f32, out_buf, pdl, st);
+}
+
+// planes per CTA and the shared memory that goes with it (smem1 = the one-plane size from strip_plan)
+int strip_pick_ppc(const StripParams& p, int smem1, int max_ppc, int* smem) {
+    const int table = kStripMaxVisits * (int)sizeof(StripVisit);
+    const int smem2 = table + 2 * (smem1 - table);
+    if (max_ppc >= 2 && p.NC % 2 == 0 && smem2 <= 200 * 1024) { *smem = smem2; return 2; }
+    *smem = smem1;
+    return 1;
 }
 
 template <typename T>
@@ -538,38 +568,43 @@ int td_strip_try_launch_mod(const td_grid* g, const void* const* batch_ptrs, int
 
 // TD_OK launched, 1 not applicable (the caller continues with the default kernels), < 0 error
 int td_strip_try_launch(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N, int C, int dtype,
-                        const float* weights, const float* rcp_weights, float* x_out, void* x_buffer, int pdl, void* stream) {
+                        const float* weights, const float* rcp_weights, float* x_out, void* x_buffer, int pdl, int max_ppc, void* stream) {
     std::lock_guard<std::mutex> lk(g_strip_mu);
     StripParams& p = g_strip_params;
-    int nthreads = 0, smem = 0, strips = 0;
-    if (strip_plan(g, batch_ptrs, num_batches, tile_bs, N, C, td_dtype_size(dtype), &p, &nthreads, &smem, &strips) != 0) return 1;
+    int nthreads = 0, smem1 = 0, strips = 0, smem = 0;
+    if (strip_plan(g, batch_ptrs, num_batches, tile_bs, N, C, td_dtype_size(dtype), &p, &nthreads, &smem1, &strips) != 0) return 1;
+    const int ppc = strip_pick_ppc(p, smem1, max_ppc, &smem);
     cudaStream_t st = (cudaStream_t)stream;
+#define TD_STRIP_CASE(TYPE, RCP) \
+    return ppc == 2 ? strip_dispatch<TYPE, 2>(p, strips, nthreads, smem, weights, RCP, x_out, x_buffer, pdl != 0, st) \
+                    : strip_dispatch<TYPE, 1>(p, strips, nthreads, smem, weights, RCP, x_out, x_buffer, pdl != 0, st)
     switch (dtype) {
-        case TD_F16: return strip_dispatch<__half>(p, strips, nthreads, smem, weights, rcp_weights, x_out, x_buffer, pdl != 0, st);
-        case TD_BF16: return strip_dispatch<__nv_bfloat16>(p, strips, nthreads, smem, weights, rcp_weights, x_out, x_buffer, pdl != 0, st);
-        case TD_F32: return strip_dispatch<float>(p, strips, nthreads, smem, weights, nullptr, x_out, x_buffer, pdl != 0, st);
+        case TD_F16: TD_STRIP_CASE(__half, rcp_weights);
+        case TD_BF16: TD_STRIP_CASE(__nv_bfloat16, rcp_weights);
+        case TD_F32: TD_STRIP_CASE(float, nullptr);
         default: return 1;
     }
+#undef TD_STRIP_CASE
 }
 
 #ifdef TD_STRIP_HOST_EMULATION
 // Test-only (tests/emul/strip_host_emul.cu): run every CTA of the strip kernel on the host, thread by thread, phase by phase.
-template <typename T>
+template <typename T, int PPC>
 static void emul_run(const StripParams& p, int strips, int nthreads, int smem_bytes, const float* weights, const float* rcp, float* out_f32,
                      void* out_buf) {
     unsigned char* smem = new unsigned char[smem_bytes + 16];
-    for (int plane = 0; plane < p.NC; ++plane)
+    for (int plane = 0; plane < p.NC; plane += PPC)
         for (int strip = 0; strip < strips; ++strip) {
             memset(smem, 0xCD, smem_bytes);       // stale shared memory must not matter
             for (int tid = 0; tid < nthreads; ++tid) strip_phase_table<T>(p, strip, plane, tid, smem);
-            for (int tid = 0; tid < nthreads; ++tid) strip_phase_copy<T>(p, strip, tid, nthreads, smem);
+            for (int tid = 0; tid < nthreads; ++tid) strip_phase_copy<T, PPC>(p, strip, tid, nthreads, smem);
             for (int tid = 0; tid < nthreads; ++tid) {
                 if (out_buf != nullptr) {
-                    if (rcp != nullptr && sizeof(T) == 2) strip_phase_consume<T, true, true>(p, strip, plane, tid, smem, weights, rcp, out_f32, (T*)out_buf);
-                    else strip_phase_consume<T, true, false>(p, strip, plane, tid, smem, weights, nullptr, out_f32, (T*)out_buf);
+                    if (rcp != nullptr && sizeof(T) == 2) strip_phase_consume<T, true, true, PPC>(p, strip, plane, tid, smem, weights, rcp, out_f32, (T*)out_buf);
+                    else strip_phase_consume<T, true, false, PPC>(p, strip, plane, tid, smem, weights, nullptr, out_f32, (T*)out_buf);
                 } else {
-                    if (rcp != nullptr && sizeof(T) == 2) strip_phase_consume<T, false, true>(p, strip, plane, tid, smem, weights, rcp, out_f32, (T*)nullptr);
-                    else strip_phase_consume<T, false, false>(p, strip, plane, tid, smem, weights, nullptr, out_f32, (T*)nullptr);
+                    if (rcp != nullptr && sizeof(T) == 2) strip_phase_consume<T, false, true, PPC>(p, strip, plane, tid, smem, weights, rcp, out_f32, (T*)nullptr);
+                    else strip_phase_consume<T, false, false, PPC>(p, strip, plane, tid, smem, weights, nullptr, out_f32, (T*)nullptr);
                 }
             }
         }
@@ -602,14 +637,19 @@ extern "C" int td_emul_strip_blend_mod(const td_grid* g, const void* const* batc
 }
 
 extern "C" int td_emul_strip_blend(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N, int C, int dtype,
-                                   const float* weights, const float* rcp_weights, float* x_out, void* x_buffer, int* out_info) {
+                                   const float* weights, const float* rcp_weights, float* x_out, void* x_buffer, int max_ppc, int* out_info) {
     static StripParams p;
-    int nthreads = 0, smem = 0, strips = 0;
-    if (strip_plan(g, batch_ptrs, num_batches, tile_bs, N, C, td_dtype_size(dtype), &p, &nthreads, &smem, &strips) != 0) return 1;
-    if (out_info != nullptr) { out_info[0] = strips; out_info[1] = nthreads; out_info[2] = smem; }
-    if (dtype == TD_F16) emul_run<__half>(p, strips, nthreads, smem, weights, rcp_weights, x_out, x_buffer);
-    else if (dtype == TD_BF16) emul_run<__nv_bfloat16>(p, strips, nthreads, smem, weights, rcp_weights, x_out, x_buffer);
-    else emul_run<float>(p, strips, nthreads, smem, weights, nullptr, x_out, x_buffer);
+    int nthreads = 0, smem1 = 0, strips = 0, smem = 0;
+    if (strip_plan(g, batch_ptrs, num_batches, tile_bs, N, C, td_dtype_size(dtype), &p, &nthreads, &smem1, &strips) != 0) return 1;
+    const int ppc = strip_pick_ppc(p, smem1, max_ppc, &smem);
+    if (out_info != nullptr) { out_info[0] = strips; out_info[1] = nthreads; out_info[2] = smem; out_info[3] = ppc; }
+#define TD_EMUL_CASE(TYPE, RCP) \
+    do { if (ppc == 2) emul_run<TYPE, 2>(p, strips, nthreads, smem, weights, RCP, x_out, x_buffer); \
+         else emul_run<TYPE, 1>(p, strips, nthreads, smem, weights, RCP, x_out, x_buffer); } while (0)
+    if (dtype == TD_F16) TD_EMUL_CASE(__half, rcp_weights);
+    else if (dtype == TD_BF16) TD_EMUL_CASE(__nv_bfloat16, rcp_weights);
+    else TD_EMUL_CASE(float, nullptr);
+#undef TD_EMUL_CASE
     return TD_OK;
 }
 #endif

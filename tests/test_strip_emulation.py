@@ -40,7 +40,7 @@ def emul():
     return ctypes.CDLL(so)
 
 
-def _strip_step(emul, x, W, H, tw, th, ov, bs, use_rcp=False, want_buffer=True):
+def _strip_step(emul, x, W, H, tw, th, ov, bs, use_rcp=False, want_buffer=True, max_ppc=2):
     """scatter (oracle) -> fake UNet per batch -> emulated strip blend.  Returns (x_out fp32, x_buffer, launch info)."""
     from multidiffusion_upscaler_for_automatic1111_b200 import engine
     N, C = x.shape[:2]
@@ -52,25 +52,26 @@ def _strip_step(emul, x, W, H, tw, th, ov, bs, use_rcp=False, want_buffer=True):
     rcp = engine.exact_reciprocals(weights) if use_rcp else None
     x_out = torch.empty((N, C, H, W), dtype=torch.float32)
     xb = torch.empty_like(x) if want_buffer else None
-    info = (ctypes.c_int * 3)()
+    info = (ctypes.c_int * 4)()
     rc = emul.td_emul_strip_blend(ctypes.byref(g), ptrs, len(outs), int(g.tile_bs), N, C, CODE[x.dtype],
                                   weights.ctypes.data_as(ctypes.c_void_p), rcp.ctypes.data_as(ctypes.c_void_p) if rcp is not None else None,
-                                  ctypes.c_void_p(x_out.data_ptr()), ctypes.c_void_p(xb.data_ptr()) if xb is not None else None, info)
+                                  ctypes.c_void_p(x_out.data_ptr()), ctypes.c_void_p(xb.data_ptr()) if xb is not None else None, max_ppc, info)
     return rc, x_out, xb, tuple(info), plan
 
 
 @pytest.mark.parametrize("case", BLEND_CASES, ids=[c[0] for c in BLEND_CASES])
 @pytest.mark.parametrize("dn", list(DTYPES))
-def test_emulated_strip_blend_matches_reference_fixture(emul, golden_dir, case, dn):
+@pytest.mark.parametrize("max_ppc", [1, 2], ids=["one_plane", "two_planes"])
+def test_emulated_strip_blend_matches_reference_fixture(emul, golden_dir, case, dn, max_ppc):
     name, N, C, W, H, tw, th, ov, bs = case
     dt = DTYPES[dn]
     x = synth.latent(synth.case_seed(name, dn), (N, C, H, W), dt)
     vec = 16 // x.element_size()
-    rc, x_out, xb, info, plan = _strip_step(emul, x, W, H, tw, th, ov, bs)
+    rc, x_out, xb, info, plan = _strip_step(emul, x, W, H, tw, th, ov, bs, max_ppc=max_ppc)
     if W % vec or min(tw, W) % vec:
         assert rc == 1                                   # not applicable: the entry point falls back to the default kernels
         return
-    assert rc == 0
+    assert rc == 0 and info[3] == (max_ppc if (N * C) % 2 == 0 else 1)
     g = np.load(os.path.join(golden_dir, "blend_small.npz"))
     want = torch.from_numpy(g[f"{name}_{dn}_md"].view(np.int32).copy()).view(torch.float32)
     assert_bit_equal(x_out, want, "strip blend vs reference")
@@ -99,10 +100,10 @@ def test_emulated_strip_blend_full_size_cfg2(emul, golden_dir):
     x = synth.latent(synth.case_seed(name, "f16"), (N, C, H, W), torch.float16)
     rc, x_out, _, info, _ = _strip_step(emul, x, W, H, tw, th, ov, bs, use_rcp=True, want_buffer=False)
     assert rc == 0
-    strips, nthreads, smem = info
-    assert (strips, nthreads) == (-(-512 // ROWS), ROWS * 64)
+    strips, nthreads, smem, ppc = info
+    assert (strips, nthreads, ppc) == (-(-512 // ROWS), ROWS * 64, 2)
     if ROWS == 8:
-        assert 50_000 < smem < 57_000
+        assert 100_000 < smem < 112_000      # two planes per CTA: 2 CTAs / SM, 256 CTAs -> still one wave on 148 SMs
     g = np.load(os.path.join(golden_dir, "blend_hashes.npz"))
     assert sha(x_out) == str(g[f"{name}_f16_md"])
 
