@@ -421,6 +421,8 @@ def gpu_arm(args, rank, world, local_rank):
                 try:      # strip form (td_strip.cu): opt-in, first timed in round 2
                     tbl["blend_strip"] = only(lambda s: wl.blend(s, 128))
                     tbl["blend_strip_L2hot"] = only(lambda s: wl.blend(0, 128))
+                    tbl["blend_strip_one_plane"] = only(lambda s: wl.blend(s, 128 | 64))
+                    tbl["blend_strip_no_pdl"] = only(lambda s: wl.blend(s, 128 | 32))
                     tbl["blend_mixture_strip"] = only(lambda s: wl.blend_mod(s, 128))
                 except Exception as e:
                     tbl["blend_strip_error"] = -1.0

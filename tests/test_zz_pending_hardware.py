@@ -77,7 +77,8 @@ STRIP = 128
 @pytest.mark.xfail(strict=False, reason="strip blend (TD_FLAG_STRIP): first hardware run pending; host emulation in test_strip_emulation.py")
 @pytest.mark.parametrize("dn", list(DTYPES))
 @pytest.mark.parametrize("use_rcp", [False, True])
-def test_strip_blend_matches_reference_fixtures_on_gpu(golden_dir, dn, use_rcp):
+@pytest.mark.parametrize("STRIP", [128, 128 | 64], ids=["two_planes", "one_plane"])
+def test_strip_blend_matches_reference_fixtures_on_gpu(golden_dir, dn, use_rcp, STRIP):
     from multidiffusion_upscaler_for_automatic1111_b200 import engine
     from helpers import bits, sha
     from test_gpu_diffusion import _run_cuda_step
