@@ -276,6 +276,7 @@ __host__ __device__ __forceinline__ void strip_phase_consume(const StripParams& 
     for (int pl = 0; pl < PPC; ++pl) acc[pl] = make_uint4(0, 0, 0, 0);
     for (int i = 0; i < nvis; ++i) {
         const StripVisit e = vis[i];
+        if ((unsigned)(e.v0 + ty) >= (unsigned)p.th) continue;     // this canvas row lies above / below the tile (its stage rows are zero)
         const unsigned char* rowp = row0 + (size_t)i * PPC * plane_stage;
         if (e.s == 0) {
             const int idx = tx - e.qx + 1;                 // staged chunk of tile chunk (tx - qx)
