@@ -176,9 +176,16 @@ class AbstractDiffusion:
         cond_dict[key] = [tcond] if isinstance(cond_dict[key], list) else tcond
 
     def _icond_key(self, cond_dict: CondDict) -> str:
-        model = getattr(self._sd_model(), "model", None)
-        ck = getattr(model, "conditioning_key", None)
-        return "c_adm" if ck in ("crossattn-adm", "adm") else "c_concat"
+        # the model's conditioning key cannot change during a job: resolved once per model object (this sits on the
+        # per-tile-batch path, 25 batches x 3 lookups per sampler step at the UI default)
+        sd_model = self._sd_model()
+        cached = self.__dict__.get("_icond_key_cache")
+        if cached is not None and cached[0] is sd_model:
+            return cached[1]
+        ck = getattr(getattr(sd_model, "model", None), "conditioning_key", None)
+        key = "c_adm" if ck in ("crossattn-adm", "adm") else "c_concat"
+        self._icond_key_cache = (sd_model, key)
+        return key
 
     def get_icond(self, cond_dict: CondDict) -> Tensor:
         icond = cond_dict[self._icond_key(cond_dict)]
@@ -783,6 +790,31 @@ class AbstractDiffusion:
         lo = batch_id * self.tile_bs * N
         hi = min((batch_id + 1) * self.tile_bs, self.num_tiles) * N
         return tiles[lo:hi]
+
+    def cat_repeat(self, x: Tensor, n: int) -> Tensor:
+        """`torch.cat([x] * n, dim=0)` (mixtureofdiffusers.py:91-99), memoised per source tensor object and version: the
+        batches of one UNet call repeat the same timestep / cond tensors, one copy serves them all."""
+        if n == 1:
+            return x
+        cache = self.__dict__.setdefault("_cat_cache", {})
+        key = (id(x), n)
+        hit = cache.get(key)
+        if hit is not None and hit[0] is x and hit[1] == x._version:
+            return hit[2]
+        out = torch.cat([x] * n, dim=0)
+        if len(cache) > 16:
+            cache.clear()
+        cache[key] = (x, x._version, out)   # the strong reference keeps id(x) from being recycled
+        return out
+
+    def _tile_batch_views(self, tiles: Tensor, N: int) -> List[Tensor]:
+        """The per-batch views of the persistent tile buffer, built once per buffer (not once per sampler step)."""
+        cached = self.__dict__.get("_tile_views_cache")
+        if cached is not None and cached[0] is tiles and cached[1] == N:
+            return cached[2]
+        views = [self._tile_batch(tiles, b, N) for b in range(self.num_batches)]
+        self._tile_views_cache = (tiles, N, views)
+        return views
 
     def _icond_tile_batches(self, icond: Tensor):
         """img2img: spatial icond is cropped per tile like the latent (multidiffusion.py:121-122)."""

@@ -127,17 +127,15 @@ class MixtureOfDiffusers(AbstractDiffusion):
                             N: int) -> Tensor:
         """One UNet call on a batch of n_rep tiles: timestep / text / vector cond repeated per tile, spatial image cond
         already cropped per tile (mixtureofdiffusers.py:89-119)."""
-        t_tile = torch.cat([t_in] * n_rep, dim=0) if n_rep > 1 else t_in
+        t_tile = self.cat_repeat(t_in, n_rep)
         if not isinstance(c_in, dict):
             raise NotImplementedError("non-dict conditioning is not supported by Mixture of Diffusers "
                                       "(the reference only prints a warning here, mixtureofdiffusers.py:103)")
-        tcond = self.get_tcond(c_in)
-        tcond_tile = torch.cat([tcond] * n_rep, dim=0) if n_rep > 1 else tcond
+        tcond_tile = self.cat_repeat(self.get_tcond(c_in), n_rep)
         if icond_tile is None:
-            icond = self.get_icond(c_in)
-            icond_tile = torch.cat([icond] * n_rep, dim=0) if n_rep > 1 else icond
+            icond_tile = self.cat_repeat(self.get_icond(c_in), n_rep)
         vcond = self.get_vcond(c_in)
-        vcond_tile = None if vcond is None else (torch.cat([vcond] * n_rep, dim=0) if n_rep > 1 else vcond)
+        vcond_tile = None if vcond is None else self.cat_repeat(vcond, n_rep)
         c_tile = self.make_cond_dict(c_in, tcond_tile, icond_tile, vcond_tile)
         self.switch_controlnet_tensors(batch_id, N, n_rep, is_denoise=True)
         self.switch_stablesr_tensors(batch_id)

@@ -91,18 +91,36 @@ class MultiDiffusion(AbstractDiffusion):
         return self.sample_one_step(x_in, org_func, repeat_func, custom_func)
 
     def repeat_cond_dict(self, cond_in: CondDict, bboxes: List[BBox]) -> CondDict:
-        """Per-batch cond (multidiffusion.py:112-129): text/vector cond repeated, spatial icond cropped per tile."""
+        """Per-batch cond (multidiffusion.py:112-129): text/vector cond repeated, spatial icond cropped per tile.
+
+        Without a spatial icond the result only depends on (cond_in, len(bboxes)): every batch of a step gets a shallow
+        copy of one memoised dict instead of rebuilding it (the tensors inside are shared, as they are read-only)."""
         n_rep = len(bboxes)
+        memo = self.__dict__.get("_cond_memo")
+        if memo is not None and memo[0] is cond_in and memo[1] == n_rep and memo[2] == self._cond_versions(cond_in):
+            return dict(memo[3])
         tcond = self.repeat_tensor(self.get_tcond(cond_in), n_rep)
         icond = self.get_icond(cond_in)
-        if tuple(icond.shape[2:]) == (self.h, self.w):
+        spatial = tuple(icond.shape[2:]) == (self.h, self.w)
+        if spatial:
             icond = self._crop_icond(icond, bboxes)
         else:
             icond = self.repeat_tensor(icond, n_rep)
         vcond = self.get_vcond(cond_in)
         if vcond is not None:
             vcond = self.repeat_tensor(vcond, n_rep)
-        return self.make_cond_dict(cond_in, tcond, icond, vcond)
+        out = self.make_cond_dict(cond_in, tcond, icond, vcond)
+        if not spatial:
+            # the source tensors are kept alive with the memo so that their ids cannot be recycled
+            sources = (self.get_tcond(cond_in), self.get_icond(cond_in), self.get_vcond(cond_in))
+            self._cond_memo = (cond_in, n_rep, self._cond_versions(cond_in), out, sources)
+            return dict(out)
+        return out
+
+    def _cond_versions(self, cond_in: CondDict):
+        """Identity + in-place version of the tensors a memoised cond dict was built from."""
+        t, i, v = self.get_tcond(cond_in), self.get_icond(cond_in), self.get_vcond(cond_in)
+        return (id(t), t._version, id(i), i._version, None if v is None else (id(v), v._version))
 
     def _crop_icond(self, icond: Tensor, bboxes: List[BBox]) -> Tensor:
         """Spatial icond -> tile batch with the same scatter kernel as the latent."""
@@ -141,15 +159,19 @@ class MultiDiffusion(AbstractDiffusion):
         x_out = None
         if self.enable_grid_bbox:
             tiles = self._scatter_all(x)
+            views = self._tile_batch_views(tiles, N)
+            state = getattr(host.get_shared(), "state", None)      # polled per tile batch (multidiffusion.py:152)
+            side_inputs = self.enable_controlnet or self.enable_stablesr
             outs = []
             for batch_id, bboxes in enumerate(self.batched_bboxes):
-                if host.interrupted():
+                if state is not None and getattr(state, "interrupted", False):
                     return x_in
-                x_tile = self._tile_batch(tiles, batch_id, N)
-                self.switch_controlnet_tensors(batch_id, N, len(bboxes))
-                self.switch_stablesr_tensors(batch_id)
-                outs.append(repeat_func(x_tile, bboxes))
-                self.update_pbar()
+                if side_inputs:
+                    self.switch_controlnet_tensors(batch_id, N, len(bboxes))
+                    self.switch_stablesr_tensors(batch_id)
+                outs.append(repeat_func(views[batch_id], bboxes))
+                if self.pbar is not None:
+                    self.update_pbar()
             if needs_buffer:
                 self.reset_buffer(x)
             x_out = engine.blend_multidiffusion(self._grid, outs, N, C, self.tile_bs, self.weights, x.dtype,

@@ -116,3 +116,41 @@ def test_repeat_tensor_semantics():
     b = torch.arange(4.0).view(2, 2)
     assert torch.equal(d.repeat_tensor(b, 3), b.repeat(3, 1))
     assert d.repeat_tensor(b, 1) is b
+
+
+def test_cond_memo_follows_the_source_tensors():
+    """repeat_cond_dict is memoised per (cond dict, repeat count): every batch gets its own dict object, and the memo
+    is dropped when a source tensor is modified in place or replaced."""
+    from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
+    from multidiffusion_upscaler_for_automatic1111_b200.tile_utils.utils import BBox
+    d = MultiDiffusion(_p(), _sampler())
+    d.init_grid_bbox(96, 96, 48, 4)
+    d.init_done()
+    bbs = [BBox(0, 0, 96, 96)] * 3
+    t = torch.arange(2 * 3 * 4, dtype=torch.float32).view(2, 3, 4)
+    cond = {"c_crossattn": [t], "c_concat": [torch.zeros(2, 5, 1, 1)]}
+    a, b = d.repeat_cond_dict(cond, bbs), d.repeat_cond_dict(cond, bbs)
+    assert a is not b and a["c_crossattn"][0] is b["c_crossattn"][0]          # fresh dict, shared (read-only) tensors
+    assert torch.equal(a["c_crossattn"][0], t.repeat(3, 1, 1)) and a["c_concat"][0].shape[0] == 6
+    t.add_(1)                                                                  # in-place update: version changes
+    c = d.repeat_cond_dict(cond, bbs)
+    assert torch.equal(c["c_crossattn"][0], t.repeat(3, 1, 1)) and c["c_crossattn"][0] is not a["c_crossattn"][0]
+    cond["c_crossattn"] = [t * 2]                                              # replaced tensor in the same dict
+    e = d.repeat_cond_dict(cond, bbs)
+    assert torch.equal(e["c_crossattn"][0], (t * 2).repeat(3, 1, 1))
+    assert d.repeat_cond_dict(cond, bbs[:2])["c_crossattn"][0].shape[0] == 4   # another repeat count
+
+
+def test_cat_repeat_memo():
+    from multidiffusion_upscaler_for_automatic1111_b200 import MixtureOfDiffusers, host
+    model = types.SimpleNamespace(apply_model=lambda x, t, c: x, model=types.SimpleNamespace(conditioning_key="crossattn"), cond_stage_key="txt")
+    host.use_shared(types.SimpleNamespace(state=types.SimpleNamespace(interrupted=False, sampling_step=0, sampling_steps=1), sd_model=model))
+    try:
+        d = MixtureOfDiffusers(_p(), _sampler())
+        x = torch.arange(6.0).view(2, 3)
+        r = d.cat_repeat(x, 3)
+        assert torch.equal(r, torch.cat([x] * 3)) and d.cat_repeat(x, 3) is r and d.cat_repeat(x, 1) is x
+        x.mul_(2)
+        assert torch.equal(d.cat_repeat(x, 3), torch.cat([x] * 3))
+    finally:
+        host.use_shared(None)
