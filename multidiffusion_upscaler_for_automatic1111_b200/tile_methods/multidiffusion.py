@@ -97,8 +97,13 @@ class MultiDiffusion(AbstractDiffusion):
         copy of one memoised dict instead of rebuilding it (the tensors inside are shared, as they are read-only)."""
         n_rep = len(bboxes)
         memo = self.__dict__.get("_cond_memo")
-        if memo is not None and memo[0] is cond_in and memo[1] == n_rep and memo[2] == self._cond_versions(cond_in):
-            return dict(memo[3])
+        token = self.__dict__.get("_step_token", 0)
+        if memo is not None and memo[0] is cond_in and memo[1] == n_rep:
+            if memo[5] == token:                       # validated earlier in this sampler step
+                return dict(memo[3])
+            if memo[2] == self._cond_versions(cond_in):
+                self._cond_memo = memo[:5] + (token,)
+                return dict(memo[3])
         tcond = self.repeat_tensor(self.get_tcond(cond_in), n_rep)
         icond = self.get_icond(cond_in)
         spatial = tuple(icond.shape[2:]) == (self.h, self.w)
@@ -113,7 +118,7 @@ class MultiDiffusion(AbstractDiffusion):
         if not spatial:
             # the source tensors are kept alive with the memo so that their ids cannot be recycled
             sources = (self.get_tcond(cond_in), self.get_icond(cond_in), self.get_vcond(cond_in))
-            self._cond_memo = (cond_in, n_rep, self._cond_versions(cond_in), out, sources)
+            self._cond_memo = (cond_in, n_rep, self._cond_versions(cond_in), out, sources, token)
             return dict(out)
         return out
 
@@ -147,6 +152,7 @@ class MultiDiffusion(AbstractDiffusion):
             return org_func(x_in)
 
         x = self._check_input(x_in)
+        self._step_token = self.__dict__.get("_step_token", 0) + 1     # memoised per-batch inputs are re-validated once per step
         regions = self.enable_custom_bbox and len(self.custom_bboxes) > 0
         # a BACKGROUND region is added to x_buffer BEFORE the division, so the un-normalised buffer is needed
         needs_buffer = regions and any(b.blend_mode == BlendMode.BACKGROUND for b in self.custom_bboxes)

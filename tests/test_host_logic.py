@@ -119,8 +119,8 @@ def test_repeat_tensor_semantics():
 
 
 def test_cond_memo_follows_the_source_tensors():
-    """repeat_cond_dict is memoised per (cond dict, repeat count): every batch gets its own dict object, and the memo
-    is dropped when a source tensor is modified in place or replaced."""
+    """repeat_cond_dict is memoised per (cond dict, repeat count): every batch gets its own dict object; the memo is
+    re-validated once per sampler step and dropped when a source tensor was modified in place or replaced."""
     from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
     from multidiffusion_upscaler_for_automatic1111_b200.tile_utils.utils import BBox
     d = MultiDiffusion(_p(), _sampler())
@@ -132,10 +132,12 @@ def test_cond_memo_follows_the_source_tensors():
     a, b = d.repeat_cond_dict(cond, bbs), d.repeat_cond_dict(cond, bbs)
     assert a is not b and a["c_crossattn"][0] is b["c_crossattn"][0]          # fresh dict, shared (read-only) tensors
     assert torch.equal(a["c_crossattn"][0], t.repeat(3, 1, 1)) and a["c_concat"][0].shape[0] == 6
-    t.add_(1)                                                                  # in-place update: version changes
+    t.add_(1)                                                                  # in-place update between sampler steps
+    d._step_token = d.__dict__.get("_step_token", 0) + 1                       # (sample_one_step bumps the token once per step)
     c = d.repeat_cond_dict(cond, bbs)
     assert torch.equal(c["c_crossattn"][0], t.repeat(3, 1, 1)) and c["c_crossattn"][0] is not a["c_crossattn"][0]
     cond["c_crossattn"] = [t * 2]                                              # replaced tensor in the same dict
+    d._step_token += 1
     e = d.repeat_cond_dict(cond, bbs)
     assert torch.equal(e["c_crossattn"][0], (t * 2).repeat(3, 1, 1))
     assert d.repeat_cond_dict(cond, bbs[:2])["c_crossattn"][0].shape[0] == 4   # another repeat count
