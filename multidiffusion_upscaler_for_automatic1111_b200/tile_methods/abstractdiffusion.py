@@ -638,6 +638,10 @@ class AbstractDiffusion:
         dev = host.device()
         if t.device != dev:
             t = t.to(dev)
+        if max(self._grid.H, self._grid.W) * scale >= 32768:
+            # beyond the kernels' 16-bit tile origins (a 32k-pixel hint): plain slicing, same tile order
+            s = scale
+            return torch.cat([t[:, :, b[1] * s:b[3] * s, b[0] * s:b[2] * s] for batch in self.batched_bboxes for b in batch], dim=0)
         g = self._grid if scale == 1 else engine.scaled_grid(self._grid, scale)
         return engine.scatter_tiles(g, t.contiguous(), flags=self._blend_flags)
 
