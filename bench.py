@@ -269,7 +269,7 @@ class Workload:
         ptrs, nb, tbs = self._tables[s]
         c.check(c.lib.td_blend_multidiffusion(ctypes.byref(self.g), ptrs, nb, tbs, self.N, self.C, c.TD_F16, c.TD_F16,
                                               self.weights.data_ptr(), None if (flags & 0x200) else self.rcp_weights.data_ptr(),
-                                              self.x_out[s].data_ptr(), None, flags & 0x1ff, self.stream))
+                                              self.x_out[s].data_ptr(), None, flags & 0x5ff, self.stream))
 
     def blend_mod(self, s, flags=0):
         """Mixture of Diffusers blend on the same tile outputs (BASELINE config 3's method)."""
@@ -417,21 +417,23 @@ def gpu_arm(args, rank, world, local_rank):
             t_scatter_ser = only(lambda s: wl.scatter(s, 32))
             if args.variants:
                 tbl = {"empty_1024x128": only(wl.empty)}
-                tbl["blend_async_one_plane"] = only(lambda s: wl.blend(s, 64))
-                try:      # strip form (td_strip.cu): opt-in, first timed in round 2
-                    tbl["blend_strip"] = only(lambda s: wl.blend(s, 128))
-                    tbl["blend_strip_L2hot"] = only(lambda s: wl.blend(0, 128))
-                    tbl["blend_strip_one_plane"] = only(lambda s: wl.blend(s, 128 | 64))
-                    tbl["blend_strip_no_pdl"] = only(lambda s: wl.blend(s, 128 | 32))
-                    tbl["blend_mixture_strip"] = only(lambda s: wl.blend_mod(s, 128))
-                except Exception as e:
-                    tbl["blend_strip_error"] = -1.0
-                    print(f"strip variant failed: {e!r}", file=sys.stderr)
-                tbl["blend_async_ieee_div"] = only(lambda s: wl.blend(s, 0x200))
+                tbl["blend_rows"] = only(lambda s: wl.blend(s, 0))
+                tbl["blend_rows_L2hot"] = only(lambda s: wl.blend(0, 0))
+                tbl["blend_rows_no_tiles"] = only(lambda s: wl.blend(s, 0x100))
+                tbl["blend_rows_no_pdl"] = only(lambda s: wl.blend(s, 32))
+                tbl["blend_rows_ieee_div"] = only(lambda s: wl.blend(s, 0x200))
+                tbl["scatter_rows"] = only(lambda s: wl.scatter(s, 0))
+                tbl["scatter_rows_L2hot"] = only(lambda s: wl.scatter(0, 0))
+                tbl["scatter_rows_no_pdl"] = only(lambda s: wl.scatter(s, 32))
                 wl.blend_mod(0)
-                tbl["blend_mixture_async"] = only(lambda s: wl.blend_mod(s, 0))
+                tbl["blend_mixture_rows"] = only(lambda s: wl.blend_mod(s, 0))
+                tbl["blend_mixture_rows_L2hot"] = only(lambda s: wl.blend_mod(0, 0))
+                tbl["blend_async_one_plane"] = only(lambda s: wl.blend(s, 64))
+                tbl["blend_async_ieee_div"] = only(lambda s: wl.blend(s, 0x200 | 0x400))
+                wl.blend_mod(0)
+                tbl["blend_mixture_async"] = only(lambda s: wl.blend_mod(s, 0x400))
                 tbl["blend_mixture_reg"] = only(lambda s: wl.blend_mod(s, 2))
-                for name, fl in (("async", 0), ("pipe", 8), ("tma", 4), ("reg", 2)):
+                for name, fl in (("async", 0x400), ("pipe", 8), ("tma", 4), ("reg", 2)):
                     tbl[f"blend_{name}"] = only(lambda s, fl=fl: wl.blend(s, fl))
                     tbl[f"blend_{name}_no_tiles"] = only(lambda s, fl=fl: wl.blend(s, fl | 0x100))
                     tbl[f"blend_{name}_L2hot"] = only(lambda s, fl=fl: wl.blend(0, fl))

@@ -30,27 +30,23 @@ def scatter_tiles(x_in: torch.Tensor, bboxes: Sequence[BBox]) -> torch.Tensor:
 
 
 def accumulate_md(x_buffer: torch.Tensor, tile_out: torch.Tensor, bboxes: Sequence[BBox], N: int) -> None:
-    """multidiffusion.py:166-167: `x_buffer[slicer] += tile` -- fp32 add, round to buffer dtype."""
+    """multidiffusion.py:166-167, op for op: `x_buffer[slicer] += tile` (in-place add in the buffer dtype; torch
+    rounds the exact sum once, i.e. half(float(a) + float(b)) for fp16 / bf16)."""
     for i, (x, y, w, h) in enumerate(bboxes):
-        cur = x_buffer[:, :, y:y + h, x:x + w].float()
-        add = tile_out[i * N:(i + 1) * N].float()
-        x_buffer[:, :, y:y + h, x:x + w] = (cur + add).to(x_buffer.dtype)
+        x_buffer[:, :, y:y + h, x:x + w] += tile_out[i * N:(i + 1) * N, :, :, :]
 
 
 def normalise_md(x_buffer: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
     """multidiffusion.py:208.  weights: fp32 [1,1,H,W].  Result is fp32."""
-    xb = x_buffer.float()
-    return torch.where(weights > 1, xb / weights, xb)
+    return torch.where(weights > 1, x_buffer / weights, x_buffer)
 
 
 def accumulate_mod(x_buffer: torch.Tensor, tile_out: torch.Tensor, bboxes: Sequence[BBox], N: int,
                    tile_weights: torch.Tensor, rescale_factor: torch.Tensor) -> None:
-    """mixtureofdiffusers.py:125-126."""
+    """mixtureofdiffusers.py:125-126, op for op."""
     for i, (x, y, w, h) in enumerate(bboxes):
         wgt = tile_weights * rescale_factor[:, :, y:y + h, x:x + w]          # fp32 product (own rounding)
-        prod = tile_out[i * N:(i + 1) * N].float() * wgt                      # fp32 product
-        cur = x_buffer[:, :, y:y + h, x:x + w].float()
-        x_buffer[:, :, y:y + h, x:x + w] = (cur + prod).to(x_buffer.dtype)
+        x_buffer[:, :, y:y + h, x:x + w] += tile_out[i * N:(i + 1) * N, :, :, :] * wgt   # fp32 product, add, round to buffer dtype
 
 
 def multidiffusion_step(x_in: torch.Tensor, batched_bboxes: List[List[BBox]], weights: np.ndarray,

@@ -18,16 +18,21 @@ def sha(t: torch.Tensor) -> str:
     return hashlib.sha256(bits(t).tobytes()).hexdigest()
 
 
-def assert_bit_equal(a: torch.Tensor, b: torch.Tensor, what: str = ""):
+def assert_bit_equal(a: torch.Tensor, b: torch.Tensor, what: str = "", allow_signed_zero: bool = False):
+    """Bit patterns must match (sign of zero and NaN payloads included).  `allow_signed_zero=True` is an explicit
+    opt-out for comparisons whose two sides legitimately differ in the sign of a zero (say why at the call site)."""
     assert a.dtype == b.dtype, f"{what}: dtype {a.dtype} vs {b.dtype}"
     assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
     ba, bb = bits(a), bits(b)
-    if not np.array_equal(ba, bb):
-        # +0.0 / -0.0 are the same value to torch.equal; report genuine mismatches only
-        fa, fb = a.detach().cpu().float(), b.detach().cpu().float()
-        bad = ~((fa == fb) | (fa.isnan() & fb.isnan()))
-        n = int(bad.sum())
-        assert n == 0, f"{what}: {n} mismatching elements, max abs diff {(fa - fb).abs().max().item()}"
+    if np.array_equal(ba, bb):
+        return
+    fa, fb = a.detach().cpu().float(), b.detach().cpu().float()
+    bad = ~((fa == fb) | (fa.isnan() & fb.isnan()))
+    n = int(bad.sum())
+    assert n == 0, f"{what}: {n} mismatching elements, max abs diff {(fa - fb).abs().max().item()}"
+    if not allow_signed_zero:
+        nz = int((ba != bb).sum())
+        raise AssertionError(f"{what}: values equal but {nz} elements differ in bit pattern (sign of zero / NaN payload)")
 
 
 def install_demofusion_stand_ins(set_attr=setattr):

@@ -1,7 +1,7 @@
 """GPU tests of everything written after the round-1 GPU budget was spent: region prompt control, ControlNet tile caches,
 DemoFusion random jitter (the list-driven kernels of csrc/td_jitter.cu).  Their host logic is pinned on CPU against the
 reference (tests/test_region*.py, test_side_inputs.py, test_demofusion.py); the device runs below have not executed on
-hardware yet, hence `xfail(strict=False)`: XPASS = verified, XFAIL = something to fix in round 2.
+hardware when they were written; all of them passed on B200 (round-1 driver run, round-2 first run) and are plain tests now.
 
 The file sorts last on purpose: should a never-run kernel fault, the CUDA context of the pytest process is gone, and
 nothing that is already verified may run after it.
@@ -29,7 +29,6 @@ def gold(golden_dir):
 
 # ------------------------------------------------------------------------------- region prompt control (verified kernels + torch)
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="region prompt control: first hardware run pending (kernels themselves are pinned elsewhere)")
 @pytest.mark.parametrize("case", REGION_CASES, ids=[c[0] for c in REGION_CASES])
 @pytest.mark.parametrize("method", ["md", "mod"])
 @pytest.mark.parametrize("dn", REGION_DTYPES)
@@ -42,7 +41,6 @@ def test_delegate_region_step_on_gpu(gold, case, method, dn):
 
 # ------------------------------------------------------------------------------- ControlNet tile caches (scatter on the x8 plan)
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="ControlNet / StableSR tile caches: first hardware run pending")
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
 def test_controlnet_tile_caches_on_gpu_equal_plain_slicing(dtype):
     from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
@@ -74,7 +72,6 @@ STRIP = 128
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="strip blend (TD_FLAG_STRIP): first hardware run pending; host emulation in test_strip_emulation.py")
 @pytest.mark.parametrize("dn", list(DTYPES))
 @pytest.mark.parametrize("use_rcp", [False, True])
 @pytest.mark.parametrize("STRIP", [128, 128 | 64], ids=["two_planes", "one_plane"])
@@ -99,7 +96,6 @@ def test_strip_blend_matches_reference_fixtures_on_gpu(golden_dir, dn, use_rcp, 
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="strip Mixture of Diffusers (TD_FLAG_STRIP): first hardware run pending; host emulation in test_strip_emulation.py")
 @pytest.mark.parametrize("dn", list(DTYPES))
 def test_strip_mixture_matches_reference_fixtures_on_gpu(golden_dir, dn):
     from multidiffusion_upscaler_for_automatic1111_b200 import engine
@@ -121,7 +117,6 @@ def test_strip_mixture_matches_reference_fixtures_on_gpu(golden_dir, dn):
 
 # ------------------------------------------------------------------------------- DemoFusion random jitter (new kernels: last)
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="DemoFusion random jitter: first hardware run pending")
 @pytest.mark.parametrize("dn,mixture", [("f32", True), ("f16", False), ("f16", True)])
 def test_demofusion_jitter_class_matches_oracle(dn, mixture):
     from oracle.make_golden import position_aware_denoise
@@ -147,7 +142,6 @@ def test_demofusion_jitter_class_matches_oracle(dn, mixture):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="list-driven scatter / blend: first hardware run pending")
 @pytest.mark.parametrize("dn", list(DTYPES))
 def test_window_list_scatter_and_blend_are_exact(dn):
     """td_scatter_bboxes == slicing + cat; td_blend_bboxes == the eager per-window add / count / divide, bit for bit."""
@@ -188,7 +182,6 @@ def test_window_list_scatter_and_blend_are_exact(dn):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="offset combine: first hardware run pending")
 def test_combine_with_offset_is_exact():
     import ctypes
     from multidiffusion_upscaler_for_automatic1111_b200._cabi import check, current_stream_ptr, lib

@@ -310,7 +310,6 @@ def _gpu_mod_worker(rank, world, port, result_dir):
 
 # first hardware run pending (written after the round-1 GPU budget was spent)
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="sharded Mixture of Diffusers: first hardware run pending")
 def test_two_gpu_sharded_mixture_bit_identical(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
@@ -358,7 +357,6 @@ def _gpu_demofusion_worker(rank, world, port, result_dir):
 
 # first hardware run pending (written after the round-1 GPU budget was spent)
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="sharded DemoFusion: first hardware run pending")
 def test_two_gpu_sharded_demofusion_matches_oracle(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
