@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TD_ABI_VERSION 2
+#define TD_ABI_VERSION 3
 
 typedef enum td_status {
     TD_OK = 0,
@@ -280,6 +280,56 @@ int td_demofusion_combine_offset(const void* x_local, const void* const* view_ba
  * accumulate, result rounded to dtype.  kernel_host: k*k fp32 values (already rounded through dtype). */
 int td_depthwise_conv2d(const void* in, void* out, int planes, int H, int W, const float* kernel_host,
                         int k, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ *  Tiled-VAE dense contractions on the tensor cores (tcgen05.mma, fp32 accumulators in TMEM).
+ *  The reference executes its conv / attention tasks at scripts/tilevae.py:618 through third-party
+ *  ldm modules (queue built at :107-204; attention tile_utils/attn.py:49-72).
+ * ------------------------------------------------------------------------- */
+
+/* One convolution (or GEMM) over NHWC activations:
+ *   y[n, oy, ox, co] = alpha * sum_{ky, kx, ci} x[n, oy*stride + ky - pad_top, ox*stride + kx - pad_left, ci] * w[ky*kw + kx][co][ci]
+ *                      + bias (+ residual[n, oy, ox, co])
+ * out-of-range input pixels read as zero (the conv's zero padding; pad(0,1,0,1) + stride 2 is pad_top = pad_left = 0).
+ * x: [N, H, W, x_pitch >= Cin], w: [kh*kw][Cout][w_pitch >= Cin], y / residual: [N, OH, OW, pitch >= Cout]; fp16 or bf16;
+ * Cin % 64 == 0 (zero-pad narrower inputs), pitches in elements and multiples of 8; fp32 accumulation.
+ * bias: fp32 [Cout] (bias_per_row = 0) or fp32 [N*OH*OW] (bias_per_row = 1: per output pixel = per GEMM row), or NULL.
+ * A GEMM D[M, Nc] = A[M, K] B[Nc, K]^T is N = H = OH = 1, W = OW = M, Cin = K, Cout = Nc, kh = kw = 1. */
+typedef struct td_conv_desc {
+    int32_t N, H, W, Cin, Cout;
+    int32_t kh, kw, stride, pad_top, pad_left;
+    int32_t OH, OW;
+    int32_t dtype;          /* TD_F16 or TD_BF16 */
+    int32_t bias_per_row;
+    float alpha;
+    int64_t x_pitch, w_pitch, y_pitch, res_pitch;
+} td_conv_desc;
+int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
+                   void* y, void* stream);
+
+/* Channels-last (NHWC) streaming kernels around the tensor-core convolutions (csrc/td_nhwc.cu).  fp16 / bf16.
+ *
+ * td_nchw_to_nhwc: tile crop (tilevae.py:532-535) + layout change + channel zero-padding:
+ *   y[n, i, j, c] = c < C ? x[n*x_img_stride + c*x_plane_stride + i*x_pitch + j] : 0,  y: [N, rows, cols, Cpad] contiguous.
+ * td_nhwc_to_nchw_region: crop_valid_region + paste (tilevae.py:248-259, :632) + layout change back:
+ *   y[n*y_img_stride + c*y_plane_stride + i*y_pitch + j] = x[n*x_img_stride + (i*x_width + j)*x_pitch + c], c < C
+ *   (x / y already offset to the region origins; strides and pitches in elements).
+ * td_upsample2x_nhwc: F.interpolate(scale_factor=2, mode="nearest") of ldm's Upsample ('upsample' task, tilevae.py:163).
+ * td_gn_stats_nhwc: get_var_mean (tilevae.py:207-215) of ONE image x: [pixels, C]; mean / var: fp32 [groups], biased.
+ * td_gn_apply_nhwc: custom_group_norm (+ SiLU when act = 1) (tilevae.py:218-245, :102-104); y may alias x.
+ * td_softmax_rows: y[r, :cols] = softmax(x[r, :cols]) (tile_utils/attn.py:58-60), y[r, cols:pitch] = 0. */
+int td_nchw_to_nhwc(const void* x, void* y, int N, int C, int rows, int cols, int64_t x_img_stride,
+                    int64_t x_plane_stride, int64_t x_pitch, int Cpad, int dtype, void* stream);
+int td_nhwc_to_nchw_region(const void* x, void* y, int N, int C, int rows, int cols, int64_t x_img_stride,
+                           int x_width, int64_t x_pitch, int64_t y_img_stride, int64_t y_plane_stride,
+                           int64_t y_pitch, int dtype, void* stream);
+int td_upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream);
+int64_t td_gn_stats_nhwc_workspace_bytes(int64_t pixels, int C, int groups);
+int td_gn_stats_nhwc(const void* x, int64_t pixels, int C, int groups, int dtype, void* workspace,
+                     int64_t workspace_bytes, float* mean, float* var, void* stream);
+int td_gn_apply_nhwc(const void* x, void* y, int64_t pixels, int C, int groups, int dtype, const float* mean,
+                     const float* var, const float* gamma, const float* beta, float eps, int act, void* stream);
+int td_softmax_rows(const void* x, void* y, int rows, int cols, int64_t pitch, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -32,7 +32,7 @@ TD_MAX_GRID_DIM = 256
 TD_MAX_BATCH_PTRS = 128
 TD_MAX_PEERS = 16
 TD_IPC_HANDLE_BYTES = 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 DTYPE_CODE = {torch.float16: TD_F16, torch.bfloat16: TD_BF16, torch.float32: TD_F32}
 
@@ -53,6 +53,17 @@ class TdGrid(ctypes.Structure):
         ("num_tiles", c_int32), ("num_batches", c_int32), ("tile_bs", c_int32),
         ("ys", c_int32 * TD_MAX_GRID_DIM),
         ("xs", c_int32 * TD_MAX_GRID_DIM),
+    ]
+
+
+class TdConvDesc(ctypes.Structure):
+    """struct td_conv_desc (include/td_b200.h)."""
+    _fields_ = [
+        ("N", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32),
+        ("kh", c_int32), ("kw", c_int32), ("stride", c_int32), ("pad_top", c_int32), ("pad_left", c_int32),
+        ("OH", c_int32), ("OW", c_int32), ("dtype", c_int32), ("bias_per_row", c_int32),
+        ("alpha", c_float),
+        ("x_pitch", c_int64), ("w_pitch", c_int64), ("y_pitch", c_int64), ("res_pitch", c_int64),
     ]
 
 
@@ -101,6 +112,16 @@ _SIGNATURES = {
     "td_demofusion_combine_offset": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                              c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
     "td_depthwise_conv2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_float), c_int, c_int, c_void_p]),
+    "td_conv2d_nhwc": (c_int, [POINTER(TdConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "td_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "td_nhwc_to_nchw_region": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int, c_int64, c_int64, c_int64, c_int64,
+                                       c_int, c_void_p]),
+    "td_upsample2x_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "td_gn_stats_nhwc_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
+    "td_gn_stats_nhwc": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "td_gn_apply_nhwc": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int,
+                                 c_void_p]),
+    "td_softmax_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p]),
     "td_blend_mixture": (c_int, [POINTER(TdGrid), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
 }

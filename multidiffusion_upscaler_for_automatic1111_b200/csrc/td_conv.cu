@@ -1,0 +1,468 @@
+// Tiled-VAE convolutions and attention GEMMs on the 5th-generation tensor cores (sm_100a):
+//   the conv / upsample / downsample / attention tasks the reference executes at scripts/tilevae.py:618 through
+//   third-party ldm modules (3x3 s1 p1 convs, 1x1 nin_shortcut / q / k / v / proj_out, nearest x2 + conv,
+//   pad(0,1,0,1) + 3x3 s2 conv; tile_utils/attn.py:49-72 QK^T and PV) as ONE implicit-GEMM kernel:
+//
+//       D[pixel, co] = alpha * sum_{tap, ci} A[pixel + offset(tap), ci] * W[tap][co][ci]  + bias  (+ residual)
+//
+// Design (B200-first):
+//   * activations NHWC fp16 / bf16 (channels innermost): a 3x3 tap is a shifted 4-D TMA box {64 ch, BW, BH, 1} of the
+//     SAME tensor -- signed start coordinates, out-of-bounds rows / columns zero-filled by the TMA unit = the
+//     convolution's zero padding, no im2col buffer, no halo handling in software.  BW x BH = 128 output pixels = the
+//     UMMA M dimension; a stride-2 convolution is the same box with element strides {1,2,2,1};
+//   * the box lands in shared memory as 128 rows x 128 bytes, 128-byte swizzled = the canonical K-major UMMA operand
+//     layout; weights [tap][Cout][Cin] load the same way ({64, BN, 1} boxes).  One elected thread issues
+//     tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BN <= 256, K = 16) four times per 64-channel stage;
+//   * fp32 accumulators live in TMEM (2 x BN columns: the epilogue of tile i overlaps the MMAs of tile i+1);
+//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
+//     (tcgen05.ld -> alpha / bias / residual -> fp16 -> swizzled smem -> TMA store, which also clips partial tiles);
+//   * persistent: one CTA per SM walks the (pixel tile, Cout block) list, 4-stage smem ring (mbarrier full / empty).
+// A plain GEMM (attention: S = Q K^T, O = P V, V^T = Wv X^T) is the 1x1 "image" with H = 1, W = M.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+
+#include "td_b200.h"
+#include "td_internal.h"
+#include "td_tma.cuh"
+
+namespace {
+
+using namespace td;
+
+constexpr int kConvThreads = 256;
+constexpr int kConvBM = 128;              // output pixels per tile = UMMA M
+constexpr int kConvBK = 64;               // channels per stage (128 bytes of fp16 = one swizzle row)
+constexpr int kConvStageA = kConvBM * kConvBK * 2;   // 16 KB
+constexpr int kConvStoreBuf = kConvBM * 128;         // 16 KB epilogue staging buffer (128 rows x 64 ch x 2 B)
+constexpr int kConvMaxStages = 8;
+
+struct ConvParams {
+    int taps_x, taps_y;        // kw, kh
+    int stride;                // 1 or 2
+    int pad_left, pad_top;
+    int OW, OH, NI;            // output image and batch
+    int Cin_chunks;            // Cin / 64
+    int Cout;                  // real output channels (bias / residual guard)
+    int BN;                    // Cout block = UMMA N (16..256, multiple of 16)
+    int n_blocks;              // ceil(Cout / BN)
+    int BW, BH;                // pixel patch (BW * BH == 128)
+    int tiles_x, tiles_y;
+    int num_tiles;             // NI * tiles_y * tiles_x * n_blocks
+    int stages;
+    int chunk_cols;            // columns per store chunk: min(64, BN)
+    int is_bf16;
+    int bias_per_row;          // bias indexed by output pixel (GEMM row) instead of channel
+    float alpha;
+    long long res_pitch;       // residual: elements between pixels (0: none)
+};
+
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %1;\n\t"
+        "@%%px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred) : "r"(0xffffffffu));
+    return pred;
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_u32(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers fp16 and bf16 inputs with fp32 accumulation
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns of this warp's TMEM lane quarter
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major): 16 B
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: fp32 accumulate, A / B both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc(int n, int is_bf16) {
+    uint32_t d = 0;
+    d |= 1u << 4;                           // D format: F32
+    d |= (is_bf16 ? 1u : 0u) << 7;          // A format
+    d |= (is_bf16 ? 1u : 0u) << 10;         // B format
+    d |= (uint32_t)(n >> 3) << 17;          // N / 8
+    d |= (uint32_t)(kConvBM >> 4) << 24;    // M / 16
+    return d;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int is_bf16) {
+    if (is_bf16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float unpack_lo(uint32_t w, int is_bf16) {
+    return is_bf16 ? __uint_as_float(w << 16) : __half2float(__ushort_as_half((unsigned short)(w & 0xffffu)));
+}
+__device__ __forceinline__ float unpack_hi(uint32_t w, int is_bf16) {
+    return is_bf16 ? __uint_as_float(w & 0xffff0000u) : __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+}
+
+struct TileCoord { int img, py, px, nb; };
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
+    TileCoord c;
+    c.nb = t % p.n_blocks;
+    int m = t / p.n_blocks;
+    c.px = m % p.tiles_x; m /= p.tiles_x;
+    c.py = m % p.tiles_y;
+    c.img = m / p.tiles_y;
+    return c;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_d, const __grid_constant__ ConvParams p,
+                 const float* __restrict__ bias, const uint16_t* __restrict__ residual) {
+    extern __shared__ unsigned char conv_smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kConvMaxStages], empty_bar[kConvMaxStages], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+    const uint32_t smem0 = (smem_u32(conv_smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
+    const int stage_b = p.BN * 128;
+    const uint32_t stage_bytes = (uint32_t)(kConvStageA + stage_b);
+    const uint32_t store0 = smem0 + (uint32_t)p.stages * stage_bytes;       // two staging buffers for the TMA store
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_d);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    if (warp == 2) {   // TMEM: 512 columns = two accumulator stages of up to 256 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    const int ksteps = p.taps_x * p.taps_y * p.Cin_chunks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const TileCoord c = decode_tile(p, t);
+                const int x0 = c.px * p.BW * p.stride - p.pad_left, y0 = c.py * p.BH * p.stride - p.pad_top;
+                int tap = 0;
+                for (int ty = 0; ty < p.taps_y; ++ty)
+                    for (int tx = 0; tx < p.taps_x; ++tx, ++tap)
+                        for (int kc = 0; kc < p.Cin_chunks; ++kc) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1u);
+                            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+                            const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
+                            tma_load_4d(sa, &map_a, kc * kConvBK, x0 + tx, y0 + ty, c.img, &full_bar[stage]);
+                            tma_load_3d_u32(sa + kConvStageA, &map_b, kc * kConvBK, c.nb * p.BN, tap, &full_bar[stage]);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc(p.BN, p.is_bf16);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                mbar_wait(&acc_empty[as], aphase ^ 1u);              // epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
+                    const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + kConvStageA);
+#pragma unroll
+                    for (int k = 0; k < kConvBK / 16; ++k)          // +32 bytes along K inside the swizzle row = +2 in the address field
+                        tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+                    tc_commit(&empty_bar[stage]);                     // frees the smem stage when these MMAs have read it
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit(&acc_full[as]);                             // accumulator complete -> epilogue
+                if (++as == 2) { as = 0; aphase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: TMEM -> registers -> smem -> TMA store =====================
+        const int q = warp & 3;                       // TMEM lane quarter of this warp
+        const int row = q * 32 + lane;                // accumulator row = pixel index inside the tile
+        const int et = threadIdx.x - 128;             // 0..127
+        const int ly = row / p.BW, lx = row - ly * p.BW;
+        int as = 0; uint32_t aphase = 0;
+        int buf = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            const TileCoord c = decode_tile(p, t);
+            const int ox = c.px * p.BW + lx, oy = c.py * p.BH + ly;
+            const bool pix_ok = ox < p.OW && oy < p.OH;
+            const long long pix = ((long long)c.img * p.OH + oy) * p.OW + ox;
+            mbar_wait(&acc_full[as], aphase);
+            tc_fence_after();
+            const int nchunks = p.BN / p.chunk_cols;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int col0 = c.nb * p.BN + ch * p.chunk_cols;
+                // the staging buffer about to be overwritten must have been read by its previous TMA store
+                if (et == 0) bulk_wait_read<1>();
+                named_bar_sync(1, 128);
+                const uint32_t sbuf = store0 + (uint32_t)buf * kConvStoreBuf;
+                for (int g = 0; g < p.chunk_cols / 16; ++g) {
+                    uint32_t r[16];
+                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + ch * p.chunk_cols + g * 16), r);
+                    tc_wait_ld();
+                    float v[16];
+                    const int cb = col0 + g * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float b = 0.0f;
+                        if (bias != nullptr) {
+                            if (p.bias_per_row) b = pix_ok ? __ldg(bias + pix) : 0.0f;
+                            else b = (cb + j < p.Cout) ? __ldg(bias + cb + j) : 0.0f;
+                        }
+                        v[j] = __fmaf_rn(__uint_as_float(r[j]), p.alpha, b);
+                    }
+                    if (residual != nullptr && pix_ok && cb + 16 <= p.Cout) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(residual + pix * p.res_pitch + cb);
+                        const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            v[2 * j] += unpack_lo(rw[j], p.is_bf16);
+                            v[2 * j + 1] += unpack_hi(rw[j], p.is_bf16);
+                        }
+                    }
+                    uint32_t o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = pack2(v[2 * j], v[2 * j + 1], p.is_bf16);
+                    // 16 columns = two 16-byte chunks (2g, 2g+1) of this row
+                    if (p.chunk_cols == 64) {      // 128-byte rows, 128-byte swizzle: chunk index XOR (row & 7)
+                        const uint32_t rb = sbuf + (uint32_t)row * 128u;
+                        const uint32_t c0 = (uint32_t)((2 * g) ^ (row & 7)) << 4, c1 = (uint32_t)((2 * g + 1) ^ (row & 7)) << 4;
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb + c0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb + c1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+                    } else {                       // narrow outputs: dense rows of chunk_cols * 2 bytes, no swizzle
+                        const uint32_t rb = sbuf + (uint32_t)row * (uint32_t)(p.chunk_cols * 2) + (uint32_t)g * 32u;
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb + 16u), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+                    }
+                }
+                if (ch == nchunks - 1) {           // every TMEM read of this accumulator stage is done: hand it back
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[as]);
+                }
+                fence_proxy_async();
+                named_bar_sync(1, 128);
+                if (et == 0) {
+                    tma_store_4d(&map_d, col0, c.px * p.BW, c.py * p.BH, c.img, sbuf);
+                    bulk_commit();
+                }
+                buf ^= 1;
+            }
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+        if (et == 0) bulk_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn conv_encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return (EncodeTiledFn) nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+int encode_map(CUtensorMap* out, const void* base, int is_bf16, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, const uint32_t* estr, bool swizzle128, const char* what) {
+    EncodeTiledFn fn = conv_encode_fn();
+    if (fn == nullptr) { td_set_error("cuTensorMapEncodeTiled is not available from this driver"); return TD_ERR_CUDA; }
+    cuuint64_t d[5]; cuuint64_t s[4]; cuuint32_t b[5]; cuuint32_t e[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = estr[i]; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    const CUresult r = fn(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+                          const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        td_set_error("cuTensorMapEncodeTiled failed (%d) for %s: dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", (int)r, what,
+                     (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                     (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+        return TD_ERR_CUDA;
+    }
+    return TD_OK;
+}
+
+struct ConvDev { int sms; int smem_optin; bool ok; };
+ConvDev conv_dev() {
+    static std::mutex mu;
+    static ConvDev cache[64];
+    static bool have[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return {0, 0, false};
+    std::lock_guard<std::mutex> lk(mu);
+    if (!have[dev]) {
+        ConvDev d{0, 0, false};
+        d.ok = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+               cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess;
+        if (d.ok && cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin) != cudaSuccess) {
+            cudaGetLastError();
+            d.ok = false;
+        }
+        cache[dev] = d;
+        have[dev] = true;
+    }
+    return cache[dev];
+}
+
+}  // namespace
+
+extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
+                              void* y, void* stream) {
+    if (d == nullptr || x == nullptr || w == nullptr || y == nullptr) { td_set_error("td_conv2d_nhwc: null argument"); return TD_ERR_INVALID_ARG; }
+    if (d->dtype != TD_F16 && d->dtype != TD_BF16) { td_set_error("td_conv2d_nhwc: dtype must be fp16 or bf16"); return TD_ERR_UNSUPPORTED; }
+    if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->OH <= 0 || d->OW <= 0 || d->Cin <= 0 || d->Cout <= 0) { td_set_error("td_conv2d_nhwc: non-positive size"); return TD_ERR_INVALID_ARG; }
+    if (d->Cin % 64 != 0) { td_set_error("td_conv2d_nhwc: Cin (%d) must be a multiple of 64 (zero-pad the channels)", d->Cin); return TD_ERR_UNSUPPORTED; }
+    if ((d->kh != 1 && d->kh != 3) || d->kh != d->kw || (d->stride != 1 && d->stride != 2)) { td_set_error("td_conv2d_nhwc: only 1x1 / 3x3, stride 1 / 2"); return TD_ERR_UNSUPPORTED; }
+    if (d->x_pitch < d->Cin || d->x_pitch % 8 != 0 || d->y_pitch < d->Cout || d->y_pitch % 8 != 0 || d->w_pitch < d->Cin || d->w_pitch % 8 != 0 ||
+        (residual != nullptr && (d->res_pitch < d->Cout || d->res_pitch % 8 != 0))) {
+        td_set_error("td_conv2d_nhwc: pitches must cover the channels and be multiples of 8 elements (16 bytes)");
+        return TD_ERR_INVALID_ARG;
+    }
+    for (const void* ptr : {x, w, (const void*)y, residual})
+        if (ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15u) != 0) { td_set_error("td_conv2d_nhwc: tensors must be 16-byte aligned"); return TD_ERR_INVALID_ARG; }
+    const ConvDev dev = conv_dev();
+    if (!dev.ok) { td_set_error("td_conv2d_nhwc: device query / shared-memory opt-in failed"); return TD_ERR_CUDA; }
+
+    ConvParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.taps_x = d->kw; p.taps_y = d->kh; p.stride = d->stride; p.pad_left = d->pad_left; p.pad_top = d->pad_top;
+    p.OW = d->OW; p.OH = d->OH; p.NI = d->N;
+    p.Cin_chunks = d->Cin / 64;
+    p.Cout = d->Cout;
+    int bn = 256;
+    if (d->Cout < 256) { bn = 16; while (bn < d->Cout) bn *= 2; }
+    p.BN = bn;
+    p.n_blocks = (d->Cout + bn - 1) / bn;
+    // pixel patch: wide for a GEMM (H == 1), 16 x 8 for images
+    if (d->OH == 1) { p.BW = 128; p.BH = 1; }
+    else if (d->OW >= 16) { p.BW = 16; p.BH = 8; }
+    else { p.BW = 8; p.BH = 16; }
+    p.tiles_x = (d->OW + p.BW - 1) / p.BW;
+    p.tiles_y = (d->OH + p.BH - 1) / p.BH;
+    const long long nt = (long long)d->N * p.tiles_x * p.tiles_y * p.n_blocks;
+    if (nt > 0x7fffffffLL) { td_set_error("td_conv2d_nhwc: too many tiles"); return TD_ERR_UNSUPPORTED; }
+    p.num_tiles = (int)nt;
+    p.chunk_cols = std::min(64, bn);
+    p.is_bf16 = d->dtype == TD_BF16;
+    p.bias_per_row = d->bias_per_row;
+    p.alpha = d->alpha;
+    p.res_pitch = residual != nullptr ? d->res_pitch : 0;
+    const int stage_bytes = kConvStageA + bn * 128;
+    const int avail = dev.smem_optin - 1024 - 2 * kConvStoreBuf;
+    p.stages = std::min(kConvMaxStages, avail / stage_bytes);
+    if (p.stages < 2) { td_set_error("td_conv2d_nhwc: not enough shared memory"); return TD_ERR_UNSUPPORTED; }
+    const size_t smem = (size_t)p.stages * stage_bytes + 2 * kConvStoreBuf + 1024;
+
+    alignas(64) CUtensorMap ma, mb, md;
+    {
+        const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+        const uint64_t str[3] = {(uint64_t)d->x_pitch * 2, (uint64_t)d->W * d->x_pitch * 2, (uint64_t)d->H * d->W * d->x_pitch * 2};
+        const uint32_t box[4] = {64, (uint32_t)(p.BW * d->stride), (uint32_t)(p.BH * d->stride), 1};
+        const uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
+        const int rc = encode_map(&ma, x, p.is_bf16, 4, dims, str, box, es, true, "activations");
+        if (rc != TD_OK) return rc;
+    }
+    {
+        const uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout, (uint64_t)(d->kh * d->kw)};
+        const uint64_t str[2] = {(uint64_t)d->w_pitch * 2, (uint64_t)d->Cout * d->w_pitch * 2};
+        const uint32_t box[3] = {64, (uint32_t)bn, 1};
+        const uint32_t es[3] = {1, 1, 1};
+        const int rc = encode_map(&mb, w, p.is_bf16, 3, dims, str, box, es, true, "weights");
+        if (rc != TD_OK) return rc;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->OW, (uint64_t)d->OH, (uint64_t)d->N};
+        const uint64_t str[3] = {(uint64_t)d->y_pitch * 2, (uint64_t)d->OW * d->y_pitch * 2, (uint64_t)d->OH * d->OW * d->y_pitch * 2};
+        const uint32_t box[4] = {(uint32_t)p.chunk_cols, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+        const uint32_t es[4] = {1, 1, 1, 1};
+        const int rc = encode_map(&md, y, p.is_bf16, 4, dims, str, box, es, p.chunk_cols == 64, "output");
+        if (rc != TD_OK) return rc;
+    }
+    const int grid = std::min(p.num_tiles, dev.sms);
+    conv_gemm_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(ma, mb, md, p, bias, (const uint16_t*)residual);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { td_set_error("td_conv2d_nhwc: launch failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+    return TD_OK;
+}

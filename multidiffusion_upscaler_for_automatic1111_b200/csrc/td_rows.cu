@@ -168,6 +168,19 @@ __device__ __forceinline__ uint4 rows_tile_window(const unsigned char* row, int 
     return Vec<T>::window(A, B, s);
 }
 
+// Per-lane-divergent table reads must not go through the constant bank (a divergent LDC replays per distinct address):
+// the consumers read the tile-column origins and the per-vector column ranges from shared memory.
+struct RowsTables {
+    short xs[TD_MAX_GRID_DIM];
+    short ys[TD_MAX_GRID_DIM];
+    unsigned char vcol_lo[kRowsMaxVec], vcol_n[kRowsMaxVec];
+};
+__device__ __forceinline__ void rows_load_tables(const RowsParams& p, RowsTables& t) {
+    for (int i = threadIdx.x; i < p.cols; i += blockDim.x) t.xs[i] = p.xs[i];
+    for (int i = threadIdx.x; i < p.rows; i += blockDim.x) t.ys[i] = p.ys[i];
+    for (int i = threadIdx.x; i < p.wv; i += blockDim.x) { t.vcol_lo[i] = p.vcol_lo[i]; t.vcol_n[i] = p.vcol_n[i]; }
+}
+
 struct RowsCommon {
     int u_begin, u_end;
 };
@@ -190,6 +203,7 @@ blend_rows_md_kernel(const __grid_constant__ RowsParams p, const float* __restri
     extern __shared__ __align__(128) unsigned char rows_smem[];
     __shared__ __align__(8) uint64_t full[kRowsMaxSlots];
     __shared__ SegTable segs[kRowsMaxSlots];
+    __shared__ RowsTables tb;
     const int tid = threadIdx.x;
     const RowsCommon c = rows_partition(p);
     const int n = c.u_end - c.u_begin;
@@ -198,6 +212,7 @@ blend_rows_md_kernel(const __grid_constant__ RowsParams p, const float* __restri
         fence_mbar_init();
         fence_proxy_async();
     }
+    rows_load_tables(p, tb);
     __syncthreads();
     rows_pdl_launch_dependents();
     rows_pdl_wait();
@@ -248,14 +263,14 @@ blend_rows_md_kernel(const __grid_constant__ RowsParams p, const float* __restri
                 }
             }
             uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-            const int jlo = p.vcol_lo[xv], jn = p.vcol_n[xv];
+            const int jlo = tb.vcol_lo[xv], jn = tb.vcol_n[xv];
             for (int q = 0; q < sg.nseg; ++q) {
                 const int rr = y - sg.yy0[q];
                 if ((unsigned)rr >= (unsigned)sg.nr[q]) continue;
                 const unsigned char* seg = sbase + sg.off[q];
                 const int nr = sg.nr[q];
                 for (int j = jlo; j < jlo + jn; ++j) {
-                    const uint4 e = rows_tile_window<T>(seg + (size_t)(j * nr + rr) * row_bytes, x0 - (int)p.xs[j], p.tw);
+                    const uint4 e = rows_tile_window<T>(seg + (size_t)(j * nr + rr) * row_bytes, x0 - (int)tb.xs[j], p.tw);
                     acc.x = rows_packed_add<T>(acc.x, e.x);
                     acc.y = rows_packed_add<T>(acc.y, e.y);
                     acc.z = rows_packed_add<T>(acc.z, e.z);
@@ -295,6 +310,7 @@ blend_rows_mod_kernel(const __grid_constant__ RowsParams p, const float* __restr
     __shared__ __align__(8) uint64_t full[kRowsMaxSlots];
     __shared__ __align__(8) uint64_t aux_full;
     __shared__ SegTable segs[kRowsMaxSlots];
+    __shared__ RowsTables tb;
     const int tid = threadIdx.x;
     const RowsCommon c = rows_partition(p);
     const int n = c.u_end - c.u_begin;
@@ -306,6 +322,7 @@ blend_rows_mod_kernel(const __grid_constant__ RowsParams p, const float* __restr
         fence_mbar_init();
         fence_proxy_async();
     }
+    rows_load_tables(p, tb);
     __syncthreads();
     rows_pdl_launch_dependents();
     rows_pdl_wait();
@@ -358,16 +375,16 @@ blend_rows_mod_kernel(const __grid_constant__ RowsParams p, const float* __restr
             float acc[VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j) acc[j] = 0.0f;
-            const int jlo = p.vcol_lo[xv], jn = p.vcol_n[xv];
+            const int jlo = tb.vcol_lo[xv], jn = tb.vcol_n[xv];
             for (int q = 0; q < sg.nseg; ++q) {
                 const int rr = y - sg.yy0[q];
                 if ((unsigned)rr >= (unsigned)sg.nr[q]) continue;
                 const unsigned char* seg = sbase + sg.off[q];
                 const int nr = sg.nr[q];
-                const int v = y - (int)p.ys[sg.band[q]];                  // tile row
+                const int v = y - (int)tb.ys[sg.band[q]];                  // tile row
                 const float* wrow = s_tw + (size_t)v * p.tw;
                 for (int j = jlo; j < jlo + jn; ++j) {
-                    const int u0 = x0 - (int)p.xs[j];
+                    const int u0 = x0 - (int)tb.xs[j];
                     const uint4 e = rows_tile_window<T>(seg + (size_t)(j * nr + rr) * row_bytes, u0, p.tw);
 #pragma unroll
                     for (int m = 0; m < VEC; ++m) {
@@ -410,6 +427,7 @@ scatter_rows_kernel(const __grid_constant__ RowsParams p, const T* __restrict__ 
     extern __shared__ __align__(128) unsigned char rows_smem[];
     __shared__ __align__(8) uint64_t full[kRowsMaxSlots];
     __shared__ SegTable segs[kRowsMaxSlots];
+    __shared__ RowsTables tb;
     const int tid = threadIdx.x;
     const RowsCommon c = rows_partition(p);
     const int n = c.u_end - c.u_begin;
@@ -418,6 +436,7 @@ scatter_rows_kernel(const __grid_constant__ RowsParams p, const T* __restrict__ 
         fence_mbar_init();
         fence_proxy_async();
     }
+    rows_load_tables(p, tb);
     __syncthreads();
     rows_pdl_launch_dependents();
     rows_pdl_wait();
@@ -439,13 +458,13 @@ scatter_rows_kernel(const __grid_constant__ RowsParams p, const T* __restrict__ 
                 const int rr = rem / p.twv, uv = rem - rr * p.twv;
                 const int t = i * p.cols + j;
                 if (t < p.tile_begin || t >= p.tile_end) continue;
-                const int y = yy0 + rr, xx = (int)p.xs[j] + uv * VEC;
+                const int y = yy0 + rr, xx = (int)tb.xs[j] + uv * VEC;
                 const unsigned char* row = sbase + (size_t)(y - y0) * crow_bytes;
                 const int a = xx & ~(VEC - 1), s = xx - a;
                 const uint4 A = lds128(row + a * (int)sizeof(T));
                 uint4 e = A;
                 if (s != 0) e = Vec<T>::window(A, lds128(row + (a + VEC) * (int)sizeof(T)), s);   // xx + VEC <= W: the next chunk exists
-                T* dst = tiles + ((long long)(t - p.tile_begin) * p.NC + plane) * ((long long)p.th * p.tw) + (long long)(y - (int)p.ys[i]) * p.tw + uv * VEC;
+                T* dst = tiles + ((long long)(t - p.tile_begin) * p.NC + plane) * ((long long)p.th * p.tw) + (long long)(y - (int)tb.ys[i]) * p.tw + uv * VEC;
                 stg128_stream(dst, e);
             }
         }
@@ -475,19 +494,23 @@ DevInfo dev_info() {
     return cache[dev];
 }
 
-template <typename KernelT>
-bool rows_smem_optin(KernelT kernel, int bytes) {
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per kernel and per device: cache keyed by the kernel's address
+// (several instantiations share one function-pointer TYPE, so a per-template static would alias them).
+bool rows_smem_optin(const void* kernel, int bytes) {
     static std::mutex mu;
-    static int granted[64] = {};
+    struct Entry { const void* fn; int dev; };
+    static Entry done[64];
+    static int ndone = 0;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
     std::lock_guard<std::mutex> lk(mu);
-    if (granted[dev] >= bytes) return true;
+    for (int i = 0; i < ndone; ++i)
+        if (done[i].fn == kernel && done[i].dev == dev) return true;
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
-    granted[dev] = bytes;
+    if (ndone < 64) done[ndone++] = Entry{kernel, dev};
     return true;
 }
 
@@ -612,7 +635,7 @@ int rows_launch_md(const RowsParams& p, int grid, const float* weights, const fl
     cudaError_t e;
 #define TD_ROWS_MD(WB, FD)                                                                                                    \
     do {                                                                                                                      \
-        if (!rows_smem_optin(blend_rows_md_kernel<T, WB, FD>, kRowsSmemBudget)) return 1;                                     \
+        if (!rows_smem_optin((const void*)blend_rows_md_kernel<T, WB, FD>, kRowsSmemBudget)) return 1;                                     \
         e = rows_launch(blend_rows_md_kernel<T, WB, FD>, grid, smem, pdl, st, p, weights, rcp, x_out, (T*)x_buffer);         \
     } while (0)
     const bool fd = rcp != nullptr && sizeof(T) == 2;
@@ -625,7 +648,7 @@ int rows_launch_md(const RowsParams& p, int grid, const float* weights, const fl
 template <typename T>
 int rows_launch_mod(const RowsParams& p, int grid, const float* tile_weights, const float* rescale, void* x_buffer, bool pdl, cudaStream_t st) {
     const size_t smem = (size_t)p.aux_bytes + (size_t)p.nslots * p.slot_bytes;
-    if (!rows_smem_optin(blend_rows_mod_kernel<T>, kRowsSmemBudget)) return 1;
+    if (!rows_smem_optin((const void*)blend_rows_mod_kernel<T>, kRowsSmemBudget)) return 1;
     return rows_check(rows_launch(blend_rows_mod_kernel<T>, grid, smem, pdl, st, p, tile_weights, rescale, (T*)x_buffer),
                       "td_blend_mixture (row-block form)");
 }
@@ -633,7 +656,7 @@ int rows_launch_mod(const RowsParams& p, int grid, const float* tile_weights, co
 template <typename T>
 int rows_launch_scatter(const RowsParams& p, int grid, const void* x, void* tiles, bool pdl, cudaStream_t st) {
     const size_t smem = (size_t)p.nslots * p.slot_bytes;
-    if (!rows_smem_optin(scatter_rows_kernel<T>, kRowsSmemBudget)) return 1;
+    if (!rows_smem_optin((const void*)scatter_rows_kernel<T>, kRowsSmemBudget)) return 1;
     return rows_check(rows_launch(scatter_rows_kernel<T>, grid, smem, pdl, st, p, (const T*)x, (T*)tiles), "td_scatter_tiles (row-block form)");
 }
 
