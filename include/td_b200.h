@@ -292,7 +292,8 @@ int td_depthwise_conv2d(const void* in, void* out, int planes, int H, int W, con
  *                      + bias (+ residual[n, oy, ox, co])
  * out-of-range input pixels read as zero (the conv's zero padding; pad(0,1,0,1) + stride 2 is pad_top = pad_left = 0).
  * x: [N, H, W, x_pitch >= Cin], w: [kh*kw][Cout][w_pitch >= Cin], y / residual: [N, OH, OW, pitch >= Cout]; fp16 or bf16;
- * Cin % 64 == 0 (zero-pad narrower inputs), pitches in elements and multiples of 8; fp32 accumulation.
+ * Cin % 8 == 0 (zero-pad narrower inputs; K is walked in chunks of 64, a partial last chunk reads zeros), pitches in
+ * elements and multiples of 8; fp32 accumulation.
  * bias: fp32 [Cout] (bias_per_row = 0) or fp32 [N*OH*OW] (bias_per_row = 1: per output pixel = per GEMM row), or NULL.
  * A GEMM D[M, Nc] = A[M, K] B[Nc, K]^T is N = H = OH = 1, W = OW = M, Cin = K, Cout = Nc, kh = kw = 1. */
 typedef struct td_conv_desc {

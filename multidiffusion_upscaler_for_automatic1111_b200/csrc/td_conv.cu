@@ -48,7 +48,7 @@ struct ConvParams {
     int stride;                // 1 or 2
     int pad_left, pad_top;
     int OW, OH, NI;            // output image and batch
-    int Cin_chunks;            // Cin / 64
+    int Cin_chunks;            // ceil(Cin / 64)
     int Cout;                  // real output channels (bias / residual guard)
     int BN;                    // Cout block = UMMA N (16..256, multiple of 16)
     int n_blocks;              // ceil(Cout / BN)
@@ -376,9 +376,16 @@ ConvDev conv_dev() {
         ConvDev d{0, 0, false};
         d.ok = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
                cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess;
-        if (d.ok && cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin) != cudaSuccess) {
-            cudaGetLastError();
-            d.ok = false;
+        if (d.ok) {   // the opt-in limit covers static + dynamic shared memory: leave room for the kernel's static part
+            cudaFuncAttributes fa;
+            if (cudaFuncGetAttributes(&fa, conv_gemm_kernel) != cudaSuccess) { cudaGetLastError(); d.ok = false; }
+            else {
+                d.smem_optin -= (int)fa.sharedSizeBytes;
+                if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin) != cudaSuccess) {
+                    cudaGetLastError();
+                    d.ok = false;
+                }
+            }
         }
         cache[dev] = d;
         have[dev] = true;
@@ -393,7 +400,7 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     if (d == nullptr || x == nullptr || w == nullptr || y == nullptr) { td_set_error("td_conv2d_nhwc: null argument"); return TD_ERR_INVALID_ARG; }
     if (d->dtype != TD_F16 && d->dtype != TD_BF16) { td_set_error("td_conv2d_nhwc: dtype must be fp16 or bf16"); return TD_ERR_UNSUPPORTED; }
     if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->OH <= 0 || d->OW <= 0 || d->Cin <= 0 || d->Cout <= 0) { td_set_error("td_conv2d_nhwc: non-positive size"); return TD_ERR_INVALID_ARG; }
-    if (d->Cin % 64 != 0) { td_set_error("td_conv2d_nhwc: Cin (%d) must be a multiple of 64 (zero-pad the channels)", d->Cin); return TD_ERR_UNSUPPORTED; }
+    if (d->Cin % 8 != 0) { td_set_error("td_conv2d_nhwc: Cin (%d) must be a multiple of 8", d->Cin); return TD_ERR_UNSUPPORTED; }
     if ((d->kh != 1 && d->kh != 3) || d->kh != d->kw || (d->stride != 1 && d->stride != 2)) { td_set_error("td_conv2d_nhwc: only 1x1 / 3x3, stride 1 / 2"); return TD_ERR_UNSUPPORTED; }
     if (d->x_pitch < d->Cin || d->x_pitch % 8 != 0 || d->y_pitch < d->Cout || d->y_pitch % 8 != 0 || d->w_pitch < d->Cin || d->w_pitch % 8 != 0 ||
         (residual != nullptr && (d->res_pitch < d->Cout || d->res_pitch % 8 != 0))) {
@@ -409,7 +416,7 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     std::memset(&p, 0, sizeof(p));
     p.taps_x = d->kw; p.taps_y = d->kh; p.stride = d->stride; p.pad_left = d->pad_left; p.pad_top = d->pad_top;
     p.OW = d->OW; p.OH = d->OH; p.NI = d->N;
-    p.Cin_chunks = d->Cin / 64;
+    p.Cin_chunks = (d->Cin + 63) / 64;   // a partial last chunk is zero-filled by the TMA unit on BOTH operands
     p.Cout = d->Cout;
     int bn = 256;
     if (d->Cout < 256) { bn = 16; while (bn < d->Cout) bn *= 2; }

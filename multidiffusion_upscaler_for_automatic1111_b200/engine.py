@@ -110,12 +110,26 @@ def _batch_table(g: TdGrid, batch_outs: Sequence[torch.Tensor], N: int, C: int, 
     return ptrs, keep, dt
 
 
+def _fit_batch_table(g: TdGrid, batch_outs: Sequence[torch.Tensor], tile_bs: int):
+    """The kernels take at most TD_MAX_BATCH_PTRS output tensors per launch (pointers travel in the kernel parameter
+    block).  The reference accepts any batch count (e.g. 441 tiles with tile_bs 3 = 147 batches): concatenate groups of
+    k consecutive full batches into one tensor each and report the new tile_bs = k * tile_bs.  Tile order is unchanged."""
+    from ._cabi import TD_MAX_BATCH_PTRS
+    n = len(batch_outs)
+    if n <= TD_MAX_BATCH_PTRS:
+        return list(batch_outs), tile_bs
+    k = -(-n // TD_MAX_BATCH_PTRS)
+    merged = [torch.cat(list(batch_outs[i:i + k]), dim=0) for i in range(0, n, k)]
+    return merged, tile_bs * k
+
+
 def blend_multidiffusion(g: TdGrid, batch_outs: Sequence[torch.Tensor], N: int, C: int, tile_bs: int,
                          weights: torch.Tensor, acc_dtype: torch.dtype, x_buffer: Optional[torch.Tensor] = None,
                          flags: int = 0, out: Optional[torch.Tensor] = None, rcp_weights: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Fused multidiffusion.py:166-167 + :208.  Returns fp32 [N,C,H,W] (fresh unless `out` is given).
 
     rcp_weights (see `exact_reciprocals`) enables the 3-instruction exact divide for integer weights."""
+    batch_outs, tile_bs = _fit_batch_table(g, batch_outs, tile_bs)
     ptrs, keep, tdt = _batch_table(g, batch_outs, N, C, tile_bs)
     dev = keep[0].device
     x_out = out if out is not None else torch.empty((N, C, g.H, g.W), dtype=torch.float32, device=dev)
@@ -141,6 +155,7 @@ def exact_reciprocals(weights_host: np.ndarray) -> Optional[np.ndarray]:
 def blend_mixture(g: TdGrid, batch_outs: Sequence[torch.Tensor], N: int, C: int, tile_bs: int,
                   tile_weights: torch.Tensor, rescale: torch.Tensor, x_buffer: torch.Tensor, flags: int = 0) -> torch.Tensor:
     """mixtureofdiffusers.py:122-126; writes and returns x_buffer."""
+    batch_outs, tile_bs = _fit_batch_table(g, batch_outs, tile_bs)
     ptrs, keep, tdt = _batch_table(g, batch_outs, N, C, tile_bs)
     dev = keep[0].device
     with torch.cuda.device(dev):

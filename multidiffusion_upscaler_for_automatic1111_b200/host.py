@@ -161,3 +161,14 @@ def store_latent(x) -> None:
     m = _a1111("sd_samplers_common")
     if m is not None and hasattr(m, "store_latent"):
         m.store_latent(x)
+
+
+cheap_approximation = None   # a caller outside the WebUI may set this (latent [4,h,w] -> RGB [3,h,w])
+
+
+def get_cheap_approximation():
+    """modules.sd_vae_approx.cheap_approximation (tilevae.py:575), the override above, or None."""
+    if cheap_approximation is not None:
+        return cheap_approximation
+    m = _a1111("sd_vae_approx")
+    return getattr(m, "cheap_approximation", None) if m is not None else None

@@ -638,8 +638,10 @@ class AbstractDiffusion:
         dev = host.device()
         if t.device != dev:
             t = t.to(dev)
-        if max(self._grid.H, self._grid.W) * scale >= 32768:
-            # beyond the kernels' 16-bit tile origins (a 32k-pixel hint): plain slicing, same tile order
+        if max(self._grid.H, self._grid.W) * scale >= 32768 or tuple(t.shape[2:]) != (self._grid.H * scale, self._grid.W * scale) or not t.is_cuda:
+            # beyond the kernels' 16-bit tile origins (a 32k-pixel hint), or a hint whose size is not exactly the scaled
+            # canvas (p.width not a multiple of 8, hints resized by the extension: the reference's slicing tolerates
+            # both, abstractdiffusion.py:494-503): plain slicing, same tile order
             s = scale
             return torch.cat([t[:, :, b[1] * s:b[3] * s, b[0] * s:b[2] * s] for batch in self.batched_bboxes for b in batch], dim=0)
         g = self._grid if scale == 1 else engine.scaled_grid(self._grid, scale)

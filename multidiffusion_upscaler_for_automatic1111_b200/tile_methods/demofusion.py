@@ -55,8 +55,9 @@ class DemoFusion(AbstractDiffusion):
     def hook(self):
         """demofusion.py:21-35: replaces CFGDenoiser.forward; inner_model.forward is patched per call."""
         steps_fn = getattr(host._a1111("sd_samplers_common"), "setup_img2img_steps", None) if host._a1111("sd_samplers_common") else None
+        steps = getattr(self.p, "steps", None)
         if steps_fn is not None:
-            _, self.t_enc = steps_fn(self.p, None)
+            steps, self.t_enc = steps_fn(self.p, None)      # with opts.img2img_fix_steps the returned steps differ from p.steps
         else:
             self.t_enc = getattr(self.p, "t_enc", getattr(self.p, "steps", 1) - 1)
         cfg = self.sampler.model_wrap_cfg
@@ -64,7 +65,7 @@ class DemoFusion(AbstractDiffusion):
         self.sampler_forward = cfg.inner_model.forward
         cfg.forward = self.forward_one_step
         if not self.is_kdiff:
-            self.timesteps = self.sampler.get_timesteps(self.p, getattr(self.p, "steps", None))
+            self.timesteps = self.sampler.get_timesteps(self.p, steps)     # demofusion.py:22,35: the steps setup_img2img_steps returned
 
     @staticmethod
     def unhook():

@@ -14,7 +14,11 @@ What is different from the reference by design (180 GB of HBM, hand-written sm_1
     lossless round trip for fp16/bf16 tile outputs);
   * no per-tile NaN test (each one is a full read + host sync, tilevae.py:625): the result
     is checked once at the end and the estimator keeps its NaN fallback.
-The convolutions / attention GEMMs stay the host application's modules (cuDNN / SDPA).
+  * fp16 / bf16 networks run channels-last with every convolution and the attention GEMMs on the tensor cores
+    (tcgen05, csrc/td_conv.cu) through `vae_engine.TensorCoreBackend`; fp32 networks keep the host application's
+    modules for the dense ops (`vae_engine.ModuleBackend`).
+The network is compiled once into an op program (`vae_engine.compile_program`); GroupNorm sites are barriers between
+tiles unless fast mode froze their statistics.
 """
 from __future__ import annotations
 
@@ -163,152 +167,83 @@ def fast_mode_estimator_input(z: torch.Tensor, tile_size: int) -> torch.Tensor:
     return ds
 
 
-# --------------------------------------------------------------------------- task queue
-def inplace_nonlinearity(x):
-    return F.silu(x, inplace=True)
-
-
-def attn_forward(net, h_: torch.Tensor) -> torch.Tensor:
-    """VAE mid-block attention without norm / residual (tile_utils/attn.py:49-72): one
-    single-head softmax(QK^T / sqrt(C)) V + proj_out.  The reference's six back-end variants
-    are memory work-arounds of this same function."""
-    q, k, v = net.q(h_), net.k(h_), net.v(h_)
-    b, c, h, w = q.shape
-    q, k, v = (t.reshape(b, 1, c, h * w).transpose(2, 3) for t in (q, k, v))   # [b, 1, hw, c]
-    o = F.scaled_dot_product_attention(q, k, v)                                 # scale = c ** -0.5
-    return net.proj_out(o.transpose(2, 3).reshape(b, c, h, w))
-
-
-def attn2task(task_queue, net):
-    task_queue.append(('store_res', lambda x: x))
-    task_queue.append(('pre_norm', net.norm))
-    task_queue.append(('attn', lambda x, net=net: attn_forward(net, x)))
-    task_queue.append(['add_res', None])
-
-
-def resblock2task(queue, block):
-    if block.in_channels != block.out_channels:
-        queue.append(('store_res', block.conv_shortcut if block.use_conv_shortcut else block.nin_shortcut))
-    else:
-        queue.append(('store_res', lambda x: x))
-    queue.append(('pre_norm', block.norm1))
-    queue.append(('silu', inplace_nonlinearity))
-    queue.append(('conv1', block.conv1))
-    queue.append(('pre_norm', block.norm2))
-    queue.append(('silu', inplace_nonlinearity))
-    queue.append(('conv2', block.conv2))
-    queue.append(['add_res', None])
-
-
-def build_sampling(task_queue, net, is_decoder):
-    if is_decoder:
-        resblock2task(task_queue, net.mid.block_1)
-        attn2task(task_queue, net.mid.attn_1)
-        resblock2task(task_queue, net.mid.block_2)
-        for i_level in reversed(range(net.num_resolutions)):
-            for i_block in range(net.num_res_blocks + 1):
-                resblock2task(task_queue, net.up[i_level].block[i_block])
-            if i_level != 0:
-                task_queue.append(('upsample', net.up[i_level].upsample))
-    else:
-        for i_level in range(net.num_resolutions):
-            for i_block in range(net.num_res_blocks):
-                resblock2task(task_queue, net.down[i_level].block[i_block])
-            if i_level != net.num_resolutions - 1:
-                task_queue.append(('downsample', net.down[i_level].downsample))
-        resblock2task(task_queue, net.mid.block_1)
-        attn2task(task_queue, net.mid.attn_1)
-        resblock2task(task_queue, net.mid.block_2)
-
-
+# --------------------------------------------------------------------------- program views / statistics merge
 def build_task_queue(net, is_decoder):
-    """tilevae.py:174-195: the Encoder / Decoder as a flat op list."""
-    task_queue = [('conv_in', net.conv_in)]
-    build_sampling(task_queue, net, is_decoder)
-    if not is_decoder or not net.give_pre_end:
-        task_queue.append(('pre_norm', net.norm_out))
-        task_queue.append(('silu', inplace_nonlinearity))
-        task_queue.append(('conv_out', net.conv_out))
-        if is_decoder and net.tanh_out:
-            task_queue.append(('tanh', torch.tanh))
-    return task_queue
-
-
-def clone_task_queue(task_queue):
-    return [[item for item in task] for task in task_queue]
-
-
-class _Norm:
-    """('apply_norm', _Norm): frozen statistics + affine of one GroupNorm site; fuses the SiLU that follows."""
-
-    def __init__(self, mean, var, layer):
-        self.mean, self.var = mean, var
-        w, b = getattr(layer, "weight", None), getattr(layer, "bias", None)
-        self.gamma, self.beta = _affine32(w, b, mean.device) if w is not None else (None, None)
-
-    def __call__(self, x, act: bool = False):
-        return custom_group_norm(x, NUM_GROUPS, self.mean, self.var, self.gamma, self.beta, GN_EPS, act=act)
+    """The compiled program in the reference's task-queue vocabulary (tilevae.py:107-204 names): a read-only VIEW for
+    callers that inspect the queue (logging, tests); execution uses `vae_engine.Program` directly."""
+    from . import vae_engine as ve
+    prog = ve.compile_program(net, is_decoder)
+    queue, first = [], True
+    for op in prog.ops:
+        if isinstance(op, ve.Skip):
+            queue.append(('store_res', op.module if op.module is not None else (lambda x: x)))
+        elif isinstance(op, ve.Norm):
+            queue.append(('pre_norm', op.module))
+            if op.act:
+                queue.append(('silu', lambda x: F.silu(x, inplace=True)))
+        elif isinstance(op, ve.Conv):
+            if first:
+                name = 'conv_in'
+            elif op.upsample_first:
+                name = 'upsample'
+            elif op.downsample:
+                name = 'downsample'
+            elif op.module is getattr(net, 'conv_out', None):
+                name = 'conv_out'
+            else:
+                name = 'conv2' if op.add_skip else 'conv1'
+            queue.append((name, op.module))
+            if op.add_skip:
+                queue.append(['add_res', None])
+        elif isinstance(op, ve.Attention):
+            queue.append(('attn', op.module))
+            queue.append(['add_res', None])
+        elif isinstance(op, ve.Tanh):
+            queue.append(('tanh', torch.tanh))
+        first = False
+    return queue
 
 
 class GroupNormParam:
-    """tilevae.py:289-361: collects per-tile statistics of one GroupNorm round and merges them.
+    """One GroupNorm round (tilevae.py:289-361): per-tile statistics in, merged statistics out.
 
-    With `group` set (tile shard over ranks) the pixel-weighted sums are all-reduced, so every rank applies
-    the statistics of ALL tiles (same weights as the reference: p_i = pixels_i / sum(pixels))."""
+    Merge rule of the reference (:320-335): weights p_i = pixels_i / sum(pixels); var = sum p_i var_i,
+    mean = sum p_i mean_i (no between-tile term).  With a process group (tile shard over ranks) the weighted sums
+    are all-reduced, so every rank applies the statistics of ALL tiles; every rank takes part in every round, tiles
+    or not -- the number of rounds follows from the program, no host agreement is needed."""
 
     def __init__(self, group=None, sharded: bool = False):
         self.group, self.sharded = group, sharded
-        self.var_list = []
-        self.mean_list = []
-        self.pixel_list = []
-        self.weight = None
-        self.bias = None
-        self.layer = None
+        self.var_list, self.mean_list, self.pixel_list = [], [], []
 
-    def add_tile(self, tile, layer):
-        var, mean = get_var_mean(tile, NUM_GROUPS)   # fp32 statistics: no fp16 overflow branch needed (tilevae.py:300-304)
+    def add(self, var: torch.Tensor, mean: torch.Tensor, pixels: int):
         self.var_list.append(var)
         self.mean_list.append(mean)
-        self.pixel_list.append(tile.shape[2] * tile.shape[3])
-        self.layer = layer
-        self.weight = getattr(layer, 'weight', None)
-        self.bias = getattr(layer, 'bias', None)
+        self.pixel_list.append(pixels)
 
-    def summary(self):
-        """Pixel-count weighted average of the tile variances and means (tilevae.py:320-335)."""
-        if len(self.var_list) == 0 and not self.sharded:
-            return None
-        if self.sharded:
-            import torch.distributed as dist
-            dev = host.device()
-            if self.var_list:
-                px = torch.tensor(self.pixel_list, dtype=torch.float32, device=self.var_list[0].device).unsqueeze(1)
-                packed = torch.cat([(torch.vstack(self.var_list) * px).sum(0), (torch.vstack(self.mean_list) * px).sum(0), px.sum().view(1)])
-            else:
-                packed = None
-            # ranks may own no tile in this round: agree on the vector length first
-            n = torch.tensor([0 if packed is None else packed.numel()], device=dev)
-            dist.all_reduce(n, op=dist.ReduceOp.MAX, group=self.group)
-            if int(n.item()) == 0:
-                return None
-            if packed is None:
-                packed = torch.zeros(int(n.item()), dtype=torch.float32, device=dev)
-            dist.all_reduce(packed, group=self.group)
-            k = (packed.numel() - 1) // 2
-            var, mean = packed[:k] / packed[-1], packed[k:2 * k] / packed[-1]
-            return _Norm(mean, var, self.layer) if self.layer is not None else _Norm(mean, var, None)
-        var = torch.vstack(self.var_list)
-        mean = torch.vstack(self.mean_list)
-        max_value = max(self.pixel_list)
-        pixels = torch.tensor(self.pixel_list, dtype=torch.float32, device=var.device) / max_value
-        pixels = (pixels / torch.sum(pixels)).unsqueeze(1)
-        return _Norm(torch.sum(mean * pixels, dim=0), torch.sum(var * pixels, dim=0), self.layer)
-
-    @staticmethod
-    def from_tile(tile, norm):
-        """Statistics of a single tensor frozen into a norm function (tilevae.py:337-361)."""
+    def add_tile(self, tile, layer=None):
+        """Reference-style entry point: statistics of an NCHW tile (fp32: no fp16 overflow branch needed, :300-304)."""
         var, mean = get_var_mean(tile, NUM_GROUPS)
-        return _Norm(mean, var, norm)
+        self.add(var, mean, tile.shape[2] * tile.shape[3])
+
+    def summary(self, stat_len: Optional[int] = None, device=None):
+        """-> (mean, var) fp32 tensors, or None when no tile contributed anywhere."""
+        if not self.sharded:
+            if not self.var_list:
+                return None
+            var, mean = torch.vstack(self.var_list), torch.vstack(self.mean_list)
+            px = torch.tensor(self.pixel_list, dtype=torch.float32, device=var.device)
+            px = (px / px.sum()).unsqueeze(1)
+            return torch.sum(mean * px, dim=0), torch.sum(var * px, dim=0)
+        import torch.distributed as dist
+        if self.var_list:
+            px = torch.tensor(self.pixel_list, dtype=torch.float32, device=self.var_list[0].device).unsqueeze(1)
+            packed = torch.cat([(torch.vstack(self.var_list) * px).sum(0), (torch.vstack(self.mean_list) * px).sum(0), px.sum().view(1)])
+        else:
+            packed = torch.zeros(2 * int(stat_len) + 1, dtype=torch.float32, device=device)
+        dist.all_reduce(packed, group=self.group)
+        k = (packed.numel() - 1) // 2
+        return packed[k:2 * k] / packed[-1], packed[:k] / packed[-1]
 
 
 # --------------------------------------------------------------------------- the hook
@@ -323,6 +258,8 @@ class VAEHook:
         self.to_gpu = to_gpu
         self.pad = 11 if is_decoder else 32
         self.verbose = False
+        self.backend_name = None      # which backend ran the last call ("tcgen05" / "modules")
+        self._program = None
         self._shard_group = None
         self._shard_world = 1
         self._shard_rank = 0
@@ -330,8 +267,7 @@ class VAEHook:
     def init_tile_shard(self, group=None):
         """Shard the VAE tiles over the ranks of `group` (one process per GPU): rank r runs tiles i with
         i % world == r; GroupNorm statistics (slow mode) are all-reduced per round and the disjoint output
-        regions are combined with one all-reduce of the canvas (x + 0 is exact).  New: the reference is
-        single-device."""
+        regions are exchanged with one all-gather.  New: the reference is single-device."""
         import torch.distributed as dist
         self._shard_group = group
         self._shard_world = dist.get_world_size(group)
@@ -364,153 +300,137 @@ class VAEHook:
                                      ib.ctypes.data_as(p), ob.ctypes.data_as(p), n))
         return ib.tolist(), ob.tolist()
 
-    @torch.no_grad()
-    def estimate_group_norm(self, z, task_queue, color_fix):
-        """tilevae.py:464-505: run the queue on the down-sampled input and freeze every GroupNorm met."""
-        tile = z
-        last_id = len(task_queue) - 1
-        while last_id >= 0 and task_queue[last_id][0] != 'pre_norm':
-            last_id -= 1
-        if last_id <= 0 or task_queue[last_id][0] != 'pre_norm':
-            raise ValueError('No group norm found in the task queue')
-        i = 0
-        while i <= last_id:
-            task = task_queue[i]
-            if task[0] == 'pre_norm':
-                norm = GroupNormParam.from_tile(tile, task[1])
-                task_queue[i] = ('apply_norm', norm)
-                if i == last_id:
-                    return True
-                fuse = task_queue[i + 1][0] == 'silu'
-                tile = norm(tile, act=fuse)
-                if fuse:
-                    i += 1
-            elif task[0] == 'store_res':
-                task_id = i + 1
-                while task_id < last_id and task_queue[task_id][0] != 'add_res':
-                    task_id += 1
-                if task_id < last_id:
-                    task_queue[task_id][1] = task[1](tile)
-            elif task[0] == 'add_res':
-                tile = tile + task[1]
-                task[1] = None
-            elif color_fix and task[0] == 'downsample':
-                return True
-            else:
-                tile = task[1](tile)
-            if torch.isnan(tile).any():
-                print('Nan detected in fast mode estimation. Fast mode disabled.')
-                return False
-            i += 1
-        raise IndexError('Should not reach here')
+    def _cheap_fallback(self, z, device, dtype):
+        """What the reference returns when interrupted before any tile finished (tilevae.py:573-577, :656): the cheap
+        latent -> RGB approximation, nearest-exact x8.  Only a decoder has one; the encoder raises like the reference
+        (None.to(...))."""
+        approx = host.get_cheap_approximation()
+        if approx is None or not self.is_decoder:
+            raise RuntimeError("[Tiled VAE]: interrupted before any tile finished and no cheap approximation is available")
+        with torch.no_grad():
+            out = torch.cat([F.interpolate(approx(x).unsqueeze(0), scale_factor=8, mode="nearest-exact") for x in z], dim=0)
+        return out.to(device=device, dtype=dtype)
 
     @torch.no_grad()
     def vae_tile_forward(self, z):
-        """tilevae.py:509-656, device-resident."""
+        """tilevae.py:509-656, device-resident, on the compiled program."""
+        from . import vae_engine as ve
         param = next(self.net.parameters())
         device, dtype = param.device, param.dtype
         if device.type != "cuda":
             raise RuntimeError(f"VAEHook: network is on {device}; the B200 tiled-VAE path has no CPU fallback")
         net, tile_size, is_decoder = self.net, self.tile_size, self.is_decoder
-
         z = z.detach().to(device=device, dtype=dtype).contiguous()
         N, height, width = z.shape[0], z.shape[2], z.shape[3]
         net.last_z_shape = z.shape
         in_bboxes, out_bboxes = self.split_tiles(height, width)
+        if self._program is None or self._program.cache.get("net_id") != id(net):
+            self._program = ve.compile_program(net, is_decoder)
+            self._program.cache["net_id"] = id(net)
+        program = self._program
+        backend = ve.pick_backend(program, device, dtype)
+        self.backend_name = backend.name
+        per_image = isinstance(backend, ve.TensorCoreBackend)     # channels-last kernels take one image at a time
+        est_in = fast_mode_estimator_input(z, tile_size) if self.fast_mode else None
 
-        # tile crop: straight HBM -> HBM (the reference goes through host RAM)
         sharded = self._shard_world > 1
-        if sharded:   # this rank's tiles only
-            mine = [i for i in range(len(in_bboxes)) if i % self._shard_world == self._shard_rank]
-            all_out_shape = None
-            in_bboxes, out_bboxes = [in_bboxes[i] for i in mine], [out_bboxes[i] for i in mine]
-        tiles: List[Optional[torch.Tensor]] = []
-        for b in in_bboxes:
-            t = torch.empty((N, z.shape[1], b[3] - b[2], b[1] - b[0]), dtype=dtype, device=device)
-            copy_region(z[:, :, b[2]:b[3], b[0]:b[1]], t)
-            tiles.append(t)
-        num_tiles = len(tiles)
-
-        single_task_queue = build_task_queue(net, is_decoder)
-        if self.fast_mode:
-            estimate_task_queue = clone_task_queue(single_task_queue)
-            if self.estimate_group_norm(fast_mode_estimator_input(z, tile_size), estimate_task_queue, color_fix=self.color_fix):
-                single_task_queue = estimate_task_queue
-        del z
-        task_queues = [clone_task_queue(single_task_queue) for _ in range(num_tiles)]
-
-        result = None
-        num_completed = 0
-        forward = True
-        while True:
+        mine = [i for i in range(len(in_bboxes)) if i % self._shard_world == self._shard_rank] if sharded else list(range(len(in_bboxes)))
+        out_c = [op for op in program.ops if isinstance(op, ve.Conv)][-1].module.out_channels
+        oh, ow = (height * 8, width * 8) if is_decoder else (height // 8, width // 8)
+        result = torch.zeros((N, out_c, oh, ow), dtype=dtype, device=device)   # zeros: a partial (interrupted) result reads 0 elsewhere
+        finished = 0
+        images = [slice(n, n + 1) for n in range(N)] if per_image else [slice(0, N)]
+        for img in images:
+            ex = ve.Executor(program, backend)
+            if est_in is not None:
+                ex.estimate(backend.load(est_in[img]), self.color_fix)
+            finished += self._run_tiles(ex, backend, z[img], result[img], [in_bboxes[i] for i in mine], [out_bboxes[i] for i in mine])
             if host.interrupted():
                 break
-            group_norm_param = GroupNormParam(self._shard_group, sharded)
-            for i in (range(num_tiles) if forward else reversed(range(num_tiles))):
-                if host.interrupted():
-                    break
-                tile = tiles[i]
-                task_queue = task_queues[i]
-                while len(task_queue) > 0:
-                    task = task_queue.pop(0)
-                    kind = task[0]
-                    if kind == 'pre_norm':
-                        group_norm_param.add_tile(tile, task[1])
-                        break
-                    elif kind == 'apply_norm':
-                        fuse = len(task_queue) > 0 and task_queue[0][0] == 'silu'
-                        if fuse:
-                            task_queue.pop(0)
-                        tile = task[1](tile, act=fuse)
-                    elif kind == 'store_res' or kind == 'store_res_cpu':
-                        task_id = 0
-                        res = task[1](tile)
-                        while task_queue[task_id][0] != 'add_res':
-                            task_id += 1
-                        task_queue[task_id][1] = res
-                    elif kind == 'add_res':
-                        tile = tile + task[1] if tile.data_ptr() == task[1].data_ptr() else tile.add_(task[1])
-                        task[1] = None
-                    else:
-                        tile = task[1](tile)
-
-                if len(task_queue) == 0:
-                    tiles[i] = None
-                    num_completed += 1
-                    if result is None:
-                        alloc = torch.zeros if sharded else torch.empty   # sharded: the other ranks' regions must read 0
-                        result = alloc((N, tile.shape[1], height * 8 if is_decoder else height // 8,
-                                        width * 8 if is_decoder else width // 8), dtype=dtype, device=device)
-                    ob = out_bboxes[i]
-                    valid = crop_valid_region(tile.to(dtype).contiguous(), in_bboxes[i], ob, is_decoder)
-                    copy_region(valid, result[:, :, ob[2]:ob[3], ob[0]:ob[1]])
-                    del tile
-                else:
-                    tiles[i] = tile
-                    if i == num_tiles - 1 and forward:
-                        forward = False
-                    elif i == 0 and not forward:
-                        forward = True
-
-            if (num_completed == num_tiles and not sharded) or host.interrupted():
-                break
-            norm = group_norm_param.summary()   # sharded: a collective -- every rank takes part in every round
-            if sharded and norm is None:
-                break
-            if norm is not None:
-                for q in task_queues:
-                    if len(q) > 0:
-                        q.insert(0, ('apply_norm', norm))
-
+        interrupted = host.interrupted()
         if sharded:
-            import torch.distributed as dist
-            out_c = self.net.conv_out.out_channels
-            if result is None:
-                result = torch.zeros((N, out_c, height * 8 if is_decoder else height // 8, width * 8 if is_decoder else width // 8),
-                                     dtype=dtype, device=device)
-            dist.all_reduce(result, group=self._shard_group)   # disjoint regions + zeros: exact
-        if result is None or num_completed != num_tiles:
-            raise RuntimeError("[Tiled VAE]: interrupted before any tile finished")
-        if torch.isnan(result).any():
+            self._exchange_regions(result, in_bboxes, out_bboxes)
+        total = len(mine) * len(images)
+        if finished == 0 and total > 0 and interrupted:
+            return self._cheap_fallback(z, device, dtype)
+        if not interrupted and torch.isnan(result).any():
             raise RuntimeError("[Tiled VAE]: NaN in the result (the reference's test_for_nans, tilevae.py:625)")
         return result
+
+    def _run_tiles(self, ex, backend, z, result, in_bboxes, out_bboxes) -> int:
+        """All tiles of one image (or image batch) through the program: rounds separated by the barrier sites."""
+        from . import vae_engine as ve
+        states = []
+        for b in in_bboxes:
+            st = ve.TileState(backend.load(z[:, :, b[2]:b[3], b[0]:b[1]]))
+            states.append(st)
+        sharded = self._shard_world > 1
+        rounds = ex.barrier_sites()
+        num_tiles = len(states)
+        done = 0
+        forward = True
+        for rnd in range(rounds + 1):
+            if host.interrupted():
+                break
+            collect = GroupNormParam(self._shard_group, sharded)
+            site = None
+            order = range(num_tiles) if forward else range(num_tiles - 1, -1, -1)     # the reference's zig-zag (:599)
+            for i in order:
+                if host.interrupted():
+                    break
+                st = states[i]
+                if st is None:
+                    continue
+                stop = ex.run(st)
+                if stop is None:
+                    backend.paste(st.act, result, in_bboxes[i], out_bboxes[i], self.is_decoder)
+                    states[i] = None
+                    done += 1
+                else:
+                    site = stop
+                    var, mean = backend.stats(st.act)
+                    collect.add(var, mean, backend.pixels(st.act))
+            forward = not forward
+            if rnd == rounds or host.interrupted():
+                break
+            if site is None and sharded:      # a rank without tiles still joins the round's all-reduce
+                site = [op for op in ex.program.ops if isinstance(op, ve.Norm) and ex.frozen[op.site] is None][rnd]
+            if site is None:
+                break
+            stat_len = NUM_GROUPS * (z.shape[0] if not isinstance(backend, ve.TensorCoreBackend) else 1)
+            merged = collect.summary(stat_len, z.device)
+            if merged is None:
+                break
+            mean, var = merged
+            for st in states:
+                if st is not None:
+                    ex.apply_barrier(st, site, mean, var)
+        return done
+
+    def _exchange_regions(self, result, in_bboxes, out_bboxes):
+        """Tile shard: every rank pasted its own tiles; gather the disjoint output regions (one all-gather of the
+        packed regions -- each byte crosses NVLink once; the round-1 all_reduce of the whole canvas moved it twice)."""
+        import torch.distributed as dist
+        world, rank = self._shard_world, self._shard_rank
+        owners = [[i for i in range(len(out_bboxes)) if i % world == r] for r in range(world)]
+        sizes = [sum((out_bboxes[i][1] - out_bboxes[i][0]) * (out_bboxes[i][3] - out_bboxes[i][2]) for i in own) for own in owners]
+        plane = result.shape[0] * result.shape[1]
+        cap = max(sizes) * plane
+        send = torch.zeros(cap, dtype=result.dtype, device=result.device)
+        off = 0
+        for i in owners[rank]:
+            b = out_bboxes[i]
+            blk = result[:, :, b[2]:b[3], b[0]:b[1]]
+            send[off:off + blk.numel()].view(blk.shape).copy_(blk)
+            off += blk.numel()
+        recv = torch.empty(world * cap, dtype=result.dtype, device=result.device)
+        dist.all_gather_into_tensor(recv, send, group=self._shard_group)
+        for r in range(world):
+            if r == rank:
+                continue
+            off = r * cap
+            for i in owners[r]:
+                b = out_bboxes[i]
+                dst = result[:, :, b[2]:b[3], b[0]:b[1]]
+                dst.copy_(recv[off:off + dst.numel()].view(dst.shape))
+                off += dst.numel()

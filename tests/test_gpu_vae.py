@@ -148,3 +148,56 @@ def test_vaehook_batch_of_two(tv):
     with torch.no_grad():
         got = hook(z2.cuda())
     assert (got.cpu() - want).abs().max().item() <= 3e-4 * max(1.0, want.abs().max().item())
+
+
+# ------------------------------------------------------------------------------- tensor-core backend (fp16 / bf16 networks)
+def _sd_width_net(is_dec, seed):
+    """Full-width SD autoencoder half (ch=128, ch_mult (1,2,4,4), 2 res blocks): the layer shapes of BASELINE cfg4."""
+    from oracle import ldm_vae
+    net = ldm_vae.seeded_init((ldm_vae.Decoder if is_dec else ldm_vae.Encoder)(), seed)
+    net.eval()
+    net.original_forward = net.forward
+    return net
+
+
+@pytest.mark.parametrize("is_dec,fast,H,W,tile", [(True, True, 40, 52, 16), (True, False, 40, 52, 16), (False, True, 200, 264, 64), (False, False, 136, 200, 64)])
+def test_vaehook_tensor_core_backend_matches_fp32_reference(tv, is_dec, fast, H, W, tile):
+    """fp16 network on the tcgen05 / channels-last backend vs the fp32 restatement of the reference's tiled algorithm
+    (oracle, run on the GPU in fp32: same tiles, same statistics merge).  fp16 activations through ~60 layers:
+    mean error <= 2e-3 * scale, max <= 3e-2 * scale."""
+    from oracle import synth
+    net = _sd_width_net(is_dec, 3 if is_dec else 4)
+    z = synth.latent(5 if is_dec else 6, (1, 4 if is_dec else 3, H, W), torch.float32)
+    ref_net = _sd_width_net(is_dec, 3 if is_dec else 4).cuda()
+    with torch.no_grad():
+        want = vae.vae_hook_call(ref_net, z.cuda(), tile, is_dec, fast, False).cpu()
+    net16 = net.cuda().half()
+    hook = tv.VAEHook(net16, tile, is_dec, fast_decoder=fast, fast_encoder=fast, color_fix=False)
+    with torch.no_grad():
+        got = hook(z.cuda().half())
+    assert hook.backend_name == "tcgen05"
+    assert got.dtype == torch.float16 and got.shape == want.shape
+    diff = (got.cpu().float() - want).abs()
+    scale = want.abs().max().item()
+    assert diff.mean().item() <= 2e-3 * scale and diff.max().item() <= 3e-2 * scale, (diff.mean().item() / scale, diff.max().item() / scale)
+
+
+def test_tensor_core_backend_matches_module_backend_on_the_same_fp16_network(tv):
+    """Same fp16 weights, same tiles: tcgen05 / channels-last backend vs cuDNN modules + NCHW kernels."""
+    from multidiffusion_upscaler_for_automatic1111_b200 import vae_engine as ve
+    from oracle import synth
+    net16 = _sd_width_net(True, 3).cuda().half()
+    z = synth.latent(5, (1, 4, 40, 52), torch.float16).cuda()
+    hook = tv.VAEHook(net16, 16, True, True, True, False)
+    with torch.no_grad():
+        a = hook(z)
+        orig = ve.pick_backend
+        ve.pick_backend = lambda program, device, dtype: ve.ModuleBackend(program, device, dtype)
+        try:
+            b = hook(z)
+        finally:
+            ve.pick_backend = orig
+    assert hook.backend_name == "modules"
+    scale = b.float().abs().max().item()
+    d = (a.float() - b.float()).abs()
+    assert d.mean().item() <= 1e-3 * scale and d.max().item() <= 2e-2 * scale

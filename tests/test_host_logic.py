@@ -156,3 +156,19 @@ def test_cat_repeat_memo():
         assert torch.equal(d.cat_repeat(x, 3), torch.cat([x] * 3))
     finally:
         host.use_shared(None)
+
+
+def test_more_batches_than_pointer_slots_are_merged_in_order():
+    """441 tiles with tile_bs 3 = 147 UNet output tensors > TD_MAX_BATCH_PTRS: consecutive batches are concatenated
+    (same tile order) instead of failing mid-sampling; the reference accepts any batch count."""
+    import torch
+    from multidiffusion_upscaler_for_automatic1111_b200 import _cabi, engine
+    T, bs, N = 441, 3, 2
+    outs = [torch.full((min(bs, T - b * bs) * N, 1, 2, 2), float(b)) for b in range(-(-T // bs))]
+    merged, new_bs = engine._fit_batch_table(None, outs, bs)
+    assert len(merged) <= _cabi.TD_MAX_BATCH_PTRS and new_bs % bs == 0
+    assert sum(m.shape[0] for m in merged) == T * N
+    assert all(m.shape[0] == new_bs * N for m in merged[:-1])
+    assert torch.equal(torch.cat(merged), torch.cat(outs))
+    same, same_bs = engine._fit_batch_table(None, outs[:10], bs)
+    assert same_bs == bs and len(same) == 10
