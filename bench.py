@@ -431,23 +431,23 @@ def gpu_arm(args, rank, world, local_rank):
             t_scatter_ser = only(lambda s: wl.scatter(s, 32))
             if args.variants:
                 tbl = {"empty_1024x128": only(wl.empty)}
-                tbl["blend_rows"] = only(lambda s: wl.blend(s, 0))
-                tbl["blend_rows_L2hot"] = only(lambda s: wl.blend(0, 0))
-                tbl["blend_rows_no_tiles"] = only(lambda s: wl.blend(s, 0x100))
-                tbl["blend_rows_no_pdl"] = only(lambda s: wl.blend(s, 32))
-                tbl["blend_rows_ieee_div"] = only(lambda s: wl.blend(s, 0x200))
-                tbl["scatter_rows"] = only(lambda s: wl.scatter(s, 0))
-                tbl["scatter_rows_L2hot"] = only(lambda s: wl.scatter(0, 0))
-                tbl["scatter_rows_no_pdl"] = only(lambda s: wl.scatter(s, 32))
+                tbl["blend_rows"] = only(lambda s: wl.blend(s, 0x400))
+                tbl["blend_rows_L2hot"] = only(lambda s: wl.blend(0, 0x400))
+                tbl["blend_rows_no_tiles"] = only(lambda s: wl.blend(s, 0x100 | 0x400))
+                tbl["blend_rows_no_pdl"] = only(lambda s: wl.blend(s, 32 | 0x400))
+                tbl["blend_rows_ieee_div"] = only(lambda s: wl.blend(s, 0x200 | 0x400))
+                tbl["scatter_rows"] = only(lambda s: wl.scatter(s, 0x400))
+                tbl["scatter_rows_L2hot"] = only(lambda s: wl.scatter(0, 0x400))
+                tbl["scatter_rows_no_pdl"] = only(lambda s: wl.scatter(s, 32 | 0x400))
                 wl.blend_mod(0)
-                tbl["blend_mixture_rows"] = only(lambda s: wl.blend_mod(s, 0))
-                tbl["blend_mixture_rows_L2hot"] = only(lambda s: wl.blend_mod(0, 0))
+                tbl["blend_mixture_rows"] = only(lambda s: wl.blend_mod(s, 0x400))
+                tbl["blend_mixture_rows_L2hot"] = only(lambda s: wl.blend_mod(0, 0x400))
                 tbl["blend_async_one_plane"] = only(lambda s: wl.blend(s, 64))
-                tbl["blend_async_ieee_div"] = only(lambda s: wl.blend(s, 0x200 | 0x400))
+                tbl["blend_async_ieee_div"] = only(lambda s: wl.blend(s, 0x200))
                 wl.blend_mod(0)
-                tbl["blend_mixture_async"] = only(lambda s: wl.blend_mod(s, 0x400))
+                tbl["blend_mixture_async"] = only(lambda s: wl.blend_mod(s, 0))
                 tbl["blend_mixture_reg"] = only(lambda s: wl.blend_mod(s, 2))
-                for name, fl in (("async", 0x400), ("pipe", 8), ("tma", 4), ("reg", 2)):
+                for name, fl in (("async", 0), ("pipe", 8), ("tma", 4), ("reg", 2)):
                     tbl[f"blend_{name}"] = only(lambda s, fl=fl: wl.blend(s, fl))
                     tbl[f"blend_{name}_no_tiles"] = only(lambda s, fl=fl: wl.blend(s, fl | 0x100))
                     tbl[f"blend_{name}_L2hot"] = only(lambda s, fl=fl: wl.blend(0, fl))

@@ -47,7 +47,8 @@ typedef enum td_dtype { TD_F16 = 0, TD_BF16 = 1, TD_F32 = 2 } td_dtype;
 #define TD_FLAG_ONE_PLANE 64u    /* cp.async blend: one (n, c) plane per CTA instead of two (A/B measurement) */
 #define TD_FLAG_STRIP 128u       /* MultiDiffusion blend: strip CTAs (8 rows x full width), opt-in, see csrc/td_strip.cu */
 #define TD_FLAG_DBG_NO_TILES 0x100u /* measurement aid: skip all tile visits (launch + epilogue floor) */
-#define TD_FLAG_NO_ROWS 0x400u   /* do not use the row-block form (csrc/td_rows.cu, the default): round-1 kernels (A/B measurement) */
+#define TD_FLAG_ROWS 0x400u      /* row-block form (csrc/td_rows.cu: one persistent CTA per SM, bulk-copy staging), opt-in: bit-identical,
+                                    measured slower than the default kernels on B200 */
 
 #define TD_MAX_GRID_DIM 256   /* max tile rows / cols of a grid plan            */
 #define TD_MAX_BATCH_PTRS 128 /* max UNet output batch tensors per blend launch */

@@ -27,7 +27,7 @@ TD_FLAG_NO_PDL = 32
 TD_FLAG_ONE_PLANE = 64
 TD_FLAG_STRIP = 128
 TD_FLAG_DBG_NO_TILES = 0x100
-TD_FLAG_NO_ROWS = 0x400
+TD_FLAG_ROWS = 0x400
 TD_MAX_GRID_DIM = 256
 TD_MAX_BATCH_PTRS = 128
 TD_MAX_PEERS = 16

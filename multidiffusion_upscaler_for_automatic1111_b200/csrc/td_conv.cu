@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -59,6 +60,9 @@ struct ConvParams {
     int chunk_cols;            // columns per store chunk: min(64, BN)
     int is_bf16;
     int bias_per_row;          // bias indexed by output pixel (GEMM row) instead of channel
+    int cluster;               // CTAs per cluster (1, 2 or 4): consecutive pixel tiles share the weight tile by TMA multicast
+    int m_tiles;               // NI * tiles_y * tiles_x
+    int m_groups;              // ceil(m_tiles / cluster)
     float alpha;
     long long res_pitch;       // residual: elements between pixels (0: none)
 };
@@ -83,6 +87,22 @@ __device__ __forceinline__ void tma_load_3d_u32(uint32_t dst, const CUtensorMap*
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
+// weight slice of this CTA, written into the same shared-memory offset of every CTA of the cluster (and completing
+// bytes on each CTA's own full barrier)
+__device__ __forceinline__ void tma_load_3d_mcast(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t src) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src) : "memory");
@@ -101,6 +121,11 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the same arrive delivered to the barrier at this offset in every CTA of `mask` (frees the stage cluster-wide)
+__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers fp16 and bf16 inputs with fp32 accumulation
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -158,13 +183,16 @@ __device__ __forceinline__ float unpack_hi(uint32_t w, int is_bf16) {
 }
 
 struct TileCoord { int img, py, px, nb; };
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
+// Work list: group g = (Cout block fastest, then pixel-tile group); the CTAs of a cluster take the `cluster` consecutive
+// pixel tiles of one group (same Cout block: they share the weight tile).  A pixel tile past the end is a dummy: its
+// loads are out of bounds (zero fill), its store is clipped away.
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int g, int crank) {
     TileCoord c;
-    c.nb = t % p.n_blocks;
-    int m = t / p.n_blocks;
+    c.nb = g % p.n_blocks;
+    int m = (g / p.n_blocks) * p.cluster + crank;
     c.px = m % p.tiles_x; m /= p.tiles_x;
     c.py = m % p.tiles_y;
-    c.img = m / p.tiles_y;
+    c.img = m / p.tiles_y;          // >= NI for a dummy tile
     return c;
 }
 
@@ -180,10 +208,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t stage_bytes = (uint32_t)(kConvStageA + stage_b);
     const uint32_t store0 = smem0 + (uint32_t)p.stages * stage_bytes;       // two staging buffers for the TMA store
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = p.cluster > 1 ? (int)cluster_rank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
+    const int cid = blockIdx.x / p.cluster, nclusters = gridDim.x / p.cluster;
+    const int num_groups = p.m_groups * p.n_blocks;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_d);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        // a stage is free when the MMAs of EVERY CTA of the cluster have read it (peers multicast into it)
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)p.cluster); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
@@ -193,7 +226,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (p.cluster > 1) cluster_sync_all(); else __syncthreads();     // barrier inits visible cluster-wide before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
     const int ksteps = p.taps_x * p.taps_y * p.Cin_chunks;
@@ -202,8 +235,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // ===================== TMA producer =====================
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-                const TileCoord c = decode_tile(p, t);
+            const int slice_rows = p.BN / p.cluster;
+            for (int g = cid; g < num_groups; g += nclusters) {
+                const TileCoord c = decode_tile(p, g, crank);
                 const int x0 = c.px * p.BW * p.stride - p.pad_left, y0 = c.py * p.BH * p.stride - p.pad_top;
                 int tap = 0;
                 for (int ty = 0; ty < p.taps_y; ++ty)
@@ -213,7 +247,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                             const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
                             tma_load_4d(sa, &map_a, kc * kConvBK, x0 + tx, y0 + ty, c.img, &full_bar[stage]);
-                            tma_load_3d_u32(sa + kConvStageA, &map_b, kc * kConvBK, c.nb * p.BN, tap, &full_bar[stage]);
+                            if (p.cluster == 1)
+                                tma_load_3d_u32(sa + kConvStageA, &map_b, kc * kConvBK, c.nb * p.BN, tap, &full_bar[stage]);
+                            else
+                                tma_load_3d_mcast(sa + kConvStageA + (uint32_t)(crank * slice_rows * 128), &map_b, kc * kConvBK,
+                                                  c.nb * p.BN + crank * slice_rows, tap, &full_bar[stage], cmask);
                             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                         }
             }
@@ -224,7 +262,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t idesc = umma_idesc(p.BN, p.is_bf16);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            for (int g = cid; g < num_groups; g += nclusters) {
                 mbar_wait(&acc_empty[as], aphase ^ 1u);              // epilogue has drained this accumulator stage
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
@@ -236,7 +274,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                     for (int k = 0; k < kConvBK / 16; ++k)          // +32 bytes along K inside the swizzle row = +2 in the address field
                         tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
-                    tc_commit(&empty_bar[stage]);                     // frees the smem stage when these MMAs have read it
+                    if (p.cluster == 1) tc_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs have read it
+                    else tc_commit_mcast(&empty_bar[stage], cmask);    // ... in every CTA of the cluster
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
                 tc_commit(&acc_full[as]);                             // accumulator complete -> epilogue
@@ -251,10 +290,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int ly = row / p.BW, lx = row - ly * p.BW;
         int as = 0; uint32_t aphase = 0;
         int buf = 0;
-        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-            const TileCoord c = decode_tile(p, t);
+        for (int g = cid; g < num_groups; g += nclusters) {
+            const TileCoord c = decode_tile(p, g, crank);
             const int ox = c.px * p.BW + lx, oy = c.py * p.BH + ly;
-            const bool pix_ok = ox < p.OW && oy < p.OH;
+            const bool pix_ok = ox < p.OW && oy < p.OH && c.img < p.NI;
             const long long pix = ((long long)c.img * p.OH + oy) * p.OW + ox;
             mbar_wait(&acc_full[as], aphase);
             tc_fence_after();
@@ -312,7 +351,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 fence_proxy_async();
                 named_bar_sync(1, 128);
                 if (et == 0) {
-                    tma_store_4d(&map_d, col0, c.px * p.BW, c.py * p.BH, c.img, sbuf);
+                    if (c.img < p.NI) tma_store_4d(&map_d, col0, c.px * p.BW, c.py * p.BH, c.img, sbuf);
                     bulk_commit();
                 }
                 buf ^= 1;
@@ -322,7 +361,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (et == 0) bulk_wait_all();
     }
     tc_fence_before();
-    __syncthreads();
+    if (p.cluster > 1) cluster_sync_all(); else __syncthreads();     // no CTA leaves while a peer may still write into it
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -428,9 +467,19 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     else { p.BW = 8; p.BH = 16; }
     p.tiles_x = (d->OW + p.BW - 1) / p.BW;
     p.tiles_y = (d->OH + p.BH - 1) / p.BH;
-    const long long nt = (long long)d->N * p.tiles_x * p.tiles_y * p.n_blocks;
-    if (nt > 0x7fffffffLL) { td_set_error("td_conv2d_nhwc: too many tiles"); return TD_ERR_UNSUPPORTED; }
-    p.num_tiles = (int)nt;
+    const long long mt = (long long)d->N * p.tiles_x * p.tiles_y;
+    if (mt * p.n_blocks > 0x3fffffffLL) { td_set_error("td_conv2d_nhwc: too many tiles"); return TD_ERR_UNSUPPORTED; }
+    p.m_tiles = (int)mt;
+    // CTA clusters: the weight tile of a k-step is fetched once per cluster (each CTA loads BN / cluster rows and
+    // multicasts them) -- the kernel is bound by L2 -> SM bytes otherwise (48 KB per 128x256x64 MMA step per CTA)
+    int cl = 1;
+    const char* force = getenv("TD_CONV_CLUSTER");
+    const int want = force != nullptr ? atoi(force) : 2;
+    if (want >= 2 && bn >= 64 && dev.sms % 2 == 0 && mt >= 2 * (long long)dev.sms) cl = 2;
+    if (want >= 4 && bn >= 128 && dev.sms % 4 == 0 && mt >= 4 * (long long)dev.sms) cl = 4;
+    p.cluster = cl;
+    p.m_groups = (int)((mt + cl - 1) / cl);
+    p.num_tiles = p.m_groups * p.n_blocks;
     p.chunk_cols = std::min(64, bn);
     p.is_bf16 = d->dtype == TD_BF16;
     p.bias_per_row = d->bias_per_row;
@@ -454,7 +503,7 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     {
         const uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout, (uint64_t)(d->kh * d->kw)};
         const uint64_t str[2] = {(uint64_t)d->w_pitch * 2, (uint64_t)d->Cout * d->w_pitch * 2};
-        const uint32_t box[3] = {64, (uint32_t)bn, 1};
+        const uint32_t box[3] = {64, (uint32_t)(bn / p.cluster), 1};
         const uint32_t es[3] = {1, 1, 1};
         const int rc = encode_map(&mb, w, p.is_bf16, 3, dims, str, box, es, true, "weights");
         if (rc != TD_OK) return rc;
@@ -467,8 +516,21 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
         const int rc = encode_map(&md, y, p.is_bf16, 4, dims, str, box, es, p.chunk_cols == 64, "output");
         if (rc != TD_OK) return rc;
     }
-    const int grid = std::min(p.num_tiles, dev.sms);
-    conv_gemm_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(ma, mb, md, p, bias, (const uint16_t*)residual);
+    const int grid = std::max(cl, std::min(p.num_tiles * cl, dev.sms) / cl * cl);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr = {};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)cl;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = cl > 1 ? 1 : 0;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_kernel, ma, mb, md, p, bias, (const uint16_t*)residual);
+    if (le != cudaSuccess) { td_set_error("td_conv2d_nhwc: launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return TD_ERR_CUDA; }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { td_set_error("td_conv2d_nhwc: launch failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
     return TD_OK;

@@ -1581,7 +1581,7 @@ extern "C" int td_scatter_tiles(const td_grid* g, const void* x, void* tiles, in
     tl_pdl = !(flags & TD_FLAG_NO_PDL);
     const bool vec_ok = !(flags & TD_FLAG_FORCE_GENERIC) && gp.W % vec == 0 && gp.tw % vec == 0 && aligned16(x) && aligned16(tiles);
     cudaStream_t s = (cudaStream_t)stream;
-    if (vec_ok && !(flags & (TD_FLAG_NO_TMA | TD_FLAG_NO_ROWS | TD_FLAG_TMA | TD_FLAG_PIPELINE))) {   // default: row-block form (td_rows.cu)
+    if (vec_ok && (flags & TD_FLAG_ROWS)) {   // opt-in: row-block form (td_rows.cu); falls through when not applicable
         const int rc = td_rows_try_launch_scatter(g, x, tiles, N, C, dtype, tile_begin, tile_end, (flags & TD_FLAG_NO_PDL) ? 0 : 1, stream);
         if (rc <= 0) return rc;
     }
@@ -1608,8 +1608,8 @@ extern "C" int td_blend_multidiffusion(const td_grid* g, const void* const* batc
     cudaStream_t s = (cudaStream_t)stream;
     if (!(flags & TD_FLAG_FORCE_GENERIC) && blend_vec_ok(bp, tile_dtype, acc_dtype, {weights, rcp_weights, x_out, x_buffer})) {
         int rc = 1;
-        if (!(flags & (TD_FLAG_NO_ROWS | TD_FLAG_STRIP | TD_FLAG_TMA | TD_FLAG_NO_TMA | TD_FLAG_PIPELINE | TD_FLAG_ONE_PLANE))) {
-            // default: row-block form (td_rows.cu); falls through to the round-1 kernels when not applicable
+        if (flags & TD_FLAG_ROWS) {
+            // opt-in: row-block form (td_rows.cu); falls through to the default kernels when not applicable
             rc = td_rows_try_launch_md(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, weights, rcp_weights, x_out, x_buffer,
                                        (flags & TD_FLAG_NO_PDL) ? 0 : 1, (flags & TD_FLAG_DBG_NO_TILES) ? 1 : 0, stream);
             if (rc <= 0) return rc;
@@ -1700,7 +1700,7 @@ extern "C" int td_blend_mixture(const td_grid* g, const void* const* batch_ptrs,
     }
     cudaStream_t s = (cudaStream_t)stream;
     if (!(flags & TD_FLAG_FORCE_GENERIC) && blend_vec_ok(bp, tile_dtype, acc_dtype, {rescale, x_buffer})) {
-        if (!(flags & (TD_FLAG_NO_ROWS | TD_FLAG_STRIP | TD_FLAG_NO_TMA))) {   // default: row-block form (td_rows.cu)
+        if (flags & TD_FLAG_ROWS) {   // opt-in: row-block form (td_rows.cu)
             const int rc = td_rows_try_launch_mod(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, tile_weights, rescale, x_buffer,
                                                   (flags & TD_FLAG_NO_PDL) ? 0 : 1, stream);
             if (rc <= 0) return rc;

@@ -1,4 +1,4 @@
-// Row-block form of the per-step hot path (the default on B200 when applicable):
+// Row-block form of the per-step hot path (TD_FLAG_ROWS, opt-in -- see the measurements at the end of this comment):
 //   scatter                       multidiffusion.py:155, mixtureofdiffusers.py:88,104
 //   blend + normalise (MD)        multidiffusion.py:166-167, :208
 //   blend (Mixture of Diffusers)  mixtureofdiffusers.py:122-126
@@ -14,13 +14,23 @@
 //     contiguous chunk: a unit's staging is ~20-30 `cp.async.bulk` copies (UBLKCP, 1-D TMA, no tensor map, no
 //     zero fill, ~1.3 KB each) issued by one warp, completing on one mbarrier per unit.  All units of a CTA are in
 //     flight before the first wait (4 x ~30 KB at BASELINE cfg2), so the HBM pipe is full ~1 us after launch;
-//   * consume: one thread per 16-byte canvas vector walks the covering tiles in ascending tile index: two aligned
-//     LDS.128 + funnel shift (tile columns are 2-byte-misaligned against the canvas), packed add rounded through
-//     the canvas dtype; chunks outside the tile are register zeros (x + (+0) is exact for MultiDiffusion; the
-//     Mixture-of-Diffusers form masks per element because its accumulator can be -0);
+//   * consume: one thread per 16-byte canvas vector -- the SAME (row slot, vector) in every unit, so the tile columns
+//     touching it, their shifts and edge predicates are computed once per kernel -- walks the covering tiles in
+//     ascending tile index: two aligned LDS.128 + funnel shift (tile columns are 2-byte-misaligned against the
+//     canvas), packed add rounded through the canvas dtype; chunks outside the tile are register zeros (x + (+0) is
+//     exact for MultiDiffusion; the Mixture-of-Diffusers form masks per element because its accumulator can be -0);
+//     threads wait for a unit on the CTA barrier (one thread blocks on the mbarrier): no spinning issue slots;
 //   * normalise in registers, one 256-bit store per thread (fp32 output, as the reference).
 // Scatter is the mirror image: one bulk copy brings a unit's canvas rows in, threads re-align and write 128-bit
 // vectors into the tile batch.
+//
+// MEASURED on B200 (round 2, BASELINE cfg2, back-to-back launches in a CUDA graph): bit-identical to the default
+// kernels on every fixture, but SLOWER -- blend 20.3 us vs 8.8 us, scatter 7.1 us vs 4.9 us, zero-visit floor 7.3 us
+// vs 3.5 us.  A 200 KB one-CTA-per-SM kernel cannot become resident while its predecessor drains (no programmatic-
+// dependent-launch overlap), pays the full launch -> barrier init -> copy latency -> consume -> store chain once per
+// launch, and the ~100 small (1.3 KB, 16-byte-aligned) bulk copies per SM complete at ~1 TB/s chip-wide (ncu:
+// the consumers sit on the unit mbarrier; L2-hot and HBM-cold runs take the same time).  Kept as an opt-in for
+// geometries with few, large tiles and as the worked example of why the default is many small co-resident CTAs.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -156,29 +166,58 @@ __device__ __forceinline__ void rows_issue(const RowsParams& p, int u, int slot,
     }
 }
 
-// ---- one tile visit of one canvas vector: elements [u0, u0 + VEC) of a staged tile row, zeros outside the tile -----
-template <typename T>
-__device__ __forceinline__ uint4 rows_tile_window(const unsigned char* row, int u0, int tw) {
-    constexpr int VEC = Vec<T>::kElems;
-    const int a = u0 & ~(VEC - 1), s = u0 - a;          // aligned chunk start (may be -VEC), shift in [0, VEC)
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    const uint4 A = (a >= 0 && a < tw) ? lds128(row + a * (int)sizeof(T)) : z;
-    if (s == 0) return A;
-    const uint4 B = (a + VEC < tw) ? lds128(row + (a + VEC) * (int)sizeof(T)) : z;   // a + VEC >= 0 always
-    return Vec<T>::window(A, B, s);
+// ---- shared-memory access by 32-bit shared-window address (no generic -> shared conversion per access) ------------
+__device__ __forceinline__ uint4 lds128_u32(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f32_u32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
 
-// Per-lane-divergent table reads must not go through the constant bank (a divergent LDC replays per distinct address):
-// the consumers read the tile-column origins and the per-vector column ranges from shared memory.
-struct RowsTables {
-    short xs[TD_MAX_GRID_DIM];
-    short ys[TD_MAX_GRID_DIM];
-    unsigned char vcol_lo[kRowsMaxVec], vcol_n[kRowsMaxVec];
+// Per-thread constants of one tile column touching the thread's canvas vector.  A thread owns the SAME (row slot, canvas
+// vector) in every unit, so everything that depends on the column only is computed once per kernel:
+//   elements [u0, u0 + VEC) of a tile row = aligned chunks A = [a, a + VEC), B = [a + VEC, a + 2 VEC), shift s = u0 - a;
+//   a chunk outside [0, tw) is register zeros (x + (+0) is exact for MultiDiffusion; MoD masks per element).
+struct ColRef {
+    int j;        // tile column
+    int aoff;     // byte offset of chunk A inside the tile row (may be -16)
+    int s;        // shift in elements, [0, VEC)
+    int va, vb;   // chunk A / B inside the tile
+    int u0;       // tile column of element 0 (MoD)
 };
-__device__ __forceinline__ void rows_load_tables(const RowsParams& p, RowsTables& t) {
-    for (int i = threadIdx.x; i < p.cols; i += blockDim.x) t.xs[i] = p.xs[i];
-    for (int i = threadIdx.x; i < p.rows; i += blockDim.x) t.ys[i] = p.ys[i];
-    for (int i = threadIdx.x; i < p.wv; i += blockDim.x) { t.vcol_lo[i] = p.vcol_lo[i]; t.vcol_n[i] = p.vcol_n[i]; }
+constexpr int kRowsMaxCols = 4;   // tile columns touching one canvas vector on this path (rows_plan checks)
+
+template <typename T>
+__device__ __forceinline__ void rows_col_refs(const RowsParams& p, int xv, ColRef (&cr)[kRowsMaxCols], int& jn) {
+    constexpr int VEC = Vec<T>::kElems;
+    const int jlo = p.vcol_lo[xv];
+    jn = p.vcol_n[xv];
+#pragma unroll
+    for (int c = 0; c < kRowsMaxCols; ++c) {
+        const int j = min(jlo + c, p.cols - 1);
+        const int u0 = xv * VEC - (int)p.xs[j];
+        const int a = u0 & ~(VEC - 1);
+        cr[c].j = j;
+        cr[c].u0 = u0;
+        cr[c].s = u0 - a;
+        cr[c].aoff = a * (int)sizeof(T);
+        cr[c].va = (a >= 0 && a < p.tw) ? 1 : 0;
+        cr[c].vb = (cr[c].s != 0 && a + VEC < p.tw) ? 1 : 0;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ uint4 rows_visit(uint32_t row_addr, const ColRef& c) {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t addr = row_addr + (uint32_t)c.aoff;
+    const uint4 A = c.va ? lds128_u32(addr) : z;
+    if (c.s == 0) return A;
+    const uint4 B = c.vb ? lds128_u32(addr + 16u) : z;
+    return Vec<T>::window(A, B, c.s);
 }
 
 struct RowsCommon {
@@ -192,6 +231,14 @@ __device__ __forceinline__ RowsCommon rows_partition(const RowsParams& p) {
     return c;
 }
 
+// One thread blocks on the unit's mbarrier, the CTA barrier releases everyone else (warps parked on a hardware barrier
+// issue nothing, a spinning try_wait loop does); every thread then takes its own (immediately successful) acquire.
+__device__ __forceinline__ void rows_wait_unit(uint64_t* bar, uint32_t parity) {
+    if (threadIdx.x == 0) mbar_wait(bar, parity);
+    __syncthreads();
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
 // =================================================================================================================
 // MultiDiffusion blend + normalise
 // =================================================================================================================
@@ -203,7 +250,6 @@ blend_rows_md_kernel(const __grid_constant__ RowsParams p, const float* __restri
     extern __shared__ __align__(128) unsigned char rows_smem[];
     __shared__ __align__(8) uint64_t full[kRowsMaxSlots];
     __shared__ SegTable segs[kRowsMaxSlots];
-    __shared__ RowsTables tb;
     const int tid = threadIdx.x;
     const RowsCommon c = rows_partition(p);
     const int n = c.u_end - c.u_begin;
@@ -212,27 +258,31 @@ blend_rows_md_kernel(const __grid_constant__ RowsParams p, const float* __restri
         fence_mbar_init();
         fence_proxy_async();
     }
-    rows_load_tables(p, tb);
+    // this thread's (row slot, canvas vector) and the tile columns touching the vector: fixed for the whole kernel
+    const int r = tid / p.wv, xv = tid - r * p.wv;
+    const int x0 = xv * VEC;
+    ColRef cr[kRowsMaxCols];
+    int jn = 0;
+    const bool worker = r < p.RC;
+    if (worker) rows_col_refs<T>(p, xv, cr, jn);
     __syncthreads();
     rows_pdl_launch_dependents();
     rows_pdl_wait();
     if (tid < 32)
         for (int k = 0; k < min(n, p.nslots); ++k) rows_issue<T, false>(p, c.u_begin + k, k, rows_smem, segs, full, (const T*)nullptr);
 
-    // weights of this thread's first task are kept in registers across the units of one row block
-    float wv[8], rv[8];
+    float wv[8], rv[8];     // weights of this thread's pixel vector, kept across the units of one row block
     int cached_b = -1;
     const uint32_t row_bytes = (uint32_t)p.tw * (uint32_t)sizeof(T);
+    const uint32_t smem0 = smem_u32(rows_smem);
     for (int k = 0; k < n; ++k) {
         const int slot = k % p.nslots;
         const int u = c.u_begin + k;
         const int b = u / p.NC, plane = u - b * p.NC;
         const int y0 = b * p.RC, nrows = min(p.H, y0 + p.RC) - y0;
-        const int ntasks = nrows * p.wv;
-        // prefetch the weights of the first task before blocking on the copies
-        if (tid < ntasks && b != cached_b) {
-            const int r = tid / p.wv, xv = tid - r * p.wv;
-            const long long wo = (long long)(y0 + r) * p.W + xv * VEC;
+        const bool active = worker && r < nrows;
+        if (active && b != cached_b) {      // fetched before blocking on the copies: the latency hides behind them
+            const long long wo = (long long)(y0 + r) * p.W + x0;
             if constexpr (VEC == 8) {
                 ldg256(weights + wo, wv);
                 if constexpr (FASTDIV) ldg256(rcp_weights + wo, rv);
@@ -242,39 +292,27 @@ blend_rows_md_kernel(const __grid_constant__ RowsParams p, const float* __restri
             }
             cached_b = b;
         }
-        mbar_wait(&full[slot], (uint32_t)((k / p.nslots) & 1));
-        const SegTable& sg = segs[slot];
-        const unsigned char* sbase = rows_smem + (size_t)slot * p.slot_bytes;
-        for (int task = tid; task < ntasks; task += kRowsThreads) {
-            const int r = task / p.wv, xv = task - r * p.wv;
-            const int y = y0 + r, x0 = xv * VEC;
-            float w8[8], r8[8];
-            if (task == tid) {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) { w8[j] = wv[j]; if constexpr (FASTDIV) r8[j] = rv[j]; }
-            } else {
-                const long long wo = (long long)y * p.W + x0;
-                if constexpr (VEC == 8) {
-                    ldg256(weights + wo, w8);
-                    if constexpr (FASTDIV) ldg256(rcp_weights + wo, r8);
-                } else {
-                    const float4 f = __ldg(reinterpret_cast<const float4*>(weights + wo));
-                    w8[0] = f.x; w8[1] = f.y; w8[2] = f.z; w8[3] = f.w;
-                }
-            }
+        rows_wait_unit(&full[slot], (uint32_t)((k / p.nslots) & 1));
+        if (active) {
+            const SegTable& sg = segs[slot];
+            const uint32_t sbase = smem0 + (uint32_t)slot * (uint32_t)p.slot_bytes;
+            const int y = y0 + r;
             uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-            const int jlo = tb.vcol_lo[xv], jn = tb.vcol_n[xv];
-            for (int q = 0; q < sg.nseg; ++q) {
-                const int rr = y - sg.yy0[q];
-                if ((unsigned)rr >= (unsigned)sg.nr[q]) continue;
-                const unsigned char* seg = sbase + sg.off[q];
-                const int nr = sg.nr[q];
-                for (int j = jlo; j < jlo + jn; ++j) {
-                    const uint4 e = rows_tile_window<T>(seg + (size_t)(j * nr + rr) * row_bytes, x0 - (int)tb.xs[j], p.tw);
-                    acc.x = rows_packed_add<T>(acc.x, e.x);
-                    acc.y = rows_packed_add<T>(acc.y, e.y);
-                    acc.z = rows_packed_add<T>(acc.z, e.z);
-                    acc.w = rows_packed_add<T>(acc.w, e.w);
+            const int nseg = sg.nseg;
+            for (int q = 0; q < nseg; ++q) {
+                const int rr = y - sg.yy0[q], nr = sg.nr[q];
+                if ((unsigned)rr >= (unsigned)nr) continue;
+                const uint32_t colstride = (uint32_t)nr * row_bytes;
+                const uint32_t rowbase = sbase + (uint32_t)sg.off[q] + (uint32_t)rr * row_bytes;
+#pragma unroll
+                for (int cc = 0; cc < kRowsMaxCols; ++cc) {
+                    if (cc < jn) {
+                        const uint4 e = rows_visit<T>(rowbase + (uint32_t)cr[cc].j * colstride, cr[cc]);
+                        acc.x = rows_packed_add<T>(acc.x, e.x);
+                        acc.y = rows_packed_add<T>(acc.y, e.y);
+                        acc.z = rows_packed_add<T>(acc.z, e.z);
+                        acc.w = rows_packed_add<T>(acc.w, e.w);
+                    }
                 }
             }
             // x_out = where(weights > 1, x_buffer / weights, x_buffer): fp32, correctly rounded divide
@@ -283,8 +321,8 @@ blend_rows_md_kernel(const __grid_constant__ RowsParams p, const float* __restri
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 const float a = Vec<T>::get(acc, j);
-                if constexpr (FASTDIV) f[j] = w8[j] > 1.0f ? rows_div_exact_small_int(a, w8[j], r8[j]) : a;
-                else f[j] = w8[j] > 1.0f ? __fdiv_rn(a, w8[j]) : a;
+                if constexpr (FASTDIV) f[j] = wv[j] > 1.0f ? rows_div_exact_small_int(a, wv[j], rv[j]) : a;
+                else f[j] = wv[j] > 1.0f ? __fdiv_rn(a, wv[j]) : a;
             }
             if constexpr (VEC == 8) stg256(out_f32 + o, f);
             else *reinterpret_cast<float4*>(out_f32 + o) = make_float4(f[0], f[1], f[2], f[3]);
@@ -310,19 +348,24 @@ blend_rows_mod_kernel(const __grid_constant__ RowsParams p, const float* __restr
     __shared__ __align__(8) uint64_t full[kRowsMaxSlots];
     __shared__ __align__(8) uint64_t aux_full;
     __shared__ SegTable segs[kRowsMaxSlots];
-    __shared__ RowsTables tb;
+    __shared__ short s_ys[TD_MAX_GRID_DIM];
     const int tid = threadIdx.x;
     const RowsCommon c = rows_partition(p);
     const int n = c.u_end - c.u_begin;
     unsigned char* slots = rows_smem + p.aux_bytes;                         // [gaussian th x tw fp32][slots]
-    const float* s_tw = reinterpret_cast<const float*>(rows_smem);
     if (tid == 0) {
         for (int s = 0; s < p.nslots; ++s) mbar_init(&full[s], 1);
         mbar_init(&aux_full, 1);
         fence_mbar_init();
         fence_proxy_async();
     }
-    rows_load_tables(p, tb);
+    for (int i = tid; i < p.rows; i += kRowsThreads) s_ys[i] = p.ys[i];
+    const int r = tid / p.wv, xv = tid - r * p.wv;
+    const int x0 = xv * VEC;
+    ColRef cr[kRowsMaxCols];
+    int jn = 0;
+    const bool worker = r < p.RC;
+    if (worker) rows_col_refs<T>(p, xv, cr, jn);
     __syncthreads();
     rows_pdl_launch_dependents();
     rows_pdl_wait();
@@ -334,65 +377,55 @@ blend_rows_mod_kernel(const __grid_constant__ RowsParams p, const float* __restr
         __syncwarp();
         for (int k = 0; k < min(n, p.nslots); ++k) rows_issue<T, false>(p, c.u_begin + k, k, slots, segs, full, (const T*)nullptr);
     }
-    float rs0[8];
+    float rs[8];
     int cached_b = -1;
     const uint32_t row_bytes = (uint32_t)p.tw * (uint32_t)sizeof(T);
-    mbar_wait(&aux_full, 0);
+    const uint32_t smem_tw = smem_u32(rows_smem), smem_slots = smem_u32(slots);
+    rows_wait_unit(&aux_full, 0);
     for (int k = 0; k < n; ++k) {
         const int slot = k % p.nslots;
         const int u = c.u_begin + k;
         const int b = u / p.NC, plane = u - b * p.NC;
         const int y0 = b * p.RC, nrows = min(p.H, y0 + p.RC) - y0;
-        const int ntasks = nrows * p.wv;
-        if (tid < ntasks && b != cached_b) {
-            const int r = tid / p.wv, xv = tid - r * p.wv;
-            const long long wo = (long long)(y0 + r) * p.W + xv * VEC;
-            if constexpr (VEC == 8) ldg256(rescale + wo, rs0);
+        const bool active = worker && r < nrows;
+        if (active && b != cached_b) {
+            const long long wo = (long long)(y0 + r) * p.W + x0;
+            if constexpr (VEC == 8) ldg256(rescale + wo, rs);
             else {
                 const float4 f = __ldg(reinterpret_cast<const float4*>(rescale + wo));
-                rs0[0] = f.x; rs0[1] = f.y; rs0[2] = f.z; rs0[3] = f.w;
+                rs[0] = f.x; rs[1] = f.y; rs[2] = f.z; rs[3] = f.w;
             }
             cached_b = b;
         }
-        mbar_wait(&full[slot], (uint32_t)((k / p.nslots) & 1));
-        const SegTable& sg = segs[slot];
-        const unsigned char* sbase = slots + (size_t)slot * p.slot_bytes;
-        for (int task = tid; task < ntasks; task += kRowsThreads) {
-            const int r = task / p.wv, xv = task - r * p.wv;
-            const int y = y0 + r, x0 = xv * VEC;
-            float rs[8];
-            if (task == tid) {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) rs[j] = rs0[j];
-            } else {
-                const long long wo = (long long)y * p.W + x0;
-                if constexpr (VEC == 8) ldg256(rescale + wo, rs);
-                else {
-                    const float4 f = __ldg(reinterpret_cast<const float4*>(rescale + wo));
-                    rs[0] = f.x; rs[1] = f.y; rs[2] = f.z; rs[3] = f.w;
-                }
-            }
+        rows_wait_unit(&full[slot], (uint32_t)((k / p.nslots) & 1));
+        if (active) {
+            const SegTable& sg = segs[slot];
+            const uint32_t sbase = smem_slots + (uint32_t)slot * (uint32_t)p.slot_bytes;
+            const int y = y0 + r;
             float acc[VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j) acc[j] = 0.0f;
-            const int jlo = tb.vcol_lo[xv], jn = tb.vcol_n[xv];
-            for (int q = 0; q < sg.nseg; ++q) {
-                const int rr = y - sg.yy0[q];
-                if ((unsigned)rr >= (unsigned)sg.nr[q]) continue;
-                const unsigned char* seg = sbase + sg.off[q];
-                const int nr = sg.nr[q];
-                const int v = y - (int)tb.ys[sg.band[q]];                  // tile row
-                const float* wrow = s_tw + (size_t)v * p.tw;
-                for (int j = jlo; j < jlo + jn; ++j) {
-                    const int u0 = x0 - (int)tb.xs[j];
-                    const uint4 e = rows_tile_window<T>(seg + (size_t)(j * nr + rr) * row_bytes, u0, p.tw);
+            const int nseg = sg.nseg;
+            for (int q = 0; q < nseg; ++q) {
+                const int rr = y - sg.yy0[q], nr = sg.nr[q];
+                if ((unsigned)rr >= (unsigned)nr) continue;
+                const uint32_t colstride = (uint32_t)nr * row_bytes;
+                const uint32_t rowbase = sbase + (uint32_t)sg.off[q] + (uint32_t)rr * row_bytes;
+                const int v = y - (int)s_ys[sg.band[q]];                            // tile row
+                const uint32_t wrow = smem_tw + (uint32_t)(v * p.tw) * 4u;          // gaussian row in shared memory
 #pragma unroll
-                    for (int m = 0; m < VEC; ++m) {
-                        const int uu = u0 + m;
-                        if ((unsigned)uu < (unsigned)p.tw) {               // elements outside the tile are not touched
-                            const float w = __fmul_rn(wrow[uu], rs[m]);
-                            const float val = __fmul_rn(Vec<T>::get(e, m), w);
-                            acc[m] = round_through<T>(__fadd_rn(acc[m], val));
+                for (int cc = 0; cc < kRowsMaxCols; ++cc) {
+                    if (cc < jn) {
+                        const uint4 e = rows_visit<T>(rowbase + (uint32_t)cr[cc].j * colstride, cr[cc]);
+                        const int u0 = cr[cc].u0;
+#pragma unroll
+                        for (int m = 0; m < VEC; ++m) {
+                            const int uu = u0 + m;
+                            if ((unsigned)uu < (unsigned)p.tw) {           // elements outside the tile are not touched
+                                const float w = __fmul_rn(lds_f32_u32(wrow + (uint32_t)uu * 4u), rs[m]);
+                                const float val = __fmul_rn(Vec<T>::get(e, m), w);
+                                acc[m] = round_through<T>(__fadd_rn(acc[m], val));
+                            }
                         }
                     }
                 }
@@ -419,6 +452,8 @@ blend_rows_mod_kernel(const __grid_constant__ RowsParams p, const float* __restr
 
 // =================================================================================================================
 // Scatter: tiles[(t - tile_begin) * NC + plane, v, u] = x[plane, ys + v, xs + u]
+// A thread owns one vector column `uv` of the tile rows for the whole kernel and walks (tile column, row) pairs with a
+// stride: no division in the loop (pair -> (j, rr) by a multiply-shift).
 // =================================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(kRowsThreads, 1)
@@ -427,7 +462,7 @@ scatter_rows_kernel(const __grid_constant__ RowsParams p, const T* __restrict__ 
     extern __shared__ __align__(128) unsigned char rows_smem[];
     __shared__ __align__(8) uint64_t full[kRowsMaxSlots];
     __shared__ SegTable segs[kRowsMaxSlots];
-    __shared__ RowsTables tb;
+    __shared__ short s_xs[TD_MAX_GRID_DIM], s_ys[TD_MAX_GRID_DIM];
     const int tid = threadIdx.x;
     const RowsCommon c = rows_partition(p);
     const int n = c.u_end - c.u_begin;
@@ -436,36 +471,44 @@ scatter_rows_kernel(const __grid_constant__ RowsParams p, const T* __restrict__ 
         fence_mbar_init();
         fence_proxy_async();
     }
-    rows_load_tables(p, tb);
+    for (int i = tid; i < p.cols; i += kRowsThreads) s_xs[i] = p.xs[i];
+    for (int i = tid; i < p.rows; i += kRowsThreads) s_ys[i] = p.ys[i];
+    const int slot_rows = kRowsThreads / p.twv;              // (column, row) pairs handled per sweep
+    const int ps = tid / p.twv, uv = tid - ps * p.twv;
+    const bool worker = ps < slot_rows;
     __syncthreads();
     rows_pdl_launch_dependents();
     rows_pdl_wait();
     if (tid < 32)
         for (int k = 0; k < min(n, p.nslots); ++k) rows_issue<T, true>(p, c.u_begin + k, k, rows_smem, segs, full, x);
     const uint32_t crow_bytes = (uint32_t)p.W * (uint32_t)sizeof(T);
+    const uint32_t smem0 = smem_u32(rows_smem);
+    const long long plane_elems = (long long)p.th * p.tw;
     for (int k = 0; k < n; ++k) {
         const int slot = k % p.nslots;
-        mbar_wait(&full[slot], (uint32_t)((k / p.nslots) & 1));
-        const SegTable& sg = segs[slot];
-        const unsigned char* sbase = rows_smem + (size_t)slot * p.slot_bytes;
-        const int plane = sg.plane, y0 = sg.y0;
-        for (int q = 0; q < sg.nseg; ++q) {
-            const int i = sg.band[q], nr = sg.nr[q], yy0 = sg.yy0[q];
-            const int per_col = nr * p.twv;
-            const int ntasks = per_col * p.cols;
-            for (int task = tid; task < ntasks; task += kRowsThreads) {
-                const int j = task / per_col, rem = task - j * per_col;
-                const int rr = rem / p.twv, uv = rem - rr * p.twv;
-                const int t = i * p.cols + j;
-                if (t < p.tile_begin || t >= p.tile_end) continue;
-                const int y = yy0 + rr, xx = (int)tb.xs[j] + uv * VEC;
-                const unsigned char* row = sbase + (size_t)(y - y0) * crow_bytes;
-                const int a = xx & ~(VEC - 1), s = xx - a;
-                const uint4 A = lds128(row + a * (int)sizeof(T));
-                uint4 e = A;
-                if (s != 0) e = Vec<T>::window(A, lds128(row + (a + VEC) * (int)sizeof(T)), s);   // xx + VEC <= W: the next chunk exists
-                T* dst = tiles + ((long long)(t - p.tile_begin) * p.NC + plane) * ((long long)p.th * p.tw) + (long long)(y - (int)tb.ys[i]) * p.tw + uv * VEC;
-                stg128_stream(dst, e);
+        rows_wait_unit(&full[slot], (uint32_t)((k / p.nslots) & 1));
+        if (worker) {
+            const SegTable& sg = segs[slot];
+            const uint32_t sbase = smem0 + (uint32_t)slot * (uint32_t)p.slot_bytes;
+            const int plane = sg.plane, y0 = sg.y0, nseg = sg.nseg;
+            for (int q = 0; q < nseg; ++q) {
+                const int i = sg.band[q], nr = sg.nr[q], yy0 = sg.yy0[q];
+                const unsigned magic = ((1u << 20) + (unsigned)nr - 1u) / (unsigned)nr;       // pair / nr for pair < 16384
+                const int npairs = nr * p.cols;
+                const int v0 = yy0 - (int)s_ys[i];
+                for (int pr = ps; pr < npairs; pr += slot_rows) {
+                    const int j = (int)(((unsigned)pr * magic) >> 20), rr = pr - j * nr;
+                    const int t = i * p.cols + j;
+                    if (t < p.tile_begin || t >= p.tile_end) continue;
+                    const int xx = (int)s_xs[j] + uv * VEC;
+                    const int a = xx & ~(VEC - 1), s = xx - a;
+                    const uint32_t addr = sbase + (uint32_t)(yy0 + rr - y0) * crow_bytes + (uint32_t)a * (uint32_t)sizeof(T);
+                    const uint4 A = lds128_u32(addr);
+                    uint4 e = A;
+                    if (s != 0) e = Vec<T>::window(A, lds128_u32(addr + 16u), s);     // xx + VEC <= W: the next chunk exists
+                    T* dst = tiles + ((long long)(t - p.tile_begin) * p.NC + plane) * plane_elems + (long long)(v0 + rr) * p.tw + uv * VEC;
+                    stg128_stream(dst, e);
+                }
             }
         }
         if (k + p.nslots < n) {
@@ -534,7 +577,7 @@ bool rows_plan(const td_grid* g, int N, int C, int es, int budget_bytes, bool sc
                 if (lo < 0) lo = j;
                 ++n;
             }
-        if (n > 255) return false;
+        if (n > kRowsMaxCols) return false;
         p->vcol_lo[v] = (unsigned char)std::max(lo, 0);
         p->vcol_n[v] = (unsigned char)n;
     }
@@ -556,6 +599,8 @@ bool rows_plan(const td_grid* g, int N, int C, int es, int budget_bytes, bool sc
             max_segs = std::max(max_segs, segs);
         }
         if (max_segs > kRowsMaxSegs) continue;
+        if (!scatter && rc * (g->W / VEC) > kRowsThreads) continue;      // blend: one (row, vector) task per thread
+        if (scatter && (g->tile_w / VEC > kRowsThreads || rc * g->cols >= 16384)) continue;
         slot = (slot + 127) & ~127;
         if (slot <= 0) continue;
         const int nslots = std::min(kRowsMaxSlots, budget_bytes / slot);
@@ -577,7 +622,6 @@ bool rows_plan(const td_grid* g, int N, int C, int es, int budget_bytes, bool sc
         if (max_rows == 0) continue;
         double eff = (double)total_rows / ((double)max_rows * sms);
         if (max_units > nslots) eff *= 0.9;                          // not everything in flight at once
-        if (!scatter && rc * (g->W / VEC) > kRowsThreads) eff *= 0.97;   // more than one blend task per thread
         if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && rc > best_rc)) {
             best_eff = eff; best_rc = rc; best_slot = slot; best_nslots = nslots;
         }

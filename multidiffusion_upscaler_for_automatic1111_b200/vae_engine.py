@@ -280,12 +280,14 @@ class TensorCoreBackend:
         k = ops.gemm_nt(x2, wk[0], bias=bk)
         Tp = ops.round_up(T, 8)
         vt = torch.empty((C, Tp), dtype=self.dtype, device=self.device)
+        if Tp != T:
+            vt[:, T:].zero_()          # K of the P V GEMM runs over the padded pitch: P's padding is 0, V's must be finite
         # V^T[c, t] = sum_i Wv[c, i] x[t, i] + bv[c]: the GEMM with the operands swapped, bias per output row
         ops.gemm_nt(wv[0], x2, bias=bv, bias_per_row=True, out=vt[:, :T])
         s = torch.empty((T, Tp), dtype=self.dtype, device=self.device)
         ops.gemm_nt(q, k, alpha=float(int(C) ** -0.5), out=s[:, :T])
         ops.softmax_rows(s, T, out=s)
-        o = ops.gemm_nt(s[:, :T], vt[:, :T])
+        o = ops.gemm_nt(s, vt)         # K = Tp (a multiple of 8; the last partial 64-chunk is zero-filled by the TMA unit)
         wp, bp, *_ = self._conv_w(m.proj_out)
         y = ops.conv2d_nhwc(o.view(1, H, W, C), wp, bp, ksize=1, residual=skip)
         return y

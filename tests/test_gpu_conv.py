@@ -159,3 +159,12 @@ def test_softmax_rows(ops):
     want = torch.softmax(x[:, :cols].float(), dim=1)
     assert (y[:, :cols].float() - want).abs().max() <= 1e-3 * want.max()
     assert float(y[:, cols:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("cluster", ["1", "2", "4"])
+def test_conv3x3_cluster_multicast(ops, monkeypatch, cluster):
+    """Enough pixel tiles (>= 4 per SM) for the CTA-cluster form: the weight tile of a k-step is fetched once per
+    cluster and multicast; odd sizes leave dummy tiles at the end of the list."""
+    monkeypatch.setenv("TD_CONV_CLUSTER", cluster)
+    _conv_case(ops, torch.float16, 1, 259, 333, 128, 256, 3, 1, 200, residual=True)   # 21 x 33 = 693 pixel tiles
+    _conv_case(ops, torch.float16, 1, 168, 336, 64, 128, 3, 1, 210)

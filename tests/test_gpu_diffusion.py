@@ -19,10 +19,10 @@ TMA = 4
 PIPE = 8
 NO_PDL = 32
 ONE_PLANE = 64
-NO_ROWS = 0x400
-# row-block bulk-copy form (default, td_rows.cu), round-1 default (cp.async-staged), persistent pipelined cp.async,
+ROWS = 0x400
+# cp.async-staged (default), row-block bulk-copy form (opt-in, td_rows.cu), persistent pipelined cp.async,
 # TMA-staged, register-staged, scalar kernels
-ALL_PATHS = [0, NO_PDL, NO_ROWS, NO_ROWS | NO_PDL, ONE_PLANE, PIPE, TMA, NO_TMA, FORCE_GENERIC]
+ALL_PATHS = [0, NO_PDL, ROWS, ROWS | NO_PDL, ONE_PLANE, PIPE, TMA, NO_TMA, FORCE_GENERIC]
 
 
 @pytest.fixture(scope="module")
@@ -126,7 +126,7 @@ def test_fast_exact_divide_is_ieee_on_its_domain(dn):
 
 
 @pytest.mark.parametrize("dn", ["f16", "bf16"])
-@pytest.mark.parametrize("flags", [0, NO_ROWS, PIPE, TMA, NO_TMA])
+@pytest.mark.parametrize("flags", [0, ROWS, PIPE, TMA, NO_TMA])
 def test_blend_with_reciprocal_weights_matches_reference(eng, golden_dir, dn, flags):
     g = np.load(os.path.join(golden_dir, "blend_small.npz"))
     for name, (N, C, W, H, tw, th, ov, bs) in zip(g["names"], g["cases"]):
