@@ -569,6 +569,258 @@ def e2e_arm(args, dev, stream, world, rank):
             "api": "MultiDiffusion.kdiff_forward (hooked inner_model.forward), identity denoiser, 25 tile batches"}
 
 
+# ----------------------------------------------------------------------------- cfg4: tiled VAE decode
+VAE_METRIC = "megapixels/sec final image (tiled VAE decode only, 8192x8192 RGB)"
+
+
+def _sd_vae_half(is_decoder: bool, seed: int):
+    """Random-init network with the published Stable-Diffusion autoencoder layout (ch 128, ch_mult (1,2,4,4), 2 res
+    blocks, GroupNorm(32, eps 1e-6), single-head attention in the mid block) and the attribute names the reference
+    walks (scripts/tilevae.py:107-195): synthetic weights, as BASELINE.json asks."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    def norm(c):
+        return nn.GroupNorm(32, c, eps=1e-6, affine=True)
+
+    class Res(nn.Module):
+        def __init__(self, cin, cout):
+            super().__init__()
+            self.in_channels, self.out_channels, self.use_conv_shortcut = cin, cout, False
+            self.norm1, self.conv1 = norm(cin), nn.Conv2d(cin, cout, 3, 1, 1)
+            self.norm2, self.conv2 = norm(cout), nn.Conv2d(cout, cout, 3, 1, 1)
+            if cin != cout:
+                self.nin_shortcut = nn.Conv2d(cin, cout, 1, 1, 0)
+
+        def forward(self, x):
+            h = self.conv2(F.silu(self.norm2(self.conv1(F.silu(self.norm1(x))))))
+            return (self.nin_shortcut(x) if self.in_channels != self.out_channels else x) + h
+
+    class Attn(nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.norm = norm(c)
+            self.q, self.k, self.v, self.proj_out = (nn.Conv2d(c, c, 1) for _ in range(4))
+
+    class Up(nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.with_conv, self.conv = True, nn.Conv2d(c, c, 3, 1, 1)
+
+    class Down(nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.with_conv, self.conv = True, nn.Conv2d(c, c, 3, 2, 0)
+
+    ch, mult, nres = 128, (1, 2, 4, 4), 2
+    net = nn.Module()
+    net.num_resolutions, net.num_res_blocks = len(mult), nres
+    net.mid = nn.Module()
+    if is_decoder:
+        net.give_pre_end, net.tanh_out = False, False
+        cur = ch * mult[-1]
+        net.conv_in = nn.Conv2d(4, cur, 3, 1, 1)
+        net.mid.block_1, net.mid.attn_1, net.mid.block_2 = Res(cur, cur), Attn(cur), Res(cur, cur)
+        ups = []
+        for lvl in reversed(range(len(mult))):
+            lv = nn.Module()
+            blocks = []
+            for _ in range(nres + 1):
+                blocks.append(Res(cur, ch * mult[lvl]))
+                cur = ch * mult[lvl]
+            lv.block = nn.ModuleList(blocks)
+            if lvl != 0:
+                lv.upsample = Up(cur)
+            ups.insert(0, lv)
+        net.up = nn.ModuleList(ups)
+        net.norm_out, net.conv_out = norm(cur), nn.Conv2d(cur, 3, 3, 1, 1)
+    else:
+        net.conv_in = nn.Conv2d(3, ch, 3, 1, 1)
+        cur = ch
+        downs = []
+        for lvl in range(len(mult)):
+            lv = nn.Module()
+            blocks = []
+            for _ in range(nres):
+                blocks.append(Res(cur, ch * mult[lvl]))
+                cur = ch * mult[lvl]
+            lv.block = nn.ModuleList(blocks)
+            if lvl != len(mult) - 1:
+                lv.downsample = Down(cur)
+            downs.append(lv)
+        net.down = nn.ModuleList(downs)
+        net.mid.block_1, net.mid.attn_1, net.mid.block_2 = Res(cur, cur), Attn(cur), Res(cur, cur)
+        net.norm_out, net.conv_out = norm(cur), nn.Conv2d(cur, 8, 3, 1, 1)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, prm in net.named_parameters():
+            if prm.dim() == 4:
+                fan_in = prm.shape[1] * prm.shape[2] * prm.shape[3]
+                prm.copy_((torch.rand(prm.shape, generator=g) * 2 - 1) * (3.0 / fan_in) ** 0.5)
+            elif name.endswith("weight"):
+                prm.copy_(1.0 + 0.25 * (torch.rand(prm.shape, generator=g) * 2 - 1))
+            else:
+                prm.copy_(0.1 * (torch.rand(prm.shape, generator=g) * 2 - 1))
+    net.eval()
+    net.original_forward = None
+    return net
+
+
+def vae_decode_flops(hook, height, width):
+    """Algorithmic FLOPs of one tiled decode: 2 * Cin * Cout * k^2 * output pixels per convolution, 4 * T^2 * C for the
+    attention's QK^T and PV (+ the 1x1 projections), summed over the tiles the hook splits the latent into."""
+    from multidiffusion_upscaler_for_automatic1111_b200 import vae_engine as ve
+    prog = ve.compile_program(hook.net, hook.is_decoder)
+    in_bboxes, _ = hook.split_tiles(height, width)
+    total = 0.0
+    for b in in_bboxes:
+        h, w = b[3] - b[2], b[1] - b[0]
+        for op in prog.ops:
+            if isinstance(op, ve.Conv):
+                if op.upsample_first:
+                    h, w = 2 * h, 2 * w
+                if op.downsample:
+                    h, w = (h - 2) // 2 + 1, (w - 2) // 2 + 1
+                m = op.module
+                total += 2.0 * m.in_channels * m.out_channels * m.kernel_size[0] * m.kernel_size[1] * h * w
+            elif isinstance(op, ve.Skip) and op.module is not None:
+                m = op.module
+                total += 2.0 * m.in_channels * m.out_channels * m.kernel_size[0] * m.kernel_size[1] * h * w
+            elif isinstance(op, ve.Attention):
+                c, t = op.module.q.in_channels, h * w
+                total += 4 * 2.0 * c * c * t + 2 * 2.0 * t * t * c
+    return total
+
+
+def vae_arm(args, rank, world, local_rank):
+    """BASELINE cfg4: tiled VAE decode only, z [1,4,1024,1024] fp16 -> 8192 x 8192 RGB, decoder tile 96 (121 tiles),
+    fast mode (the UI default) unless --vae-slow.  One bench step = one whole decode through `VAEHook`."""
+    from multidiffusion_upscaler_for_automatic1111_b200 import tilevae, vae_engine as ve, vae_ops
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    lat = args.vae_latent
+    net = _sd_vae_half(True, 1).to(dev).half()
+    hook = tilevae.VAEHook(net, 96, True, fast_decoder=not args.vae_slow, fast_encoder=True, color_fix=False)
+    if world > 1:
+        hook.init_tile_shard(None)
+    g = torch.Generator().manual_seed(7)
+    z_host = torch.randn((1, 4, lat, lat), generator=g).half().pin_memory()
+    z = z_host.to(dev)
+    out_host = torch.empty((1, 3, lat * 8, lat * 8), dtype=torch.float16).pin_memory()
+    mp = (lat * 8) ** 2 / 1e6
+    stream = torch.cuda.current_stream(dev)
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        y = hook(z)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    ms = event_time_ms(lambda: [hook(z) for _ in range(steps)], stream)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    sec = float(t.item()) / 1e3 / steps
+
+    def e2e_step():
+        zd = z_host.to(dev, non_blocking=True)
+        out_host.copy_(hook(zd), non_blocking=True)
+    e2e_step(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_ms = event_time_ms(lambda: [e2e_step() for _ in range(steps)], stream)
+    e2e_sec = max(e2e_ms / 1e3, time.perf_counter() - t0) / steps
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        if world > 1:
+            torch.distributed.barrier()
+        return
+
+    flops = vae_decode_flops(hook, lat, lat)
+    tf_burst, tf_sust = 1661.3, 1404.6
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        tf_burst, tf_sust, peak_src = float(pk["bf16_tflops"]), float(pk["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json, cuBLAS bf16)"
+    except Exception:
+        tf_burst, tf_sust, peak_src = 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+    # dominant kernel: the level-0 128 -> 128 3x3 convolution of a full tile (944 x 944), timed alone
+    x = (torch.randn((1, 944, 944, 128), device=dev) * 0.5).half()
+    w = (torch.randn((9, 128, 128), device=dev) * 0.03).half()
+    b = torch.zeros(128, device=dev)
+    yb = torch.empty_like(x)
+    conv = lambda: vae_ops.conv2d_nhwc(x, w, b, ksize=3, pad=(1, 1), out=yb)
+    conv(); torch.cuda.synchronize()
+    t_conv = event_time_ms(lambda: [conv() for _ in range(20)], stream) / 20 * 1e-3
+    conv_flops = 2.0 * 944 * 944 * 128 * 128 * 9
+    # in-run parity: the same fp16 network on a 160 x 160 corner of the latent, tensor-core backend vs module backend
+    zc = z[:, :, :160, :160].contiguous()
+    a_tc = hook(zc).float()
+    orig = ve.pick_backend
+    ve.pick_backend = lambda program, device, dtype: ve.ModuleBackend(program, device, dtype)
+    try:
+        a_mod = hook(zc).float()
+    finally:
+        ve.pick_backend = orig
+    scale = a_mod.abs().max().item()
+    diff = (a_tc - a_mod).abs()
+    line = {
+        "metric": VAE_METRIC, "value": mp / sec, "unit": "MP/s", "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"BASELINE cfg4: tiled VAE decode only, z [1,4,{lat},{lat}] fp16 -> {lat * 8}x{lat * 8} RGB, decoder tile 96, "
+                               f"{len(hook.split_tiles(lat, lat)[0])} tiles, {'slow (GroupNorm barrier per site)' if args.vae_slow else 'fast'} mode, "
+                               "random-init SD-shaped decoder (ch 128, mult 1-2-4-4)",
+                   "backend": hook.backend_name, "l2": "activations of one tile (228 MB at level 0) exceed L2",
+                   "parallelism": "single GPU" if world == 1 else f"VAE tiles round-robin over {world} ranks, all-gather of the output regions"},
+        "clocks": clocks,
+        "e2e": {"value": mp / e2e_sec, "unit": "MP/s", "h2d_bytes_per_step": z_host.numel() * 2, "d2h_bytes_per_step": out_host.numel() * 2,
+                "ms_per_step": e2e_sec * 1e3, "api": "VAEHook.__call__ (hooked decoder forward), pinned-host latent in, pinned-host image out"},
+        "gpu_launches": None,
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (td_conv2d_nhwc, tcgen05 implicit GEMM), 128->128 3x3 on [1,944,944,128]",
+                     "achieved": conv_flops / t_conv / 1e12, "peak": tf_burst, "unit": "TFLOP/s", "frac": conv_flops / t_conv / 1e12 / tf_burst,
+                     "traffic": None, "peak_source": peak_src + ", burst (kernel timed alone)", "algorithmic_flops": conv_flops,
+                     "avg_launch_us": t_conv * 1e6,
+                     "whole_decode": {"algorithmic_flops": flops, "achieved": flops / sec / 1e12, "peak": tf_sust,
+                                      "frac": flops / sec / 1e12 / tf_sust, "peak_source": "sustained (inside a long step)"}},
+        "parity": {"what": "tcgen05 / channels-last backend vs cuDNN-module backend, same fp16 weights, z[:, :, :160, :160] (4 tiles)",
+                   "mean_rel": diff.mean().item() / scale, "max_rel": diff.max().item() / scale},
+        "impl": "b200",
+    }
+    cpu = vae_cpu_baseline(args.cpu_budget)
+    line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+
+
+def vae_cpu_baseline(budget_s: float):
+    """The reference's tiled VAE algorithm on the host cores (oracle restatement, fp32 torch CPU) on a bounded sample:
+    a 96 x 96 latent (768 x 768 px image), decoder tile 48, fast mode."""
+    from oracle import ldm_vae, vae
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = ldm_vae.seeded_init(ldm_vae.Decoder(), 1).eval()
+    z = torch.randn((1, 4, 96, 96), generator=torch.Generator().manual_seed(7))
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        vae.vae_hook_call(net, z, 48, True, True, False)
+    dt = time.perf_counter() - t0
+    return {"value": (96 * 8) ** 2 / 1e6 / dt, "unit": "MP/s", "cores": torch.get_num_threads(), "kind": "port", "seconds": dt,
+            "sample": "one tiled decode of a 96x96 latent (768x768 px, decoder tile 48, fast mode), oracle restatement of "
+                      "scripts/tilevae.py on torch CPU fp32"}
+
+
+def vae_reference_arm(args, rank):
+    if rank != 0:
+        return
+    cpu = vae_cpu_baseline(args.cpu_budget)
+    line = {"impl": "reference", "metric": VAE_METRIC, "value": cpu["value"], "unit": "MP/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+            "ms_per_step": cpu["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": cpu["sample"]}, "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -581,12 +833,19 @@ def main():
     ap.add_argument("--profile-e2e", action="store_true")
     ap.add_argument("--variants", action="store_true", help="print a table of per-kernel micro-timings to stderr")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg4"], help="BASELINE.json config: cfg2 = MultiDiffusion hot path "
+                    "(default, the headline), cfg4 = tiled VAE decode only")
+    ap.add_argument("--vae-latent", type=int, default=1024, help="cfg4: latent edge (1024 -> 8192^2 image)")
+    ap.add_argument("--vae-slow", action="store_true", help="cfg4: slow mode (GroupNorm statistics merged over all tiles at every site)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        reference_arm(args, rank)
+        (vae_reference_arm if args.config == "cfg4" else reference_arm)(args, rank)
+        return
+    if args.config == "cfg4":
+        vae_arm(args, rank, world, local_rank)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         sys.exit(f"--gpus {args.gpus} needs torchrun (WORLD_SIZE={world})")

@@ -236,6 +236,20 @@ int td_blend_multidiffusion_peer(const td_grid* g, const void* const* batch_ptrs
                                  float* x_out, void* x_buffer, const uint32_t* wait_flags, int world,
                                  const uint32_t* wait_value, uint32_t flags, void* stream);
 
+/* Row-strip tile shard: td_blend_multidiffusion restricted to canvas rows [row_begin, row_end) (multiples of 8, or H),
+ * preceded in-kernel by the acquire wait of td_blend_multidiffusion_peer on wait_flags[0 .. wait_count) (wait_count 0: no
+ * wait).  A rank blends only the rows it owns; batch_ptrs has one entry per tile ROW (tile_bs = cols): the rank's own tile
+ * outputs or the halo buffer its neighbours pushed the overlapping tile rows into (entries of tile rows that do not
+ * touch the range are never dereferenced).  Same arithmetic, same tile order: bit-identical to the whole-canvas blend. */
+int td_blend_multidiffusion_rows(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs,
+                                 int N, int C, int tile_dtype, int acc_dtype, const float* weights,
+                                 const float* rcp_weights, float* x_out, void* x_buffer, int row_begin, int row_end,
+                                 const uint32_t* wait_flags, int wait_count, const uint32_t* wait_value,
+                                 uint32_t flags, void* stream);
+/* One warp spins (acquire, system scope, bounded) until flags[i] >= *value for i < count: stream-ordered work after it
+ * sees what the signalling ranks wrote before their td_peer_signal. */
+int td_peer_wait(const uint32_t* flags, int count, const uint32_t* value, void* stream);
+
 /* ------------------------------------------------------------------------- *
  *  DemoFusion extras (tile_methods/demofusion.py).
  * ------------------------------------------------------------------------- */

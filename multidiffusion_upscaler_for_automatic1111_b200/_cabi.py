@@ -101,6 +101,9 @@ _SIGNATURES = {
     "td_peer_signal": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p]),
     "td_blend_multidiffusion_peer": (c_int, [POINTER(TdGrid), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_uint32, c_void_p]),
+    "td_blend_multidiffusion_rows": (c_int, [POINTER(TdGrid), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_uint32, c_void_p]),
+    "td_peer_wait": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "td_dilated_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int32),
                                   POINTER(c_int32), POINTER(c_int32), c_int, c_int, c_void_p]),
     "td_demofusion_combine": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -51,6 +51,7 @@ struct BlendParams {
     const uint32_t* wait_flags;  // tile shard: spin until wait_flags[i] >= *wait_value for i < wait_world
     int wait_world;
     const uint32_t* wait_value;  // this rank's device-side step counter (bumped by td_peer_signal)
+    int py0, py_count;      // cp.async kernels: first patch row and patch-row count of this launch (row-range blend; 0, 0 = all)
     long long tile_stride;  // N*C*th*tw elements
     const void* batch_ptrs[TD_MAX_BATCH_PTRS];
 };
@@ -193,8 +194,10 @@ blend_grid_vec_kernel(const __grid_constant__ BlendParams p, const float* __rest
         if ((int)threadIdx.x < p.wait_world) {
             const uint32_t want = *p.wait_value;
             uint32_t v;
-            do {
+            unsigned long long spins = 0;
+            do {   // bounded: a peer that never signals (crashed / interrupted rank) becomes a launch error, not a hung GPU
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.wait_flags + threadIdx.x) : "memory");
+                if (++spins > (1ull << 31)) __trap();
             } while ((int32_t)(v - want) < 0);
         }
     }
@@ -457,13 +460,14 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
     const GeomParams& g = p.g;
     const int tid = threadIdx.x;
     const int plane = blockIdx.z * PPC;      // first plane of this CTA (the host launches PPC > 1 only if it divides N*C)
-    const int x_lo = blockIdx.x * BX, y_lo = blockIdx.y * kAsY;
+    const int by = (int)blockIdx.y + p.py0;   // patch row (a row-range launch starts at py0)
+    const int x_lo = blockIdx.x * BX, y_lo = by * kAsY;
     pdl_launch_dependents();
 
     // tiles touching this patch: host-computed per patch row / col (uniform constant-bank reads)
-    const int r_lo = p.prow_lo[blockIdx.y], c_lo = p.pcol_lo[blockIdx.x];
+    const int r_lo = p.prow_lo[by], c_lo = p.pcol_lo[blockIdx.x];
     const int nc = p.pcol_n[blockIdx.x];
-    const int nv = g.dbg_no_tiles ? 0 : (int)p.prow_n[blockIdx.y] * nc;   // <= the host's stage count
+    const int nv = g.dbg_no_tiles ? 0 : (int)p.prow_n[by] * nc;   // <= the host's stage count
 
     // this thread's output vector; its weights are fetched now so that their latency hides behind the tile copies
     const int tx = tid % kAsX, ty = tid / kAsX;
@@ -483,8 +487,10 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
         // the barrier below publishes it to the CTA)
         const uint32_t want = *p.wait_value;
         uint32_t v;
-        do {
+        unsigned long long spins = 0;
+        do {   // bounded: a peer that never signals becomes a launch error, not a hung GPU
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.wait_flags + (tid - (kAsThreads - 32))) : "memory");
+            if (++spins > (1ull << 31)) __trap();
         } while ((int32_t)(v - want) < 0);
     }
 
@@ -1395,7 +1401,7 @@ int launch_blend_async_ppc(const BlendParams& bp, const float* weights, const fl
     static SmemOptIn configured;
     int rc = ensure_dyn_smem(blend_md_async_kernel<T, WRITE_BUF, FASTDIV, PPC>, smem, &configured);
     if (rc != TD_OK) return rc;
-    dim3 grid((unsigned)px, (unsigned)py, (unsigned)(planes / PPC));
+    dim3 grid((unsigned)px, (unsigned)(bp.py_count > 0 ? bp.py_count : py), (unsigned)(planes / PPC));
     launch_pdl(blend_md_async_kernel<T, WRITE_BUF, FASTDIV, PPC>, grid, dim3(kAsThreads), (size_t)smem, st, bp, weights, rcp_weights,
                out_f32, (T*)out_buf);
     return TD_OK;
@@ -1537,6 +1543,7 @@ int fill_blend(const td_grid* g, const void* const* batch_ptrs, int num_batches,
     }
     bp->tile_bs = tile_bs;
     bp->wait_flags = nullptr; bp->wait_world = 0; bp->wait_value = nullptr;
+    bp->py0 = 0; bp->py_count = 0;
     bp->bs_magic = magic_u16((unsigned)tile_bs);
     bp->num_batches = num_batches;
     bp->tile_stride = (long long)N * C * g->tile_h * g->tile_w;
@@ -1641,6 +1648,43 @@ extern "C" int td_blend_multidiffusion(const td_grid* g, const void* const* batc
         }
     }
     return dispatch_generic<MODE_MD>(tile_dtype, acc_dtype, bp, weights, nullptr, nullptr, x_out, x_buffer, s);
+}
+
+extern "C" int td_blend_multidiffusion_rows(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N,
+                                            int C, int tile_dtype, int acc_dtype, const float* weights, const float* rcp_weights,
+                                            float* x_out, void* x_buffer, int row_begin, int row_end, const uint32_t* wait_flags,
+                                            int wait_count, const uint32_t* wait_value, uint32_t flags, void* stream) {
+    BlendParams bp;
+    tl_pdl = !(flags & TD_FLAG_NO_PDL);
+    tl_ppc_max = (flags & TD_FLAG_ONE_PLANE) ? 1 : TD_AS_PPC;
+    int st = fill_blend(g, batch_ptrs, num_batches, tile_bs, N, C, tile_dtype, acc_dtype, &bp);
+    if (st != TD_OK) return st;
+    if (weights == nullptr || x_out == nullptr) { td_set_error("td_blend_multidiffusion_rows: null weights / x_out"); return TD_ERR_INVALID_ARG; }
+    if (row_begin < 0 || row_end > g->H || row_begin > row_end || row_begin % 8 != 0 || (row_end % 8 != 0 && row_end != g->H)) {
+        td_set_error("td_blend_multidiffusion_rows: rows [%d,%d) must lie in [0,%d) on multiples of 8", row_begin, row_end, g->H);
+        return TD_ERR_INVALID_ARG;
+    }
+    if (wait_count < 0 || wait_count > TD_MAX_PEERS || (wait_count > 0 && (wait_flags == nullptr || wait_value == nullptr))) {
+        td_set_error("td_blend_multidiffusion_rows: bad wait table");
+        return TD_ERR_INVALID_ARG;
+    }
+    if (row_begin == row_end) return TD_OK;
+    if (!blend_vec_ok(bp, tile_dtype, acc_dtype, {weights, rcp_weights, x_out, x_buffer})) {
+        td_set_error("td_blend_multidiffusion_rows: needs the vector path (same tile / canvas dtype, W and tile_w multiples of the vector, 16-byte aligned buffers)");
+        return TD_ERR_UNSUPPORTED;
+    }
+    bp.py0 = row_begin / 8;
+    bp.py_count = (row_end - row_begin + 7) / 8;
+    if (wait_count > 0) { bp.wait_flags = wait_flags; bp.wait_world = wait_count; bp.wait_value = wait_value; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    switch (tile_dtype) {
+        case TD_F16: rc = try_launch_blend_async<__half>(g, bp, weights, rcp_weights, x_out, x_buffer, false, s); break;
+        case TD_BF16: rc = try_launch_blend_async<__nv_bfloat16>(g, bp, weights, rcp_weights, x_out, x_buffer, false, s); break;
+        default: rc = try_launch_blend_async<float>(g, bp, weights, nullptr, x_out, x_buffer, false, s); break;
+    }
+    if (rc == 1) { td_set_error("td_blend_multidiffusion_rows: geometry outside the cp.async kernel's limits"); return TD_ERR_UNSUPPORTED; }
+    return rc;
 }
 
 extern "C" int td_debug_check_fast_div(int dtype, int max_w, unsigned long long* mismatches_dev, void* stream) {

@@ -34,6 +34,20 @@ __global__ void peer_signal_kernel(const __grid_constant__ SignalTable tbl, int 
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(tbl.ptrs[t] + rank), "r"(v) : "memory");
 }
 
+// One warp: lane i spins until flags[i] >= *value (acquire, system scope).  Stream-ordered work after this kernel sees
+// everything the signalling ranks wrote before their td_peer_signal.  Bounded spin: a missing peer traps (launch error).
+__global__ void peer_wait_kernel(const uint32_t* flags, int count, const uint32_t* value) {
+    const int t = threadIdx.x;
+    if (t >= count) return;
+    const uint32_t want = *value;
+    uint32_t v;
+    unsigned long long spins = 0;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + t) : "memory");
+        if (++spins > (1ull << 31)) __trap();
+    } while ((int32_t)(v - want) < 0);
+}
+
 int cuda_fail(const char* what, cudaError_t e) {
     td_set_error("%s: %s", what, cudaGetErrorString(e));
     return TD_ERR_CUDA;
@@ -93,4 +107,15 @@ extern "C" int td_peer_signal(void* const* flag_ptrs, int world, int rank, uint3
     peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(tbl, world, rank, step_counter);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? TD_OK : cuda_fail("td_peer_signal", e);
+}
+
+extern "C" int td_peer_wait(const uint32_t* flags, int count, const uint32_t* value, void* stream) {
+    if (count < 0 || count > TD_MAX_PEERS || (count > 0 && (flags == nullptr || value == nullptr))) {
+        td_set_error("td_peer_wait: bad arguments");
+        return TD_ERR_INVALID_ARG;
+    }
+    if (count == 0) return TD_OK;
+    peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, count, value);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? TD_OK : cuda_fail("td_peer_wait", e);
 }

@@ -151,3 +151,295 @@ def blend_multidiffusion_peer(g, exchange: PeerExchange, parity: int, shard: Til
                                                ctypes.c_void_p(exchange.flag_ptrs[exchange.rank]), exchange.world,
                                                ctypes.c_void_p(exchange.counter_ptr), 0, _cabi.current_stream_ptr(dev)))
     return x_out
+
+
+# ===================================================================================================================
+# Row-strip tile shard with halo-only exchange (the default multi-GPU form of MultiDiffusion)
+# ===================================================================================================================
+class StripShard:
+    """Row-strip partition of a grid plan over `world` ranks (pure bookkeeping, no device work).
+
+    Rank r denoises the tiles of a contiguous run of tile ROWS ("bands") and owns the canvas rows
+    `[B[r], B[r+1])`, B[r] = the first band's origin rounded down to a multiple of 8 (B[0] = 0, B[world] = H).  A canvas
+    row is covered by the bands whose extent `[ys[i], ys[i] + th)` contains it; for a row of rank r these are its own
+    bands and bands of LOWER ranks that reach down into the strip (never higher ones: they start at or below
+    B[r+1]).  So per sampler step
+      * tile halo, down the ranks: rank p sends rank q > p the rows `[v0, v1)` of every tile of band i that fall
+        into q's strip (`halo_out` / `halo_in`) -- at BASELINE cfg2 about 54 tile rows per boundary instead of the
+        whole tile list;
+      * latent halo, up the ranks: rank r scatters from canvas rows `[ys[first band], ys[last band] + th)`, which
+        reach into the strips of higher ranks; they send those rows of the blended latent back (`x_out` / `x_in`).
+    Every pixel is blended by exactly one rank, with the covering tiles in the same ascending order as on one GPU:
+    the union of the strips is bit-identical to the single-GPU latent."""
+
+    def __init__(self, ys: Sequence[int], cols: int, tile_h: int, H: int, rank: int, world: int):
+        if not (0 <= rank < world):
+            raise ValueError(f"rank {rank} outside world {world}")
+        rows = len(ys)
+        self.rank, self.world, self.rows, self.cols, self.tile_h, self.H = rank, world, rows, cols, tile_h, H
+        self.ys = [int(v) for v in ys]
+        base, extra = divmod(rows, world)
+        counts = [base + (1 if r < extra else 0) for r in range(world)]
+        self.band_begin = [sum(counts[:r]) for r in range(world)]
+        self.band_end = [self.band_begin[r] + counts[r] for r in range(world)]
+        B = []
+        for r in range(world):
+            if counts[r] == 0:
+                B.append(H)
+            else:
+                B.append(0 if self.band_begin[r] == 0 else self.ys[self.band_begin[r]] // 8 * 8)
+        B.append(H)
+        for r in range(world - 1, -1, -1):      # monotone (overlap > tile pitch could put a later origin first)
+            B[r] = min(B[r], B[r + 1])
+        self.B = B
+
+    # ---- per-rank views ---------------------------------------------------------------------------------------
+    def bands(self, r: Optional[int] = None) -> range:
+        r = self.rank if r is None else r
+        return range(self.band_begin[r], self.band_end[r])
+
+    def tile_range(self, r: Optional[int] = None):
+        r = self.rank if r is None else r
+        return self.band_begin[r] * self.cols, self.band_end[r] * self.cols
+
+    def strip(self, r: Optional[int] = None):
+        r = self.rank if r is None else r
+        return self.B[r], self.B[r + 1]
+
+    def owner_of_band(self, i: int) -> int:
+        for r in range(self.world):
+            if self.band_begin[r] <= i < self.band_end[r]:
+                return r
+        raise IndexError(i)
+
+    def halo_in(self, r: Optional[int] = None):
+        """[(band i, owner rank, v0, v1)]: tile rows [v0, v1) of every tile of band i (not r's own) that rank r blends."""
+        r = self.rank if r is None else r
+        lo, hi = self.strip(r)
+        out = []
+        if hi <= lo:
+            return out
+        for i in range(self.rows):
+            if self.band_begin[r] <= i < self.band_end[r]:
+                continue
+            v0, v1 = max(0, lo - self.ys[i]), min(self.tile_h, hi - self.ys[i])
+            if v1 > v0:
+                out.append((i, self.owner_of_band(i), v0, v1))
+        return out
+
+    def halo_out(self, r: Optional[int] = None):
+        """[(band i, destination rank, v0, v1)] of rank r's own bands."""
+        r = self.rank if r is None else r
+        return [(i, q, v0, v1) for q in range(self.world) if q != r for (i, p, v0, v1) in self.halo_in(q) if p == r]
+
+    def scatter_rows(self, r: Optional[int] = None):
+        """Canvas rows rank r reads when it scatters its tiles."""
+        r = self.rank if r is None else r
+        if self.band_end[r] == self.band_begin[r]:
+            return 0, 0
+        return self.ys[self.band_begin[r]], self.ys[self.band_end[r] - 1] + self.tile_h
+
+    def x_in(self, r: Optional[int] = None):
+        """[(owner rank q, y0, y1)]: blended-latent rows outside r's strip that r needs for its next scatter."""
+        r = self.rank if r is None else r
+        lo, hi = self.scatter_rows(r)
+        out = []
+        for q in range(self.world):
+            if q == r:
+                continue
+            a, b = max(lo, self.B[q]), min(hi, self.B[q + 1])
+            if b > a:
+                out.append((q, a, b))
+        return out
+
+    def x_out(self, r: Optional[int] = None):
+        r = self.rank if r is None else r
+        return [(p, a, b) for p in range(self.world) if p != r for (q, a, b) in self.x_in(p) if q == r]
+
+
+class _PeerFlags:
+    """One flag array + device-side step counter per rank, mapped into every rank (see PeerExchange)."""
+
+    def __init__(self, device, group):
+        self.device, self.group = device, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        with torch.cuda.device(device):
+            self._buf = _RawCudaBuffer(256)
+        self._opened: List[int] = []
+
+    def handle(self) -> bytes:
+        return self._buf.handle()
+
+    def open(self, handles: Sequence[bytes]):
+        self.ptrs = [0] * self.world
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs[r] = self._buf.ptr
+                continue
+            p = ctypes.c_void_p()
+            check(lib.td_ipc_open(ctypes.create_string_buffer(h, len(h)), ctypes.byref(p)))
+            self.ptrs[r] = p.value
+            self._opened.append(p.value)
+
+    @property
+    def counter_ptr(self) -> int:
+        return self._buf.ptr + 128
+
+    def signal(self, targets: Sequence[int]):
+        """Bump this rank's counter and publish it into slot `rank` of the flag arrays of `targets` (and its own)."""
+        tbl = [self.ptrs[r] if (r in targets or r == self.rank) else self.ptrs[self.rank] for r in range(self.world)]
+        table = (ctypes.c_void_p * self.world)(*tbl)
+        with torch.cuda.device(self.device):
+            check(lib.td_peer_signal(table, self.world, self.rank, ctypes.c_void_p(self.counter_ptr), _cabi.current_stream_ptr(self.device)))
+
+    def wait_args(self, first: int, count: int):
+        """(flags pointer, count, value pointer) for a wait on ranks [first, first + count)."""
+        return ctypes.c_void_p(self.ptrs[self.rank] + 4 * first), count, ctypes.c_void_p(self.counter_ptr)
+
+    def wait(self, first: int, count: int):
+        f, c, v = self.wait_args(first, count)
+        with torch.cuda.device(self.device):
+            check(lib.td_peer_wait(f, c, v, _cabi.current_stream_ptr(self.device)))
+
+    def close(self):
+        for p in self._opened:
+            lib.td_ipc_close(ctypes.c_void_p(p))
+        self._opened = []
+        self._buf.free()
+
+
+class StripExchange:
+    """Device side of the row-strip shard: the halo buffer and the blended latent of every rank are cudaMalloc'd
+    and mapped into their neighbours through CUDA IPC; halos are PUSHED (strided copies with peer destinations, over
+    NVLink), published with a release store of the step counter, and awaited inside the blend kernel / by a one-warp
+    wait kernel.  No NCCL call on the data path; every launch is replayable from a CUDA graph."""
+
+    def __init__(self, shard: StripShard, N: int, C: int, tile_w: int, W: int, dtype: torch.dtype, device: torch.device, group=None):
+        self.shard, self.N, self.C, self.tw, self.W, self.dtype, self.device, self.group = shard, N, C, tile_w, W, dtype, device, group
+        sh = shard
+        self.es = torch.empty((), dtype=dtype).element_size()
+        self.band_elems = sh.cols * N * C * sh.tile_h * tile_w                 # one band of tiles [cols*N, C, th, tw]
+        self.halo_bands = [i for (i, _, _, _) in sh.halo_in()]
+        n_own = len(sh.bands())
+        with torch.cuda.device(device):
+            self._own = torch.empty(max(1, n_own) * self.band_elems, dtype=dtype, device=device)
+            self._halo = _RawCudaBuffer(max(1, len(self.halo_bands)) * self.band_elems * self.es)
+            self._xout = _RawCudaBuffer(N * C * sh.H * W * 4)
+            self.flags_tiles, self.flags_x = _PeerFlags(device, group), _PeerFlags(device, group)
+            torch.cuda.synchronize(device)
+        mine = [self._halo.handle(), self._xout.handle(), self.flags_tiles.handle(), self.flags_x.handle(), self.halo_bands]
+        everyone: List[Optional[list]] = [None] * sh.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self._opened: List[int] = []
+        self.peer_halo, self.peer_xout, self.peer_halo_bands = [0] * sh.world, [0] * sh.world, [None] * sh.world
+        for r in range(sh.world):
+            self.peer_halo_bands[r] = everyone[r][4]
+            if r == sh.rank:
+                self.peer_halo[r], self.peer_xout[r] = self._halo.ptr, self._xout.ptr
+                continue
+            for slot, h in ((self.peer_halo, everyone[r][0]), (self.peer_xout, everyone[r][1])):
+                p = ctypes.c_void_p()
+                check(lib.td_ipc_open(ctypes.create_string_buffer(h, len(h)), ctypes.byref(p)))
+                slot[r] = p.value
+                self._opened.append(p.value)
+        self.flags_tiles.open([e[2] for e in everyone])
+        self.flags_x.open([e[3] for e in everyone])
+        self.x_out = self._xout.tensor(device).view(torch.float32).view(N, C, sh.H, W)
+        self._senders = sorted({p for (_, p, _, _) in sh.halo_in()})
+        self._x_senders = sorted({q for (q, _, _) in sh.x_in()})
+        dist.barrier(group=group)
+
+    # ---- this rank's tile outputs -----------------------------------------------------------------------------
+    def own_tiles(self) -> torch.Tensor:
+        """[(own bands * cols) * N, C, th, tw]: where the UNet's outputs of this rank's tiles go (tile-major)."""
+        sh = self.shard
+        n = len(sh.bands()) * sh.cols * self.N
+        return self._own[:n * self.C * sh.tile_h * self.tw].view(n, self.C, sh.tile_h, self.tw)
+
+    def _copy_rows(self, src_ptr: int, dst_ptr: int, planes: int, rows: int, cols: int, src_plane: int, src_pitch: int, dst_plane: int,
+                   dst_pitch: int, dtype: torch.dtype):
+        with torch.cuda.device(self.device):
+            check(lib.td_copy_region(ctypes.c_void_p(src_ptr), ctypes.c_void_p(dst_ptr), planes, rows, cols, src_plane, src_pitch, dst_plane,
+                                     dst_pitch, _cabi.dtype_code(dtype), _cabi.current_stream_ptr(self.device)))
+
+    def push_tile_halos(self):
+        """Rows [v0, v1) of every tile of my band i -> the halo slot of band i on rank q (peer memory), then signal."""
+        sh = self.shard
+        plane = sh.tile_h * self.tw
+        planes = sh.cols * self.N * self.C
+        targets = set()
+        for (i, q, v0, v1) in sh.halo_out():
+            src = self._own.data_ptr() + ((i - sh.band_begin[sh.rank]) * self.band_elems + v0 * self.tw) * self.es
+            slot = self.peer_halo_bands[q].index(i)
+            dst = self.peer_halo[q] + (slot * self.band_elems + v0 * self.tw) * self.es
+            self._copy_rows(src, dst, planes, v1 - v0, self.tw, plane, self.tw, plane, self.tw, self.dtype)
+            targets.add(q)
+        self.flags_tiles.signal(sorted(targets))
+
+    def band_pointer_table(self):
+        """One pointer per tile row for td_blend_multidiffusion_rows: own band, halo slot, or (unused) my buffer."""
+        sh = self.shard
+        ptrs = []
+        for i in range(sh.rows):
+            if sh.band_begin[sh.rank] <= i < sh.band_end[sh.rank]:
+                ptrs.append(self._own.data_ptr() + (i - sh.band_begin[sh.rank]) * self.band_elems * self.es)
+            elif i in self.halo_bands:
+                ptrs.append(self._halo.ptr + self.halo_bands.index(i) * self.band_elems * self.es)
+            else:
+                ptrs.append(self._own.data_ptr())
+        return (ctypes.c_void_p * sh.rows)(*ptrs)
+
+    def blend(self, g, weights: torch.Tensor, rcp_weights: Optional[torch.Tensor], flags: int = 0) -> torch.Tensor:
+        """Blend this rank's strip into its IPC-mapped latent buffer (waits in-kernel for the tile halos)."""
+        sh = self.shard
+        lo, hi = sh.strip()
+        first = self._senders[0] if self._senders else 0
+        count = (self._senders[-1] - first + 1) if self._senders else 0
+        f, c, v = self.flags_tiles.wait_args(first, count)
+        if not hasattr(self, "_ptr_table"):
+            self._ptr_table = self.band_pointer_table()
+        with torch.cuda.device(self.device):
+            check(lib.td_blend_multidiffusion_rows(ctypes.byref(g), self._ptr_table, sh.rows, sh.cols, self.N, self.C, _cabi.dtype_code(self.dtype),
+                                                   _cabi.dtype_code(self.dtype), weights.data_ptr(),
+                                                   rcp_weights.data_ptr() if rcp_weights is not None else None, self.x_out.data_ptr(), None,
+                                                   lo, hi, f if count else None, count, v if count else None, int(flags),
+                                                   _cabi.current_stream_ptr(self.device)))
+        return self.x_out
+
+    def push_x_halos_and_wait(self):
+        """Rows of my strip that lower ranks scatter from -> their latent buffers; then wait for mine to arrive."""
+        sh = self.shard
+        targets = set()
+        plane = sh.H * self.W
+        for (p, a, b) in sh.x_out():
+            off = a * self.W * 4
+            self._copy_rows(self._xout.ptr + off, self.peer_xout[p] + off, self.N * self.C, b - a, self.W, plane, self.W, plane, self.W, torch.float32)
+            targets.add(p)
+        self.flags_x.signal(sorted(targets))
+        if self._x_senders:
+            first = self._x_senders[0]
+            self.flags_x.wait(first, self._x_senders[-1] - first + 1)
+
+    def gather_latent(self, x: torch.Tensor) -> torch.Tensor:
+        """All ranks' strips of `x` (any tensor laid out like the latent) -> the full latent on every rank."""
+        sh = self.shard
+        rows = max(sh.B[r + 1] - sh.B[r] for r in range(sh.world))
+        send = torch.zeros((x.shape[0], x.shape[1], rows, x.shape[3]), dtype=x.dtype, device=x.device)
+        lo, hi = sh.strip()
+        if hi > lo:
+            send[:, :, :hi - lo] = x[:, :, lo:hi]
+        recv = torch.empty((sh.world,) + tuple(send.shape), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group)
+        out = torch.empty_like(x)
+        for r in range(sh.world):
+            a, b = sh.strip(r)
+            if b > a:
+                out[:, :, a:b] = recv[r][:, :, :b - a]
+        return out
+
+    def close(self):
+        for p in self._opened:
+            lib.td_ipc_close(ctypes.c_void_p(p))
+        self._opened = []
+        self.flags_tiles.close(); self.flags_x.close()
+        self._halo.free(); self._xout.free()

@@ -98,7 +98,7 @@ def merge_tile_stats(vars_: Sequence[torch.Tensor], means: Sequence[torch.Tensor
     """tilevae.py:320-335: pixel-count weighted average of the per-tile variances and means."""
     var = torch.vstack(list(vars_))
     mean = torch.vstack(list(means))
-    px = torch.tensor(list(pixels), dtype=torch.float32) / max(pixels)
+    px = torch.tensor(list(pixels), dtype=torch.float32, device=var.device) / max(pixels)
     px = (px / px.sum()).unsqueeze(1)
     return (var * px).sum(dim=0), (mean * px).sum(dim=0)
 
