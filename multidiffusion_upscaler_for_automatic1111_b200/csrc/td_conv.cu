@@ -53,7 +53,12 @@ struct ConvParams {
     int Cout;                  // real output channels (bias / residual guard)
     int BN;                    // Cout block = UMMA N (16..256, multiple of 16)
     int n_blocks;              // ceil(Cout / BN)
-    int BW, BH;                // pixel patch (BW * BH == 128)
+    int BW, BH;                // pixel patch of one CTA tile: BW * BH == 128 * MT
+    int MT;                    // 128-pixel sub-tiles per CTA tile (1 or 2): they share the weight tile of a k-step, which
+                               // halves the weight bytes an SM pulls per FLOP (the kernel is bound by L2 -> SM bytes)
+    int BWs, BHs;              // sub-tile shape (store box): 16 x 8 image rows, or 128 x 1 for a GEMM
+    int sub_dx, sub_dy;        // origin of sub-tile mt inside the patch: (mt * sub_dx, mt * sub_dy)
+    int acc_stages;            // accumulator stages in TMEM: 512 / (MT * BN) capped at 2
     int tiles_x, tiles_y;
     int num_tiles;             // NI * tiles_y * tiles_x * n_blocks
     int stages;
@@ -205,7 +210,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __shared__ uint32_t tmem_base_slot;
     const uint32_t smem0 = (smem_u32(conv_smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
     const int stage_b = p.BN * 128;
-    const uint32_t stage_bytes = (uint32_t)(kConvStageA + stage_b);
+    const uint32_t stage_a = (uint32_t)(p.MT * kConvStageA);
+    const uint32_t stage_bytes = stage_a + (uint32_t)stage_b;
+    const uint32_t acc_cols = (uint32_t)(p.MT * p.BN);                      // TMEM columns of one accumulator stage
     const uint32_t store0 = smem0 + (uint32_t)p.stages * stage_bytes;       // two staging buffers for the TMA store
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int crank = p.cluster > 1 ? (int)cluster_rank() : 0;
@@ -248,9 +255,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
                             tma_load_4d(sa, &map_a, kc * kConvBK, x0 + tx, y0 + ty, c.img, &full_bar[stage]);
                             if (p.cluster == 1)
-                                tma_load_3d_u32(sa + kConvStageA, &map_b, kc * kConvBK, c.nb * p.BN, tap, &full_bar[stage]);
+                                tma_load_3d_u32(sa + stage_a, &map_b, kc * kConvBK, c.nb * p.BN, tap, &full_bar[stage]);
                             else
-                                tma_load_3d_mcast(sa + kConvStageA + (uint32_t)(crank * slice_rows * 128), &map_b, kc * kConvBK,
+                                tma_load_3d_mcast(sa + stage_a + (uint32_t)(crank * slice_rows * 128), &map_b, kc * kConvBK,
                                                   c.nb * p.BN + crank * slice_rows, tap, &full_bar[stage], cmask);
                             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                         }
@@ -265,21 +272,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int g = cid; g < num_groups; g += nclusters) {
                 mbar_wait(&acc_empty[as], aphase ^ 1u);              // epilogue has drained this accumulator stage
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+                const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
-                    const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + kConvStageA);
+                    const uint64_t db = umma_desc_sw128(sa + stage_a);
+                    for (int mt = 0; mt < p.MT; ++mt) {             // the sub-tiles of the patch share this k-step's weight tile
+                        const uint64_t da = umma_desc_sw128(sa + (uint32_t)(mt * kConvStageA));
 #pragma unroll
-                    for (int k = 0; k < kConvBK / 16; ++k)          // +32 bytes along K inside the swizzle row = +2 in the address field
-                        tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kConvBK / 16; ++k)      // +32 bytes along K inside the swizzle row = +2 in the address field
+                            tc_mma_f16(d_tmem + (uint32_t)(mt * p.BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+                    }
                     if (p.cluster == 1) tc_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs have read it
                     else tc_commit_mcast(&empty_bar[stage], cmask);    // ... in every CTA of the cluster
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
                 tc_commit(&acc_full[as]);                             // accumulator complete -> epilogue
-                if (++as == 2) { as = 0; aphase ^= 1u; }
+                if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
             }
         }
     } else if (warp >= 4) {
@@ -287,76 +297,93 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int q = warp & 3;                       // TMEM lane quarter of this warp
         const int row = q * 32 + lane;                // accumulator row = pixel index inside the tile
         const int et = threadIdx.x - 128;             // 0..127
-        const int ly = row / p.BW, lx = row - ly * p.BW;
         int as = 0; uint32_t aphase = 0;
         int buf = 0;
         for (int g = cid; g < num_groups; g += nclusters) {
             const TileCoord c = decode_tile(p, g, crank);
-            const int ox = c.px * p.BW + lx, oy = c.py * p.BH + ly;
-            const bool pix_ok = ox < p.OW && oy < p.OH && c.img < p.NI;
-            const long long pix = ((long long)c.img * p.OH + oy) * p.OW + ox;
             mbar_wait(&acc_full[as], aphase);
             tc_fence_after();
             const int nchunks = p.BN / p.chunk_cols;
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const int col0 = c.nb * p.BN + ch * p.chunk_cols;
-                // the staging buffer about to be overwritten must have been read by its previous TMA store
-                if (et == 0) bulk_wait_read<1>();
-                named_bar_sync(1, 128);
-                const uint32_t sbuf = store0 + (uint32_t)buf * kConvStoreBuf;
-                for (int g = 0; g < p.chunk_cols / 16; ++g) {
-                    uint32_t r[16];
-                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + ch * p.chunk_cols + g * 16), r);
-                    tc_wait_ld();
-                    float v[16];
-                    const int cb = col0 + g * 16;
+            for (int mt = 0; mt < p.MT; ++mt) {
+                const int pidx = mt * kConvBM + row;          // pixel index inside the patch (= shared-memory row of the A box)
+                const int ly = pidx / p.BW, lx = pidx - ly * p.BW;
+                const int ox = c.px * p.BW + lx, oy = c.py * p.BH + ly;
+                const bool pix_ok = ox < p.OW && oy < p.OH && c.img < p.NI;
+                const long long pix = ((long long)c.img * p.OH + oy) * p.OW + ox;
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    const int col0 = c.nb * p.BN + ch * p.chunk_cols;
+                    // the staging buffer about to be overwritten must have been read by its previous TMA store
+                    if (et == 0) bulk_wait_read<1>();
+                    named_bar_sync(1, 128);
+                    const uint32_t sbuf = store0 + (uint32_t)buf * kConvStoreBuf;
+                    for (int g16 = 0; g16 < p.chunk_cols / 16; ++g16) {
+                        uint32_t r[16];
+                        __syncwarp();
+                        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * acc_cols + (uint32_t)(mt * p.BN + ch * p.chunk_cols + g16 * 16), r);
+                        tc_wait_ld();
+                        float v[16];
+                        const int cb = col0 + g16 * 16;
+                        if (bias != nullptr && !p.bias_per_row && cb + 16 <= p.Cout) {      // 16 bias values: four 128-bit loads
+                            const float4* bp4 = reinterpret_cast<const float4*>(bias + cb);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float b = 0.0f;
-                        if (bias != nullptr) {
-                            if (p.bias_per_row) b = pix_ok ? __ldg(bias + pix) : 0.0f;
-                            else b = (cb + j < p.Cout) ? __ldg(bias + cb + j) : 0.0f;
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 b4 = __ldg(bp4 + j4);
+                                v[4 * j4 + 0] = __fmaf_rn(__uint_as_float(r[4 * j4 + 0]), p.alpha, b4.x);
+                                v[4 * j4 + 1] = __fmaf_rn(__uint_as_float(r[4 * j4 + 1]), p.alpha, b4.y);
+                                v[4 * j4 + 2] = __fmaf_rn(__uint_as_float(r[4 * j4 + 2]), p.alpha, b4.z);
+                                v[4 * j4 + 3] = __fmaf_rn(__uint_as_float(r[4 * j4 + 3]), p.alpha, b4.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float b = 0.0f;
+                                if (bias != nullptr) {
+                                    if (p.bias_per_row) b = pix_ok ? __ldg(bias + pix) : 0.0f;
+                                    else b = (cb + j < p.Cout) ? __ldg(bias + cb + j) : 0.0f;
+                                }
+                                v[j] = __fmaf_rn(__uint_as_float(r[j]), p.alpha, b);
+                            }
                         }
-                        v[j] = __fmaf_rn(__uint_as_float(r[j]), p.alpha, b);
-                    }
-                    if (residual != nullptr && pix_ok && cb + 16 <= p.Cout) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(residual + pix * p.res_pitch + cb);
-                        const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-                        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                        if (residual != nullptr && pix_ok && cb + 16 <= p.Cout) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(residual + pix * p.res_pitch + cb);
+                            const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            v[2 * j] += unpack_lo(rw[j], p.is_bf16);
-                            v[2 * j + 1] += unpack_hi(rw[j], p.is_bf16);
+                            for (int j = 0; j < 8; ++j) {
+                                v[2 * j] += unpack_lo(rw[j], p.is_bf16);
+                                v[2 * j + 1] += unpack_hi(rw[j], p.is_bf16);
+                            }
+                        }
+                        uint32_t o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = pack2(v[2 * j], v[2 * j + 1], p.is_bf16);
+                        // 16 columns = two 16-byte chunks (2 g16, 2 g16 + 1) of this row
+                        if (p.chunk_cols == 64) {      // 128-byte rows, 128-byte swizzle: chunk index XOR (row & 7)
+                            const uint32_t rb = sbuf + (uint32_t)row * 128u;
+                            const uint32_t c0 = (uint32_t)((2 * g16) ^ (row & 7)) << 4, c1 = (uint32_t)((2 * g16 + 1) ^ (row & 7)) << 4;
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb + c0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb + c1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+                        } else {                       // narrow outputs: dense rows of chunk_cols * 2 bytes, no swizzle
+                            const uint32_t rb = sbuf + (uint32_t)row * (uint32_t)(p.chunk_cols * 2) + (uint32_t)g16 * 32u;
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb + 16u), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
                         }
                     }
-                    uint32_t o[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = pack2(v[2 * j], v[2 * j + 1], p.is_bf16);
-                    // 16 columns = two 16-byte chunks (2g, 2g+1) of this row
-                    if (p.chunk_cols == 64) {      // 128-byte rows, 128-byte swizzle: chunk index XOR (row & 7)
-                        const uint32_t rb = sbuf + (uint32_t)row * 128u;
-                        const uint32_t c0 = (uint32_t)((2 * g) ^ (row & 7)) << 4, c1 = (uint32_t)((2 * g + 1) ^ (row & 7)) << 4;
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb + c0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb + c1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
-                    } else {                       // narrow outputs: dense rows of chunk_cols * 2 bytes, no swizzle
-                        const uint32_t rb = sbuf + (uint32_t)row * (uint32_t)(p.chunk_cols * 2) + (uint32_t)g * 32u;
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb + 16u), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+                    if (mt == p.MT - 1 && ch == nchunks - 1) {   // every TMEM read of this accumulator stage is done: hand it back
+                        tc_fence_before();
+                        mbar_arrive(&acc_empty[as]);
                     }
+                    fence_proxy_async();
+                    named_bar_sync(1, 128);
+                    if (et == 0) {
+                        if (c.img < p.NI)
+                            tma_store_4d(&map_d, col0, c.px * p.BW + mt * p.sub_dx, c.py * p.BH + mt * p.sub_dy, c.img, sbuf);
+                        bulk_commit();
+                    }
+                    buf ^= 1;
                 }
-                if (ch == nchunks - 1) {           // every TMEM read of this accumulator stage is done: hand it back
-                    tc_fence_before();
-                    mbar_arrive(&acc_empty[as]);
-                }
-                fence_proxy_async();
-                named_bar_sync(1, 128);
-                if (et == 0) {
-                    if (c.img < p.NI) tma_store_4d(&map_d, col0, c.px * p.BW, c.py * p.BH, c.img, sbuf);
-                    bulk_commit();
-                }
-                buf ^= 1;
             }
-            if (++as == 2) { as = 0; aphase ^= 1u; }
+            if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
         }
         if (et == 0) bulk_wait_all();
     }
@@ -461,10 +488,20 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     if (d->Cout < 256) { bn = 16; while (bn < d->Cout) bn *= 2; }
     p.BN = bn;
     p.n_blocks = (d->Cout + bn - 1) / bn;
-    // pixel patch: wide for a GEMM (H == 1), 16 x 8 for images
-    if (d->OH == 1) { p.BW = 128; p.BH = 1; }
-    else if (d->OW >= 16) { p.BW = 16; p.BH = 8; }
-    else { p.BW = 8; p.BH = 16; }
+    // pixel sub-tile (128 pixels = UMMA M): wide for a GEMM (H == 1), 16 x 8 for images; MT sub-tiles per CTA tile
+    if (d->OH == 1) { p.BWs = 128; p.BHs = 1; p.sub_dx = 128; p.sub_dy = 0; }
+    else if (d->OW >= 16) { p.BWs = 16; p.BHs = 8; p.sub_dx = 0; p.sub_dy = 8; }
+    else { p.BWs = 8; p.BHs = 16; p.sub_dx = 0; p.sub_dy = 16; }
+    {
+        const char* fm = getenv("TD_CONV_MT");
+        const int want_mt = fm != nullptr ? atoi(fm) : 2;
+        const long long sub_tiles = (long long)d->N * ((d->OW + p.BWs - 1) / p.BWs) * ((d->OH + p.BHs - 1) / p.BHs) * p.n_blocks;
+        // two sub-tiles per CTA when the grid stays full (>= 4 sub-tiles per SM) and the box fits (<= 256 per dimension)
+        p.MT = (want_mt >= 2 && sub_tiles >= 4LL * dev.sms && bn >= 32 && (p.BWs + p.sub_dx) * d->stride <= 256 && (p.BHs + p.sub_dy) * d->stride <= 256) ? 2 : 1;
+    }
+    p.BW = p.BWs + (p.MT - 1) * p.sub_dx;
+    p.BH = p.BHs + (p.MT - 1) * p.sub_dy;
+    p.acc_stages = std::min(2, 512 / (p.MT * bn));
     p.tiles_x = (d->OW + p.BW - 1) / p.BW;
     p.tiles_y = (d->OH + p.BH - 1) / p.BH;
     const long long mt = (long long)d->N * p.tiles_x * p.tiles_y;
@@ -474,7 +511,7 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     // multicasts them) -- the kernel is bound by L2 -> SM bytes otherwise (48 KB per 128x256x64 MMA step per CTA)
     int cl = 1;
     const char* force = getenv("TD_CONV_CLUSTER");
-    const int want = force != nullptr ? atoi(force) : 2;
+    const int want = force != nullptr ? atoi(force) : 1;   // measured: no gain on B200 (the bound is bytes INTO the SM, which multicast does not cut)
     if (want >= 2 && bn >= 64 && dev.sms % 2 == 0 && mt >= 2 * (long long)dev.sms) cl = 2;
     if (want >= 4 && bn >= 128 && dev.sms % 4 == 0 && mt >= 4 * (long long)dev.sms) cl = 4;
     p.cluster = cl;
@@ -485,7 +522,7 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     p.bias_per_row = d->bias_per_row;
     p.alpha = d->alpha;
     p.res_pitch = residual != nullptr ? d->res_pitch : 0;
-    const int stage_bytes = kConvStageA + bn * 128;
+    const int stage_bytes = p.MT * kConvStageA + bn * 128;
     const int avail = dev.smem_optin - 1024 - 2 * kConvStoreBuf;
     p.stages = std::min(kConvMaxStages, avail / stage_bytes);
     if (p.stages < 2) { td_set_error("td_conv2d_nhwc: not enough shared memory"); return TD_ERR_UNSUPPORTED; }
@@ -511,7 +548,7 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     {
         const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->OW, (uint64_t)d->OH, (uint64_t)d->N};
         const uint64_t str[3] = {(uint64_t)d->y_pitch * 2, (uint64_t)d->OW * d->y_pitch * 2, (uint64_t)d->OH * d->OW * d->y_pitch * 2};
-        const uint32_t box[4] = {(uint32_t)p.chunk_cols, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+        const uint32_t box[4] = {(uint32_t)p.chunk_cols, (uint32_t)p.BWs, (uint32_t)p.BHs, 1};
         const uint32_t es[4] = {1, 1, 1, 1};
         const int rc = encode_map(&md, y, p.is_bf16, 4, dims, str, box, es, p.chunk_cols == 64, "output");
         if (rc != TD_OK) return rc;

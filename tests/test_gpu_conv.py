@@ -162,9 +162,24 @@ def test_softmax_rows(ops):
 
 
 @pytest.mark.parametrize("cluster", ["1", "2", "4"])
-def test_conv3x3_cluster_multicast(ops, monkeypatch, cluster):
-    """Enough pixel tiles (>= 4 per SM) for the CTA-cluster form: the weight tile of a k-step is fetched once per
-    cluster and multicast; odd sizes leave dummy tiles at the end of the list."""
+@pytest.mark.parametrize("mt", ["1", "2"])
+def test_conv3x3_large_grid_forms(ops, monkeypatch, cluster, mt):
+    """Enough pixel tiles (>= 4 per SM) for the large-grid forms: two 128-pixel sub-tiles per CTA sharing the weight tile
+    of a k-step (TD_CONV_MT), CTA clusters with the weight tile multicast (TD_CONV_CLUSTER); odd sizes leave partial
+    and dummy tiles at the end of the list."""
     monkeypatch.setenv("TD_CONV_CLUSTER", cluster)
-    _conv_case(ops, torch.float16, 1, 259, 333, 128, 256, 3, 1, 200, residual=True)   # 21 x 33 = 693 pixel tiles
-    _conv_case(ops, torch.float16, 1, 168, 336, 64, 128, 3, 1, 210)
+    monkeypatch.setenv("TD_CONV_MT", mt)
+    _conv_case(ops, torch.float16, 1, 259, 333, 128, 256, 3, 1, 200, residual=True)   # 21 x 33 = 693 sub-tiles, BN 256 (one TMEM stage at MT 2)
+    _conv_case(ops, torch.float16, 1, 253, 336, 64, 128, 3, 1, 210)                   # BN 128: two TMEM stages at MT 2
+    _conv_case(ops, torch.float16, 1, 663, 541, 64, 64, 3, 2, 220)                    # stride 2 with the doubled box (714 output sub-tiles)
+
+
+@pytest.mark.parametrize("mt", ["1", "2"])
+def test_gemm_large_m(ops, monkeypatch, mt):
+    monkeypatch.setenv("TD_CONV_MT", mt)
+    dtype = torch.float16
+    M, K, N = 80003, 64, 128
+    a, b = _rand((M, K), dtype, 1, 0.5), _rand((N, K), dtype, 2, 0.5)
+    bias = _rand((M,), torch.float32, 5)
+    got = ops.gemm_nt(a, b, bias=bias, bias_per_row=True)
+    _check(got, a.float() @ b.float().t() + bias[:, None], dtype, f"gemm large M, MT={mt}")
