@@ -207,6 +207,100 @@ def synthetic_latent(seed: int, shape, dtype=torch.float16) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def canvas_for(world: int, scaling: str):
+    """Latent canvas (H, W).  strong: BASELINE cfg2's 512 x 512 whatever N.  weak: N x the cfg2 area -- every rank keeps a
+    cfg2-sized share of the tiles (more GPUs = larger upscale, the regime tile sharding exists for)."""
+    if scaling == "strong" or world == 1:
+        return CFG["H"], CFG["W"]
+    return {2: (1024, 512), 4: (2048, 512), 8: (2048, 1024)}.get(world, (512 * min(world, 4), 512 * max(1, world // 4)))
+
+
+class StripWorkload:
+    """N > 1: row-strip tile shard with halo-only exchange (parallel.StripShard / StripExchange).  One step of rank r =
+    scatter its tiles -> [UNet: stubbed, outputs pre-generated in the exchange's own-tile buffer] -> push the overlapping
+    tile rows to the next rank(s) + signal -> blend its strip (waits in-kernel for the halos) -> push the latent halo
+    rows back + signal + wait."""
+
+    def __init__(self, device, rank, world, scaling):
+        from multidiffusion_upscaler_for_automatic1111_b200 import _cabi, engine, parallel
+        self.cabi, self.engine, self.parallel = _cabi, engine, parallel
+        c = CFG
+        self.dev, self.rank, self.world, self.scaling = device, rank, world, scaling
+        self.N, self.C = c["N"], c["C"]
+        self.H, self.W = canvas_for(world, scaling)
+        self.g = engine.make_grid(self.W, self.H, c["tile"], c["tile"], c["overlap"], c["tile_bs"])
+        g = self.g
+        self.T = g.num_tiles
+        w_host = engine.grid_weights(g)
+        self.weights = torch.from_numpy(w_host).to(device)
+        self.rcp_weights = torch.from_numpy(engine.exact_reciprocals(w_host)).to(device)
+        self.shard = parallel.StripShard(list(g.ys[:g.rows]), g.cols, g.tile_h, g.H, rank, world)
+        self.ex = parallel.StripExchange(self.shard, self.N, self.C, g.tile_w, g.W, torch.float16, device)
+        self.t0, self.t1 = self.shard.tile_range()
+        self.x = synthetic_latent(rank, (self.N, self.C, g.H, g.W), torch.float16).to(device)
+        own = self.ex.own_tiles()
+        own.copy_((torch.randn(own.shape, device=device, dtype=torch.float32) * 0.8).half())
+        self.tiles_in = torch.empty_like(own)
+        self.stream = ctypes.c_void_p(0)
+        es = 2
+        lo, hi = self.shard.strip()
+        self.bytes_scatter = (self.N * self.C * (self.shard.scatter_rows()[1] - self.shard.scatter_rows()[0]) * g.W + own.numel()) * es
+        halo_rows = sum(v1 - v0 for (_, _, v0, v1) in self.shard.halo_in())
+        self.bytes_blend = (own.numel() + halo_rows * g.cols * self.N * self.C * g.tile_w) * es + self.N * self.C * (hi - lo) * g.W * 4 + (hi - lo) * g.W * 4
+        self.halo_bytes_out = sum((v1 - v0) for (_, _, v0, v1) in self.shard.halo_out()) * g.cols * self.N * self.C * g.tile_w * es + \
+            sum(b - a for (_, a, b) in self.shard.x_out()) * g.W * self.N * self.C * 4
+        self.nsets, self.set_mb = 1, (self.x.numel() * 2 + 2 * own.numel() * 2 + self.N * self.C * g.H * g.W * 4) / 1e6
+        self.exchange_mode = "strip"
+
+    def set_stream(self):
+        self.stream = self.cabi.current_stream_ptr(self.dev)
+
+    def scatter(self, s=0, flags=0):
+        c = self.cabi
+        if self.t1 > self.t0:
+            c.check(c.lib.td_scatter_tiles(ctypes.byref(self.g), self.x.data_ptr(), self.tiles_in.data_ptr(), self.N, self.C, c.TD_F16,
+                                           self.t0, self.t1, flags, self.stream))
+
+    def step(self, i):
+        self.scatter()
+        self.ex.push_tile_halos()
+        self.ex.blend(self.g, self.weights, self.rcp_weights)
+        self.ex.push_x_halos_and_wait()
+
+    def launches_per_step(self):
+        sh = self.shard
+        return 1 + len(sh.halo_out()) + 1 + 1 + len(sh.x_out()) + 1 + (1 if sh.x_in() else 0)
+
+    def parity(self):
+        """One more step, then: every rank's strip == the single-GPU blend of ALL ranks' tile outputs (computed on every
+        rank from the gathered outputs; compared on the gathered latent).  Bit patterns."""
+        import torch.distributed as dist
+        g, sh = self.g, self.shard
+        self.step(0)
+        torch.cuda.synchronize()
+        full = self.ex.gather_latent(self.ex.x_out)
+        per_band = g.cols * self.N
+        nb = max(len(sh.bands(r)) for r in range(self.world))
+        own = self.ex.own_tiles()
+        pad = torch.zeros((nb * per_band,) + tuple(own.shape[1:]), dtype=own.dtype, device=self.dev)
+        pad[:own.shape[0]] = own
+        allo = torch.empty((self.world,) + tuple(pad.shape), dtype=own.dtype, device=self.dev)
+        dist.all_gather_into_tensor(allo.view(-1), pad.view(-1))
+        outs = []
+        for r in range(self.world):
+            for k, _ in enumerate(sh.bands(r)):
+                outs.append(allo[r][k * per_band:(k + 1) * per_band])
+        want = self.engine.blend_multidiffusion(g, outs, self.N, self.C, g.cols, self.weights, torch.float16, rcp_weights=self.rcp_weights)
+        torch.cuda.synchronize()
+        ok = torch.equal(full.view(torch.int32), want.view(torch.int32))
+        t = torch.tensor([1 if ok else 0], device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def close(self):
+        self.ex.close()
+
+
 class Workload:
     def __init__(self, device, rank, world, nsets, exchange="peer"):
         from multidiffusion_upscaler_for_automatic1111_b200 import _cabi, engine
@@ -509,6 +603,127 @@ def gpu_arm(args, rank, world, local_rank):
             torch.distributed.destroy_process_group()
         else:
             os._exit(0)   # NCCL communicators captured in CUDA graphs can block a clean teardown; the line is out
+
+
+def strip_arm(args, rank, world, local_rank):
+    """N > 1 (default exchange): row-strip tile shard, halo-only exchange.  Prints the weak-scaling line (per-rank work
+    fixed: the canvas grows with N) with the strong-scaling numbers (BASELINE cfg2's 512 x 512 canvas split over the
+    ranks) in `strong`; both with an in-run parity check of the gathered latent against the single-GPU blend."""
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.distributed.init_process_group("nccl", device_id=dev)
+    dist = torch.distributed
+    peak, peak_src = load_peaks()
+    stream = torch.cuda.Stream(dev)
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    results = {}
+    for scaling in (["weak", "strong"] if args.scaling == "weak" else ["strong"]):
+        wl = StripWorkload(dev, rank, world, scaling)
+        with torch.cuda.stream(stream):
+            wl.set_stream()
+            for i in range(max(args.warmup, 3)):
+                wl.step(i)
+            torch.cuda.synchronize()
+            dist.barrier()
+            use_graph = not args.no_graph
+            if use_graph:
+                replay = timed_graph_loop(wl.step, args.steps, stream)
+                replay()
+            else:
+                def replay():
+                    for i in range(args.steps):
+                        wl.step(i)
+            torch.cuda.synchronize()
+            dist.barrier()
+            ms = event_time_ms(replay, stream)             # EXACTLY args.steps steps
+            dist.barrier()
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item()) / 1e3 / args.steps
+            ok = wl.parity()
+            e2e = strip_e2e(args, dev, stream, world, rank) if scaling == "strong" else None
+        mp_img = wl.H * wl.W * 64 / 1e6
+        results[scaling] = {"value": mp_img / (SAMPLER_STEPS * sec), "ms_per_step": sec * 1e3, "canvas": [wl.H, wl.W], "tiles": wl.T,
+                            "tiles_this_rank": wl.t1 - wl.t0, "strip_rows": list(wl.shard.strip()), "halo_bytes_out_per_step": wl.halo_bytes_out,
+                            "launches_per_step": wl.launches_per_step(), "parity_ok": ok, "cuda_graph": use_graph, "e2e": e2e}
+        dist.barrier()
+        wl.close()
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        cpu_dt, cpu_done, cpu_threads, cpu_kind = run_cpu(10 ** 9, 2, budget_s=args.cpu_budget)
+        head = results["weak" if args.scaling == "weak" else "strong"]
+        line = {
+            "metric": METRIC, "value": head["value"], "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {**workload_config(), "canvas_latent": head["canvas"], "tiles": head["tiles"], "cuda_graph": head["cuda_graph"],
+                       "l2": "one buffer set (L2-resident tile outputs): the N > 1 step is bound by launch and NVLink signal latency, not HBM",
+                       "parallelism": f"row-strip tile shard over {world} ranks: each rank denoises a run of tile rows and blends the canvas "
+                                      "rows it owns; per step only the overlapping tile rows go down the ranks and the scattered-from "
+                                      "latent rows come back (pushed into CUDA-IPC peer buffers over NVLink, release/acquire flags, no NCCL "
+                                      "on the data path)" + (f"; weak scaling: the canvas grows with N ({head['canvas'][0]} x {head['canvas'][1]} "
+                                      "latent), per-rank tile count fixed" if args.scaling == "weak" else "")},
+            "clocks": clocks, "parity_ok": head["parity_ok"], "e2e": results.get("strong", {}).get("e2e"),
+            "gpu_launches": args.steps * head["launches_per_step"],
+            "strip": head, "strong": results.get("strong") if args.scaling == "weak" else None,
+            "roofline": None,
+            "cpu_baseline": {"value": mp_per_s(cpu_dt), "unit": "MP/s", "cores": cpu_threads, "kind": cpu_kind, "ms_per_step": cpu_dt * 1e3,
+                             "sample": f"{cpu_done} sampler steps of BASELINE cfg2 on the host cores, identity denoiser, torch CPU, {cpu_threads} threads"},
+            "impl": "b200",
+        }
+        print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def strip_e2e(args, dev, stream, world, rank):
+    """The metric through MultiDiffusion.kdiff_forward on the strip shard (BASELINE cfg2 canvas): every step copies the
+    latent from pinned host memory, runs the hooked forward (identity denoiser on this rank's tiles) and reads this
+    rank's rows of the result back."""
+    import types
+
+    from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
+    c = CFG
+    inner = types.SimpleNamespace(forward=lambda x, sigma, cond=None: x)
+    sampler = types.SimpleNamespace(model_wrap_cfg=types.SimpleNamespace(inner_model=inner, image_cfg_scale=None))
+    p = types.SimpleNamespace(width=c["W"] * 8, height=c["H"] * 8, sampler_name="Euler a")
+    d = MultiDiffusion(p, sampler)
+    d.init_grid_bbox(c["tile"], c["tile"], c["overlap"], c["tile_bs"])
+    d.init_done()
+    d.init_tile_shard(None, fused=True)
+    d.hook()
+    fwd = sampler.model_wrap_cfg.inner_model.forward
+    lo, hi = d._strip.strip()
+    x_host = synthetic_latent(0, (c["N"], c["C"], c["H"], c["W"]), torch.float16).pin_memory()
+    out_host = torch.empty((c["N"], c["C"], max(hi - lo, 1), c["W"]), dtype=torch.float32).pin_memory()
+    x_dev = torch.empty_like(x_host, device=dev)
+    sigma = torch.ones(c["N"], device=dev, dtype=torch.float16)
+    cond = {"c_crossattn": [torch.zeros(c["N"], 77, 768, device=dev, dtype=torch.float16)],
+            "c_concat": [torch.zeros(c["N"], 5, 1, 1, device=dev, dtype=torch.float16)]}
+
+    def step():
+        x_dev.copy_(x_host, non_blocking=True)
+        out = fwd(x_dev, sigma, cond=cond)
+        if hi > lo:
+            out_host.copy_(out[:, :, lo:hi], non_blocking=True)
+
+    n = 50
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    torch.distributed.barrier()
+    t0 = time.perf_counter()
+    ms = event_time_ms(lambda: [step() for _ in range(n)], stream)
+    wall = time.perf_counter() - t0
+    t = torch.tensor([max(ms / 1e3, wall) / n], device=dev)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    sec = float(t.item())
+    torch.distributed.barrier()
+    d._strip_exchange.close()
+    return {"value": mp_per_s(sec), "unit": "MP/s", "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": out_host.numel() * 4,
+            "ms_per_step": sec * 1e3, "steps": n,
+            "api": "MultiDiffusion.kdiff_forward on the row-strip shard (per rank: full latent in, own rows out), identity denoiser"}
 
 
 def load_traffic(kernel: str):
@@ -829,7 +1044,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--buffer-sets", type=int, default=8)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N>1: how tile outputs reach the other ranks")
+    ap.add_argument("--exchange", default="strip", choices=["strip", "peer", "nccl"],
+                    help="N>1: strip = row-strip shard with halo-only exchange (default); peer / nccl = round-1 replicate-all forms")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1 strip shard: weak = canvas grows with N (per-rank work fixed; the strong numbers ride along), strong = cfg2 canvas split")
     ap.add_argument("--profile-e2e", action="store_true")
     ap.add_argument("--variants", action="store_true", help="print a table of per-kernel micro-timings to stderr")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
@@ -849,6 +1067,9 @@ def main():
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         sys.exit(f"--gpus {args.gpus} needs torchrun (WORLD_SIZE={world})")
+    if world > 1 and args.exchange == "strip":
+        strip_arm(args, rank, world, local_rank)
+        return
     gpu_arm(args, rank, world, local_rank)
 
 

@@ -396,6 +396,8 @@ class StripExchange:
         first = self._senders[0] if self._senders else 0
         count = (self._senders[-1] - first + 1) if self._senders else 0
         f, c, v = self.flags_tiles.wait_args(first, count)
+        if hi <= lo:                       # this rank owns no canvas rows (more ranks than tile rows)
+            return self.x_out
         if not hasattr(self, "_ptr_table"):
             self._ptr_table = self.band_pointer_table()
         with torch.cuda.device(self.device):

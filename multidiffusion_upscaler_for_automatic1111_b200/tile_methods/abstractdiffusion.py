@@ -112,6 +112,9 @@ class AbstractDiffusion:
         self._shard_fused = False
         self._exchange = None                 # parallel.PeerExchange (fused path)
         self._shard_step = 0
+        self._shard_mode = "replicate"
+        self._strip = None
+        self._strip_exchange = None
 
     # ----------------------------------------------------------------- helpers
     def _sd_model(self):
@@ -240,22 +243,64 @@ class AbstractDiffusion:
         return 1.0
 
     # ------------------------------------------------------------- multi-GPU
-    def init_tile_shard(self, group=None, fused: bool = True):
-        """Shard the tile list over the ranks of `group` (one process per GPU).  Call after init_grid_bbox.
+    def init_tile_shard(self, group=None, fused: bool = True, mode: Optional[str] = None):
+        """Shard the tiles over the ranks of `group` (one process per GPU).  Call after init_grid_bbox.
 
-        Each rank denoises `tiles[begin:end)` only; per step the tile outputs are exchanged (fused: peer
-        reads over NVLink inside the blend kernel; else NCCL all-gather) and every rank blends the full
-        latent deterministically (bit-identical across ranks and to a single-GPU run)."""
+        mode "strip" (default with fused=True for MultiDiffusion): rank r denoises a contiguous run of tile ROWS and
+        blends only the canvas rows it owns; per step only the overlapping tile rows go to the next rank(s) and the
+        rows of the blended latent the previous rank(s) scatter from come back (parallel.StripShard / StripExchange:
+        pushed over NVLink into CUDA-IPC-mapped buffers, flag-synchronised, no NCCL on the data path).  The tensor
+        `sample_one_step` returns is valid on the rank's own rows plus that halo; `gather_latent` assembles the full
+        latent (after the last step).  Bit-identical to a single-GPU run.
+        mode "replicate": each rank denoises `tiles[begin:end)`, ALL tile outputs are exchanged (fused: peer reads over
+        NVLink inside the blend kernel; else NCCL all-gather) and every rank blends the full latent."""
         import torch.distributed as dist
         from .. import parallel
         if self._grid is None:
             raise RuntimeError("init_tile_shard() must follow init_grid_bbox()")
-        self._shard = parallel.TileShard(self.num_tiles, dist.get_rank(group), dist.get_world_size(group))
-        self._shard_group, self._shard_fused = group, fused
+        if mode is None:
+            mode = "strip" if (fused and self.method == "MultiDiffusion") else "replicate"
+        if mode not in ("strip", "replicate"):
+            raise ValueError(f"unknown shard mode {mode!r}")
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        self._shard_group, self._shard_fused, self._shard_mode = group, fused, mode
         bboxes = [b for batch in self.batched_bboxes for b in batch]
+        g = self._grid
+        if mode == "strip":
+            self._strip = parallel.StripShard(list(g.ys[:g.rows]), g.cols, g.tile_h, g.H, rank, world)
+            t0, t1 = self._strip.tile_range()
+            self._shard = parallel.TileShard(self.num_tiles, rank, world)     # kept for callers that read .begin / .end
+            self._shard.begin, self._shard.end = t0, t1
+        else:
+            self._strip = None
+            self._shard = parallel.TileShard(self.num_tiles, rank, world)
         local = bboxes[self._shard.begin:self._shard.end]
         self.local_batched_bboxes = [local[i:i + self.tile_bs] for i in range(0, len(local), self.tile_bs)]
         return self._shard
+
+    def gather_latent(self, x: Tensor) -> Tensor:
+        """Strip shard: the full latent from every rank's rows of `x` (call once, after the last sampler step).
+        Other modes keep the latent replicated: returns x."""
+        if getattr(self, "_strip", None) is None or self._strip_exchange is None:
+            return x
+        return self._strip_exchange.gather_latent(x)
+
+    def _strip_step(self, outs, x: Tensor, N: int, C: int) -> Tensor:
+        """Strip-shard tail of MultiDiffusion.sample_one_step: own tile outputs -> halo push -> strip blend -> latent halo."""
+        from .. import parallel
+        g = self._grid
+        if self._strip_exchange is None:
+            self._strip_exchange = parallel.StripExchange(self._strip, N, C, g.tile_w, g.W, x.dtype, x.device, self._shard_group)
+        ex = self._strip_exchange
+        own = ex.own_tiles()
+        off = 0
+        for o in outs:
+            own[off:off + o.shape[0]].copy_(o)
+            off += o.shape[0]
+        ex.push_tile_halos()
+        x_out = ex.blend(g, self.weights, self._rcp_weights if x.dtype != torch.float32 else None, flags=self._blend_flags)
+        ex.push_x_halos_and_wait()
+        return x_out
 
     def _exchange_and_blend_md(self, outs, x: Tensor, N: int, C: int) -> Tensor:
         """Tile-shard tail of MultiDiffusion.sample_one_step."""

@@ -208,21 +208,32 @@ class MultiDiffusion(AbstractDiffusion):
         return x_out
 
     def _sample_one_step_sharded(self, x_in: Tensor, x: Tensor, repeat_func: Callable, N: int, C: int) -> Tensor:
-        """This rank's chunk of the tile list, then exchange + deterministic blend (init_tile_shard)."""
+        """This rank's tiles, then the exchange + deterministic blend (init_tile_shard).
+
+        An interrupt (multidiffusion.py:152) stops the denoiser calls of THIS rank but not its part of the exchange:
+        the peers' kernels wait for this rank's signal, so the step always publishes (possibly stale) tile outputs,
+        blends and signals -- the step counters stay in lock-step -- and only then returns x_in like the reference."""
         sh = self._shard
         outs = []
+        interrupted = False
         if sh.num_local > 0:
             self._tiles = engine.scatter_tiles(self._grid, x, out=self._tiles, tile_begin=sh.begin, tile_end=sh.end,
                                                flags=self._blend_flags)
             off = 0
             for batch_id, bboxes in enumerate(self.local_batched_bboxes):
-                if host.interrupted():
-                    return x_in
                 x_tile = self._tiles[off * N:(off + len(bboxes)) * N]
                 off += len(bboxes)
+                if interrupted or host.interrupted():
+                    interrupted = True
+                    outs.append(x_tile)          # placeholder with the right shape: the exchange must still happen
+                    continue
                 outs.append(repeat_func(x_tile, bboxes))
                 self.update_pbar()
-        return self._exchange_and_blend_md(outs, x, N, C)
+        if self._shard_mode == "strip":
+            out = self._strip_step(outs, x, N, C)
+        else:
+            out = self._exchange_and_blend_md(outs, x, N, C)
+        return x_in if interrupted else out
 
     def get_noise(self, x_in: Tensor, sigma_in: Tensor, cond_in: CondDict, step: int) -> Tensor:
         """Tiled eps prediction used by noise inversion (multidiffusion.py:220-243)."""

@@ -22,14 +22,17 @@ def test_reference_arm_prints_one_contract_line():
     assert d["vs_baseline"] is None and d["data"].startswith("synthetic")
     assert d["e2e"] == {"value": d["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    # the unmodified reference when its tree is present (build container), its op-for-op restatement on the GPU box
+    assert cb["kind"] == ("reference" if os.path.isdir("/root/reference/tile_methods") else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["config"]["workload"].startswith("SD1.5 4096x4096") and (d["config"]["H"], d["config"]["W"], d["config"]["tile"]) == (512, 512, 96)
 
 
 def test_gpu_arm_takes_nothing_from_the_oracle():
-    """Only the cpu_baseline / reference leg may execute oracle/ (it IS the CPU restatement being timed)."""
+    """Only the cpu_baseline / reference legs may execute oracle/ (they ARE the CPU restatement being timed)."""
     src = open(os.path.join(ROOT, "bench.py")).read()
-    imports = [(m.start(), m.group(0)) for m in re.finditer(r"from oracle import [^\n]+", src)]
-    assert len(imports) == 1, imports
-    head = src[:imports[0][0]]
-    assert head.rstrip().endswith('all host threads."""') or "def run_cpu" in head[-400:] or "oracle port" in head[-300:]
+    for m in re.finditer(r"from oracle import [^\n]+", src):
+        head = src[:m.start()]
+        fn = re.findall(r"\ndef (\w+)\(", head)[-1]
+        assert fn in ("cpu_reference_step_fn", "vae_cpu_baseline"), f"`{m.group(0)}` inside {fn}(): the GPU arm must not use the oracle"
+    assert "import oracle" not in src

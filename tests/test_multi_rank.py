@@ -207,6 +207,63 @@ def test_gloo_world2_sharded_demofusion_equals_single(tmp_path):
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
 
 
+
+# ------------------------------------------------------------------------------------------- strip shard plan (no GPU)
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8, 12])
+@pytest.mark.parametrize("geom", [(512, 512, 96, 96, 48), (128, 200, 32, 24, 8), (96, 97, 96, 96, 48), (1024, 2048, 96, 96, 48)])
+def test_strip_shard_plan_covers_and_reproduces_the_single_device_blend(world, geom):
+    """parallel.StripShard: every canvas row is owned by exactly one rank; the rows a rank receives as tile halo are
+    exactly what its strip needs from foreign tile rows; the latent halo covers its scatter extent; and blending each
+    strip from own + halo rows only is bit-identical to the single-device step."""
+    import numpy as np
+    from multidiffusion_upscaler_for_automatic1111_b200 import engine, parallel
+    W, H, tw, th, ov = geom
+    N, C = (2, 4) if H * W <= 512 * 512 else (1, 1)
+    plan = tiling.GridPlan(W, H, tw, th, ov, 4, False)
+    g = engine.make_grid(W, H, tw, th, ov, 4)
+    ys, cols = list(g.ys[:g.rows]), g.cols
+    x = synth.latent(1, (N, C, H, W), torch.float16)
+    full = blend.multidiffusion_step(x, plan.batched_bboxes, plan.weights, lambda t, bb: t * 0.5)
+    outs = [x[:, :, y:y + h, xx:xx + w] * 0.5 for (xx, y, w, h) in plan.bboxes]
+    wgt = torch.from_numpy(plan.weights).view(1, 1, H, W)
+    got = torch.zeros_like(full)
+    cover = np.zeros(H, int)
+    shards = [parallel.StripShard(ys, cols, th, H, r, world) for r in range(world)]
+    for r, sh in enumerate(shards):
+        lo, hi = sh.strip()
+        assert hi <= lo or (lo % 8 == 0 and (hi % 8 == 0 or hi == H))
+        if hi <= lo:
+            assert sh.halo_in() == []      # an empty strip (its tiles may still feed other ranks' strips)
+            continue
+        cover[lo:hi] += 1
+        avail = {i: (0, th) for i in sh.bands()}
+        for (i, pr, v0, v1) in sh.halo_in():
+            assert sh.owner_of_band(i) == pr and (i, r, v0, v1) in shards[pr].halo_out()
+            avail[i] = (v0, v1)
+        buf = torch.zeros((N, C, H, W), dtype=torch.float16)
+        for t, (xx, y, w, h) in enumerate(plan.bboxes):
+            i = t // cols
+            if i not in avail:
+                assert y + h <= lo or y >= hi, "a tile row that touches the strip is neither owned nor received"
+                continue
+            v0, v1 = avail[i]
+            a, b = max(y, lo), min(y + h, hi)
+            if b > a:
+                assert a >= y + v0 and b <= y + v1, "halo rows do not cover the strip part of the tile"
+                buf[:, :, a:b, xx:xx + w] += outs[t][:, :, a - y:b - y]
+        o = torch.where(wgt > 1, buf / wgt, buf)
+        got[:, :, lo:hi] = o[:, :, lo:hi]
+        s0, s1 = sh.scatter_rows()
+        have = np.zeros(H, bool)
+        have[lo:hi] = True
+        for (q, a, b) in sh.x_in():
+            assert (r, a, b) in shards[q].x_out()
+            have[a:b] = True
+        assert have[s0:s1].all(), "latent halo does not cover the scatter extent"
+    assert (cover == 1).all()
+    assert torch.equal(got, full)
+
+
 # ------------------------------------------------------------------------------------------- GPU
 def _gpu_worker(rank, world, port, result_dir):
     from multidiffusion_upscaler_for_automatic1111_b200 import MultiDiffusion
@@ -228,7 +285,7 @@ def _gpu_worker(rank, world, port, result_dir):
                 d = MultiDiffusion(p, sampler)
                 d.init_grid_bbox(c["tw"], c["th"], c["ov"], c["bs"])
                 d.init_done()
-                sh = d.init_tile_shard(None, fused=fused)
+                sh = d.init_tile_shard(None, fused=fused, mode="replicate")
                 d.hook()
                 cond = {"c_crossattn": [torch.zeros(c["N"], 77, 8, device="cuda")], "c_concat": [torch.zeros(c["N"], 5, 1, 1, device="cuda")]}
                 for step in range(3):    # several steps: double-buffered exchange + monotonic flags
@@ -240,6 +297,41 @@ def _gpu_worker(rank, world, port, result_dir):
                 if d._exchange is not None:
                     dist.barrier()
                     d._exchange.close()
+        # row-strip shard (default fused mode): each rank blends its own rows from own + halo tile rows; several steps
+        for c in (CASE, CASE2, dict(CASE2, W=256, H=640, N=1)):
+            x = synth.latent(31, (c["N"], c["C"], c["H"], c["W"]), torch.float16)
+            plan, want = _oracle(c, x)
+
+            def unet(x_tile, sigma, cond=None):
+                bbs = d.local_batched_bboxes[state["i"]]
+                state["i"] += 1
+                return synth.fake_denoise(x_tile, bbs, c["N"])
+            state = {"i": 0}
+            inner = types.SimpleNamespace(forward=unet)
+            sampler = types.SimpleNamespace(model_wrap_cfg=types.SimpleNamespace(inner_model=inner, image_cfg_scale=None))
+            p = types.SimpleNamespace(width=c["W"] * 8, height=c["H"] * 8, sampler_name="Euler a")
+            d = MultiDiffusion(p, sampler)
+            d.init_grid_bbox(c["tw"], c["th"], c["ov"], c["bs"])
+            d.init_done()
+            d.init_tile_shard(None, fused=True)
+            assert d._shard_mode == "strip"
+            d.hook()
+            cond = {"c_crossattn": [torch.zeros(c["N"], 77, 8, device="cuda")], "c_concat": [torch.zeros(c["N"], 5, 1, 1, device="cuda")]}
+            for step in range(3):
+                state["i"] = 0
+                out = inner.forward(x.cuda(), torch.ones(c["N"], device="cuda"), cond=cond)
+                torch.cuda.synchronize()
+                sh = d._strip
+                lo, hi = sh.strip()
+                assert torch.equal(out[:, :, lo:hi].cpu(), want[:, :, lo:hi]), f"rank {rank} strip rows differ at step {step}"
+                for (q, a, b) in sh.x_in():
+                    assert torch.equal(out[:, :, a:b].cpu(), want[:, :, a:b]), f"rank {rank}: latent halo from rank {q} differs at step {step}"
+                assert state["i"] == len(d.local_batched_bboxes)
+                dist.barrier()      # the next step's halo pushes must not overtake this step's checks
+            full = d.gather_latent(out)
+            assert torch.equal(full.cpu(), want), f"rank {rank}: gathered latent differs"
+            dist.barrier()
+            d._strip_exchange.close()
         # tiled VAE, tiles sharded over the ranks: fast mode (no collective until the canvas all-reduce) and slow mode
         # (GroupNorm statistics all-reduced every round) must both reproduce the single-process oracle on every rank
         from multidiffusion_upscaler_for_automatic1111_b200 import tilevae
