@@ -623,53 +623,56 @@ class AbstractDiffusion:
             combined_noise = inverse_noise
         return self.sample_img2img_original(p, x, combined_noise, conditioning, unconditional_conditioning, steps, image_conditioning)
 
+    def _inversion_conditioning(self, prompts: List[str]) -> CondDict:
+        """Conditioning of the inversion pass: the job's prompts, no negative prompt, the job's image conditioning."""
+        cond = self.p.sd_model.get_learned_conditioning(prompts)
+        if isinstance(cond, Tensor):        # SD1 / SD2: one tensor
+            return self.make_cond_dict({"c_crossattn": [], "c_concat": []}, cond, self.p.image_conditioning)
+        # SDXL: {"crossattn", "vector"}
+        return self.make_cond_dict({"crossattn": None, "vector": None, "c_concat": []}, cond["crossattn"], self.p.image_conditioning,
+                                   cond["vector"])
+
+    def _inversion_interval(self, dnw, x: Tensor, sigma_from, sigma_to, cond_in: CondDict, step: int, skip: int) -> Tensor:
+        """One explicit-Euler interval of the probability-flow ODE dx/dsigma = (x - D(x, sigma)) / sigma, walked UP the
+        noise schedule from `sigma_from` to `sigma_to`; D is evaluated at sigma_to with the tiled denoiser, its timestep
+        divided by the retouch factor (the img2imgalt "sigma adjustment", abstractdiffusion.py:714-733)."""
+        sigma_in = sigma_to * x.new_ones([x.shape[0]])
+        c_out, c_in = (k[(...,) + (None,) * (x.ndim - k.ndim)] for k in dnw.get_scalings(sigma_in)[skip:])
+        t = dnw.sigma_to_t(sigma_in) / self.noise_inverse_retouch
+        eps = self.get_noise(x * c_in, t, cond_in, step)
+        denoised = x + eps * c_out
+        slope = (x - denoised) / sigma_to
+        return x + slope * (sigma_to - sigma_from)
+
     @noise_inverse
     @torch.no_grad()
     def find_noise_for_image_sigma_adjustment(self, dnw, steps: int, prompts: List[str]) -> Tensor:
-        """Euler integration of the probability-flow ODE from the image towards noise, each eps evaluated by the tiled
-        denoiser `get_noise` (abstractdiffusion.py:681-742, after the WebUI's img2imgalt script)."""
+        """The latent the sampler would have started from to arrive at the input image (abstractdiffusion.py:681-742):
+        integrate the ODE from the image towards noise over the reversed k-diffusion schedule, one tiled denoiser call per
+        interval, and return it in units of the largest sigma.  Interruptible between intervals (returns what it has)."""
         assert self.p.sampler_name == "Euler"
         shared = host.get_shared()
         state = shared.state
-
-        x = self.p.init_latent
-        s_in = x.new_ones([x.shape[0]])
-        skip = 1 if shared.sd_model.parameterization == "v" else 0
-        sigmas = dnw.get_sigmas(steps).flip(0)
-
-        cond = self.p.sd_model.get_learned_conditioning(prompts)
-        if isinstance(cond, Tensor):        # SD1 / SD2
-            cond_in = self.make_cond_dict({"c_crossattn": [], "c_concat": []}, cond, self.p.image_conditioning)
-        else:                               # SDXL
-            cond_in = self.make_cond_dict({"crossattn": None, "vector": None, "c_concat": []}, cond["crossattn"],
-                                          self.p.image_conditioning, cond["vector"])
-
+        skip = 1 if shared.sd_model.parameterization == "v" else 0      # v-models return (c_skip, c_out, c_in)
+        schedule = dnw.get_sigmas(steps).flip(0)                         # ascending: 0 -> sigma_max
+        cond_in = self._inversion_conditioning(prompts)
         state.sampling_steps = steps
         pbar = None
         if getattr(self.p, "show_tile_progress", True):
             from tqdm import tqdm
             pbar = tqdm(total=steps, desc="Noise Inversion")
-        for i in range(1, len(sigmas)):
+        x = self.p.init_latent
+        for k in range(1, len(schedule)):
             if state.interrupted:
                 return x
             state.sampling_step += 1
-
-            sigma_in = torch.cat([sigmas[i] * s_in])
-            c_out, c_in = [k[(...,) + (None,) * (x.ndim - k.ndim)] for k in dnw.get_scalings(sigma_in)[skip:]]
-            t = dnw.sigma_to_t(sigma_in) / self.noise_inverse_retouch
-
-            eps = self.get_noise(x * c_in, t, cond_in, steps - i)
-            denoised = x + eps * c_out
-
-            d = (x - denoised) / sigmas[i]          # Euler step towards the next (larger) sigma
-            x = x + d * (sigmas[i] - sigmas[i - 1])
+            x = self._inversion_interval(dnw, x, schedule[k - 1], schedule[k], cond_in, steps - k, skip)
             host.store_latent(x)
-            del sigma_in, c_out, c_in, t, eps, denoised, d
             if pbar is not None:
                 pbar.update(1)
         if pbar is not None:
             pbar.close()
-        return x / sigmas[-1]
+        return x / schedule[-1]
 
     @noise_inverse
     @torch.no_grad()
@@ -697,9 +700,22 @@ class AbstractDiffusion:
         hi = min((batch_id + 1) * self.tile_bs, self.num_tiles) * rows_per_tile
         return tiles[lo:hi]
 
+    def _side_input_tiles(self, full: Tensor, scale: int, park_on_cpu: bool):
+        """(per tile batch, per custom region) crops of one side input living at `scale` x the latent resolution."""
+        park = (lambda t: t.cpu()) if park_on_cpu else (lambda t: t)
+        per_batch, per_region = [], []
+        if self.batched_bboxes:
+            tiles = self._crop_side_input(full, scale)
+            rows = full.shape[0]
+            per_batch = [park(self._batch_rows(tiles, b, rows)) for b in range(len(self.batched_bboxes))]
+        for bbox in self.custom_bboxes:
+            per_region.append(park(full[:, :, bbox[1] * scale:bbox[3] * scale, bbox[0] * scale:bbox[2] * scale]))
+        return per_batch, per_region
+
     @controlnet
     def init_controlnet(self, controlnet_script, control_tensor_cpu: bool):
-        """abstractdiffusion.py:454-464."""
+        """Register the ControlNet extension's script object; its hints are cropped once per job
+        (abstractdiffusion.py:454-464)."""
         self.enable_controlnet = True
         self.controlnet_script = controlnet_script
         self.control_tensor_cpu = control_tensor_cpu
@@ -708,117 +724,102 @@ class AbstractDiffusion:
         self.control_tensor_custom = []
         self.prepare_controlnet_tensors()
 
+    def _control_params(self):
+        return self.control_params if (self.enable_controlnet and self.control_tensor_batch is not None) else []
+
     @controlnet
     def reset_controlnet_tensors(self):
-        """Give the ControlNet its full-size hints back (abstractdiffusion.py:466-472)."""
-        if not self.enable_controlnet or self.control_tensor_batch is None:
-            return
-        for param_id in range(len(self.control_params)):
-            self.control_params[param_id].hint_cond = self.org_control_tensor_batch[param_id]
+        """Hand every ControlNet unit its full-size hint back (abstractdiffusion.py:466-472)."""
+        for unit, full in zip(self._control_params(), getattr(self, "org_control_tensor_batch", [])):
+            unit.hint_cond = full
 
     @controlnet
     def prepare_controlnet_tensors(self, refresh: bool = False):
-        """Crop every ControlNet hint into the tile batches once and cache them (abstractdiffusion.py:474-518).
-        Hints live in pixel space: the tile list is scaled by opt_f.  The tiles of one hint sit in ONE tensor
-        (a scatter launch); `control_tensor_batch[param][batch]` are views of it."""
+        """Crop the hint of every ControlNet unit into the tile batches and the custom regions, once per job
+        (abstractdiffusion.py:474-518).  Hints live in pixel space, i.e. at opt_f x the latent grid; all grid tiles of
+        one hint come from ONE scatter launch and `control_tensor_batch[unit][batch]` are views of its output."""
         if not refresh and (self.control_tensor_batch is not None or self.control_params is not None):
             return
         if not self.enable_controlnet or self.controlnet_script is None:
             return
-        latest_network = self.controlnet_script.latest_network
-        if latest_network is None or not hasattr(latest_network, "control_params"):
+        network = self.controlnet_script.latest_network
+        if network is None or not hasattr(network, "control_params"):
             return
-        self.control_params = latest_network.control_params
-        tensors = [param.hint_cond for param in latest_network.control_params]
-        self.org_control_tensor_batch = tensors
-        if len(tensors) == 0:
+        self.control_params = network.control_params
+        self.org_control_tensor_batch = [unit.hint_cond for unit in self.control_params]
+        if not self.org_control_tensor_batch:
             return
-
-        self.control_tensor_batch = []
-        self.control_tensor_custom = []                 # (the reference keeps stale entries here on refresh)
-        for control_tensor in tensors:
-            if control_tensor.dim() == 3:
-                control_tensor.unsqueeze_(0)            # in place, like the reference: the param sees 4-d from now on
-            per_batch = []
-            if self.enable_grid_bbox or self.batched_bboxes:
-                tiles = self._crop_side_input(control_tensor, opt_f)
-                rows = control_tensor.shape[0]
-                for batch_id in range(len(self.batched_bboxes)):
-                    tile = self._batch_rows(tiles, batch_id, rows)
-                    per_batch.append(tile.cpu() if self.control_tensor_cpu else tile)
+        self.control_tensor_batch, self.control_tensor_custom = [], []      # (the reference keeps stale region crops on refresh)
+        for hint in self.org_control_tensor_batch:
+            if hint.dim() == 3:
+                hint.unsqueeze_(0)          # in place, like the reference: the unit sees a 4-d hint from now on
+            per_batch, per_region = self._side_input_tiles(hint, opt_f, self.control_tensor_cpu)
             self.control_tensor_batch.append(per_batch)
-            if len(self.custom_bboxes) > 0:
-                custom = []
-                for bbox in self.custom_bboxes:
-                    tile = control_tensor[:, :, bbox[1] * opt_f:bbox[3] * opt_f, bbox[0] * opt_f:bbox[2] * opt_f]
-                    custom.append(tile.cpu() if self.control_tensor_cpu else tile)
-                self.control_tensor_custom.append(custom)
+            if per_region:
+                self.control_tensor_custom.append(per_region)
 
     @controlnet
     def switch_controlnet_tensors(self, batch_id: int, x_batch_size: int, tile_batch_size: int, is_denoise=False):
-        """Point every ControlNet at the hint tiles of this tile batch (abstractdiffusion.py:520-535): k-diffusion
-        wants each tile's hint x_batch_size times in a row, DDIM the whole batch repeated."""
-        if not self.enable_controlnet or self.control_tensor_batch is None:
-            return
-        for param_id in range(len(self.control_params)):
-            control_tile = self.control_tensor_batch[param_id][batch_id]
+        """Point every ControlNet unit at the hint crops of tile batch `batch_id`, replicated the way the sampler
+        replicates the latent (abstractdiffusion.py:520-535): k-diffusion keeps the x_batch_size copies of a tile
+        adjacent, the DDIM family repeats the whole tile batch (twice more when cond and uncond run together)."""
+        for unit_id, unit in enumerate(self._control_params()):
+            crops = self.control_tensor_batch[unit_id][batch_id]
             if self.is_kdiff:
-                control_tile = control_tile[:tile_batch_size].repeat_interleave(x_batch_size, dim=0)
+                crops = crops[:tile_batch_size].repeat_interleave(x_batch_size, dim=0)
             else:
-                control_tile = control_tile.repeat([x_batch_size if is_denoise else x_batch_size * 2, 1, 1, 1])
-            self.control_params[param_id].hint_cond = control_tile.to(host.device())
+                crops = crops.repeat([x_batch_size * (1 if is_denoise else 2), 1, 1, 1])
+            unit.hint_cond = crops.to(host.device())
 
     @controlnet
     def set_custom_controlnet_tensors(self, bbox_id: int, repeat_size: int):
-        """abstractdiffusion.py:537-544."""
+        """The hint crop of custom region `bbox_id`, once per latent in the region's batch (abstractdiffusion.py:537-544)."""
         if not self.enable_controlnet or not len(self.control_tensor_custom):
             return
-        for param_id in range(len(self.control_params)):
-            control_tensor = self.control_tensor_custom[param_id][bbox_id].to(host.device())
-            self.control_params[param_id].hint_cond = control_tensor.repeat((repeat_size, 1, 1, 1))
+        for unit_id, unit in enumerate(self.control_params):
+            unit.hint_cond = self.control_tensor_custom[unit_id][bbox_id].to(host.device()).repeat((repeat_size, 1, 1, 1))
+
+    def _stablesr_model(self):
+        script = getattr(self, "stablesr_script", None)
+        model = getattr(script, "stablesr_model", None) if script is not None else None
+        return model if self.enable_stablesr else None
 
     @stablesr
     def init_stablesr(self, stablesr_script):
-        """abstractdiffusion.py:547-568: StableSR hands over its latent image through a hook; it is cropped into the
-        tile batches (latent space, the grid as is) with one scatter launch."""
+        """StableSR publishes its conditioning latent through a hook (abstractdiffusion.py:547-568); when it does, crop
+        it into the tile batches and regions (latent space: the grid as is, one scatter launch)."""
         if stablesr_script.stablesr_model is None:
             return
         self.stablesr_script = stablesr_script
 
-        def set_image_hook(latent_image):
+        def on_latent_image(latent_image):
             self.enable_stablesr = True
             self.stablesr_tensor = latent_image
-            self.stablesr_tensor_batch = []
-            if self.batched_bboxes:
-                tiles = self._crop_side_input(latent_image, 1)
-                rows = latent_image.shape[0]
-                self.stablesr_tensor_batch = [self._batch_rows(tiles, b, rows) for b in range(len(self.batched_bboxes))]
-            if len(self.custom_bboxes) > 0:
-                self.stablesr_tensor_custom = [latent_image[:, :, bbox[1]:bbox[3], bbox[0]:bbox[2]] for bbox in self.custom_bboxes]
+            per_batch, per_region = self._side_input_tiles(latent_image, 1, False)
+            self.stablesr_tensor_batch = per_batch
+            if per_region:
+                self.stablesr_tensor_custom = per_region
 
-        stablesr_script.stablesr_model.set_image_hooks["TiledDiffusion"] = set_image_hook
+        stablesr_script.stablesr_model.set_image_hooks["TiledDiffusion"] = on_latent_image
 
     @stablesr
     def reset_stablesr_tensors(self):
-        if not self.enable_stablesr or self.stablesr_script.stablesr_model is None:
-            return
-        self.stablesr_script.stablesr_model.latent_image = self.stablesr_tensor
+        model = self._stablesr_model()
+        if model is not None:
+            model.latent_image = self.stablesr_tensor
 
     @stablesr
     def switch_stablesr_tensors(self, batch_id: int):
-        if not self.enable_stablesr or self.stablesr_script.stablesr_model is None:
-            return
-        if self.stablesr_tensor_batch is None:
-            return
-        self.stablesr_script.stablesr_model.latent_image = self.stablesr_tensor_batch[batch_id]
+        model = self._stablesr_model()
+        if model is not None and self.stablesr_tensor_batch is not None:
+            model.latent_image = self.stablesr_tensor_batch[batch_id]
 
     @stablesr
     def set_custom_stablesr_tensors(self, bbox_id: int):
-        if not self.enable_stablesr or self.stablesr_script.stablesr_model is None:
-            return
-        if not len(getattr(self, "stablesr_tensor_custom", [])):
-            return
-        self.stablesr_script.stablesr_model.latent_image = self.stablesr_tensor_custom[bbox_id]
+        model = self._stablesr_model()
+        crops = getattr(self, "stablesr_tensor_custom", [])
+        if model is not None and len(crops):
+            model.latent_image = crops[bbox_id]
 
     # ----------------------------------------------------------- engine glue
     def _check_input(self, x_in: Tensor) -> Tensor:
