@@ -250,6 +250,23 @@ int td_blend_multidiffusion_rows(const td_grid* g, const void* const* batch_ptrs
  * sees what the signalling ranks wrote before their td_peer_signal. */
 int td_peer_wait(const uint32_t* flags, int count, const uint32_t* value, void* stream);
 
+/* Region prompt control (custom bboxes): everything after the regions' denoiser calls in ONE launch --
+ * multidiffusion.py:187-216 / mixtureofdiffusers.py:145-175.  x_buffer: the grid accumulator [N,C,H,W] of `dtype`
+ * (zeros when the background layer is off).  Regions in list order; mode 0 = BACKGROUND (added into the accumulator,
+ * multiplied by the fp32 [h*w] `aux` when given: Mixture of Diffusers' custom_weights), mode 1 = FOREGROUND (`aux` =
+ * fp32 [h*w] feather mask: averaged over overlapping regions and laid over the normalised background).
+ * weights: fp32 [H*W] divide-where->1 canvas (MultiDiffusion) or NULL (Mixture of Diffusers).  out: fp32 [N,C,H,W].
+ * Every rounding of the reference's tensor expressions is reproduced (see csrc/td_region.cu). */
+#define TD_MAX_REGIONS 32
+typedef struct td_region {
+    int32_t x, y, w, h;
+    int32_t mode;
+    const void* out;     /* region denoiser output [N, C, h, w] of `dtype`, device */
+    const float* aux;
+} td_region;
+int td_region_composite(const void* x_buffer, const float* weights, const td_region* regions, int n_regions,
+                        int N, int C, int H, int W, int dtype, float* out, void* stream);
+
 /* ------------------------------------------------------------------------- *
  *  DemoFusion extras (tile_methods/demofusion.py).
  * ------------------------------------------------------------------------- */

@@ -56,6 +56,14 @@ class TdGrid(ctypes.Structure):
     ]
 
 
+TD_MAX_REGIONS = 32
+
+
+class TdRegion(ctypes.Structure):
+    """struct td_region (include/td_b200.h)."""
+    _fields_ = [("x", c_int32), ("y", c_int32), ("w", c_int32), ("h", c_int32), ("mode", c_int32), ("out", c_void_p), ("aux", c_void_p)]
+
+
 class TdConvDesc(ctypes.Structure):
     """struct td_conv_desc (include/td_b200.h)."""
     _fields_ = [
@@ -104,6 +112,7 @@ _SIGNATURES = {
     "td_blend_multidiffusion_rows": (c_int, [POINTER(TdGrid), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_uint32, c_void_p]),
     "td_peer_wait": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "td_region_composite": (c_int, [c_void_p, c_void_p, POINTER(TdRegion), c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "td_dilated_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int32),
                                   POINTER(c_int32), POINTER(c_int32), c_int, c_int, c_void_p]),
     "td_demofusion_combine": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,

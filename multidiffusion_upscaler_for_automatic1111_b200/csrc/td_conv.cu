@@ -316,11 +316,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     if (et == 0) bulk_wait_read<1>();
                     named_bar_sync(1, 128);
                     const uint32_t sbuf = store0 + (uint32_t)buf * kConvStoreBuf;
-                    for (int g16 = 0; g16 < p.chunk_cols / 16; ++g16) {
-                        uint32_t r[16];
-                        __syncwarp();
-                        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * acc_cols + (uint32_t)(mt * p.BN + ch * p.chunk_cols + g16 * 16), r);
-                        tc_wait_ld();
+                    // all TMEM loads of the chunk in flight before the single wait (up to 64 columns = 64 registers)
+                    uint32_t racc[4][16];
+                    const int ng = p.chunk_cols / 16;
+                    __syncwarp();
+                    const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * acc_cols + (uint32_t)(mt * p.BN + ch * p.chunk_cols);
+                    tc_ld16(tcol, racc[0]);
+                    if (ng > 1) tc_ld16(tcol + 16u, racc[1]);
+                    if (ng > 2) { tc_ld16(tcol + 32u, racc[2]); tc_ld16(tcol + 48u, racc[3]); }
+                    tc_wait_ld();
+                    // residual rows of this chunk: issued early, consumed per group below
+                    const bool has_res = residual != nullptr && pix_ok;
+#pragma unroll
+                    for (int g16 = 0; g16 < 4; ++g16) {
+                        if (g16 >= ng) break;
+                        const uint32_t (&r)[16] = racc[g16];
                         float v[16];
                         const int cb = col0 + g16 * 16;
                         if (bias != nullptr && !p.bias_per_row && cb + 16 <= p.Cout) {      // 16 bias values: four 128-bit loads
@@ -344,7 +354,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 v[j] = __fmaf_rn(__uint_as_float(r[j]), p.alpha, b);
                             }
                         }
-                        if (residual != nullptr && pix_ok && cb + 16 <= p.Cout) {
+                        if (has_res && cb + 16 <= p.Cout) {
                             const uint4* rp = reinterpret_cast<const uint4*>(residual + pix * p.res_pitch + cb);
                             const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
                             const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -497,7 +507,11 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
         const int want_mt = fm != nullptr ? atoi(fm) : 2;
         const long long sub_tiles = (long long)d->N * ((d->OW + p.BWs - 1) / p.BWs) * ((d->OH + p.BHs - 1) / p.BHs) * p.n_blocks;
         // two sub-tiles per CTA when the grid stays full (>= 4 sub-tiles per SM) and the box fits (<= 256 per dimension)
-        p.MT = (want_mt >= 2 && sub_tiles >= 4LL * dev.sms && bn >= 32 && (p.BWs + p.sub_dx) * d->stride <= 256 && (p.BHs + p.sub_dy) * d->stride <= 256) ? 2 : 1;
+        // ... and while two accumulator stages still fit in TMEM (BN <= 128): with one stage the epilogue no longer overlaps
+        // the next tile's MMAs (measured: 256 -> 256 at 472^2 drops from 1309 to 1110 TFLOP/s, 128 -> 128 at 944^2 rises
+        // from 859 to 1035); TD_CONV_MT=3 forces two sub-tiles for any BN (measurement only)
+        const bool fits2 = 2 * 2 * bn <= 512 || want_mt >= 3;
+        p.MT = (want_mt >= 2 && fits2 && sub_tiles >= 4LL * dev.sms && bn >= 32 && (p.BWs + p.sub_dx) * d->stride <= 256 && (p.BHs + p.sub_dy) * d->stride <= 256) ? 2 : 1;
     }
     p.BW = p.BWs + (p.MT - 1) * p.sub_dx;
     p.BH = p.BHs + (p.MT - 1) * p.sub_dy;
