@@ -233,3 +233,32 @@ def blend_bboxes(batch_outs: Sequence[torch.Tensor], tile_bs: int, origins_dev: 
         check(lib.td_blend_bboxes(ptrs, len(batch_outs), int(tile_bs), origins_dev.data_ptr(), origins_host, int(n_tiles), N, C, H, W,
                                   int(tile_h), int(tile_w), dtype_code(dt), out.data_ptr(), current_stream_ptr(dev)))
     return out
+
+
+def region_composite(x_buffer: torch.Tensor, weights: Optional[torch.Tensor], regions: Sequence[tuple], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Everything after the custom regions' denoiser calls in one launch (multidiffusion.py:187-216,
+    mixtureofdiffusers.py:145-175).  regions: [(x, y, w, h, mode, region_out [N,C,h,w], aux fp32 [h,w] or None)] in list
+    order, mode 0 BACKGROUND (aux = optional multiplier) / 1 FOREGROUND (aux = feather mask).  weights: the fp32
+    divide-where->1 canvas (MultiDiffusion) or None.  Returns fp32 [N,C,H,W]."""
+    from ._cabi import TdRegion
+    _require_cuda(x_buffer, "x_buffer")
+    N, C, H, W = x_buffer.shape
+    xb = x_buffer.contiguous()
+    arr = (TdRegion * max(1, len(regions)))()
+    keep = []
+    for i, (rx, ry, rw, rh, mode, r_out, aux) in enumerate(regions):
+        _require_cuda(r_out, "region output")
+        ro = r_out.to(xb.dtype).contiguous()
+        if tuple(ro.shape) != (N, C, rh, rw):
+            raise ValueError(f"region {i}: output shape {tuple(ro.shape)} != {(N, C, rh, rw)}")
+        ax = None
+        if aux is not None:
+            ax = aux.to(device=xb.device, dtype=torch.float32).expand(rh, rw).contiguous() if aux.dim() == 2 else \
+                aux.to(device=xb.device, dtype=torch.float32).reshape(rh, rw).contiguous()
+        keep += [ro, ax]
+        arr[i] = TdRegion(int(rx), int(ry), int(rw), int(rh), int(mode), ro.data_ptr(), ax.data_ptr() if ax is not None else None)
+    res = out if out is not None else torch.empty((N, C, H, W), dtype=torch.float32, device=xb.device)
+    with torch.cuda.device(xb.device):
+        check(lib.td_region_composite(xb.data_ptr(), weights.data_ptr() if weights is not None else None, arr, len(regions), N, C, H, W,
+                                      dtype_code(xb.dtype), res.data_ptr(), current_stream_ptr(xb.device)))
+    return res

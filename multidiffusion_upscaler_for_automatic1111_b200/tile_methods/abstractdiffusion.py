@@ -488,45 +488,35 @@ class AbstractDiffusion:
 
     _INTERRUPTED = object()
 
-    def _custom_region_pass(self, x: Tensor, custom_func: Callable, add_background: Callable, poll_interrupt: bool):
+    def _custom_region_pass(self, x: Tensor, custom_func: Callable, poll_interrupt: bool):
         """Second half of a tiled step (multidiffusion.py:170-204, mixtureofdiffusers.py:128-165): every custom region is
-        cropped from the latent, denoised by `custom_func`, and either added to `x_buffer` (BACKGROUND, through
-        `add_background`) or collected into the feather buffers (FOREGROUND).
+        cropped from the latent and denoised by `custom_func`.  The adds into x_buffer / the feather buffers are NOT done
+        here: the outputs are collected and composited in one launch by `_composite_regions`.
 
-        Returns None, the feather triple (buffer, mask, count), or `_INTERRUPTED`."""
-        N, C, H, W = x.shape
-        feather = None
+        Returns [(bbox_id, bbox, x_tile_out)] or `_INTERRUPTED`."""
+        done = []
         use_networks = not getattr(self.p, "disable_extra_networks", False)
         for bbox_id, bbox in enumerate(self.custom_bboxes):
             if poll_interrupt and host.interrupted():
                 return self._INTERRUPTED
             if use_networks:
                 host.extra_networks_activate(self.p, bbox.extra_network_data)
-            x_tile_out = custom_func(x[bbox.slicer], bbox_id, bbox)
-            if bbox.blend_mode == BlendMode.BACKGROUND:
-                add_background(bbox_id, bbox, x_tile_out)
-            elif bbox.blend_mode == BlendMode.FOREGROUND:
-                if feather is None:
-                    feather = (torch.zeros_like(self.x_buffer), torch.zeros((1, 1, H, W), device=x.device),
-                               torch.zeros((1, 1, H, W), device=x.device))
-                if bbox.feather_mask.device != x.device:
-                    bbox.feather_mask = bbox.feather_mask.to(x.device)
-                feather[0][bbox.slicer] += x_tile_out
-                feather[1][bbox.slicer] += bbox.feather_mask
-                feather[2][bbox.slicer] += 1
+            done.append((bbox_id, bbox, custom_func(x[bbox.slicer], bbox_id, bbox)))
             if use_networks:
                 host.extra_networks_deactivate(self.p, bbox.extra_network_data)
             self.update_pbar()
-        return feather
+        return done
 
-    @staticmethod
-    def _feather_composite(x_out: Tensor, feather: Tuple[Tensor, Tensor, Tensor]) -> Tensor:
-        """multidiffusion.py:210-216 / mixtureofdiffusers.py:168-173: average overlapping foreground regions, then
-        lay them over the background with their (averaged) feather masks."""
-        buf, mask, count = feather
-        buf = torch.where(count > 1, buf / count, buf)
-        mask = torch.where(count > 1, mask / count, mask)
-        return torch.where(count > 0, x_out * (1 - mask) + buf * mask, x_out)
+    def _composite_regions(self, x_buffer: Tensor, weights: Optional[Tensor], done, background_aux=None) -> Tensor:
+        """x_buffer (grid accumulator) + the collected region outputs -> the step's result, fp32 (td_region_composite:
+        BACKGROUND adds in list order, normalisation by `weights` when given, FOREGROUND feather average and overlay)."""
+        regions = []
+        for bbox_id, bbox, out in done:
+            if bbox.blend_mode == BlendMode.BACKGROUND:
+                regions.append((bbox.x, bbox.y, bbox.w, bbox.h, 0, out, background_aux(bbox_id) if background_aux is not None else None))
+            elif bbox.blend_mode == BlendMode.FOREGROUND:
+                regions.append((bbox.x, bbox.y, bbox.w, bbox.h, 1, out, bbox.feather_mask))
+        return engine.region_composite(x_buffer, weights.view(x_buffer.shape[2], x_buffer.shape[3]) if weights is not None else None, regions)
 
     # -------------------------------------------------- tiled noise inversion
     @noise_inverse

@@ -112,16 +112,14 @@ class MixtureOfDiffusers(AbstractDiffusion):
             c_out = self.make_cond_dict(c_in, tcond, icond, self.get_vcond(c_in))
             return sd_model.apply_model(x_tile, t_in, cond=c_out)
 
-        def add_background(bbox_id: int, bbox: CustomBBox, x_tile_out: Tensor):
-            cw = self.custom_weights[bbox_id]
-            if cw.device != x.device:
-                cw = self.custom_weights[bbox_id] = cw.to(x.device)
-            self.x_buffer[bbox.slicer] += x_tile_out * cw
-
-        feather = self._custom_region_pass(x, custom_func, add_background, poll_interrupt=False)
-        if feather is None:
-            return self.x_buffer
-        return self._feather_composite(self.x_buffer, feather)
+        done = self._custom_region_pass(x, custom_func, poll_interrupt=False)
+        # mixtureofdiffusers.py:145-175 in one launch: BACKGROUND adds weighted by the pre-rescaled custom weights, no
+        # normalisation, FOREGROUND feather overlay
+        out = self._composite_regions(self.x_buffer, None, done, background_aux=lambda bbox_id: self.custom_weights[bbox_id])
+        if any(b.blend_mode == BlendMode.FOREGROUND for _, b, _ in done):
+            return out                       # the reference's overlay promotes to fp32 (fp32 mask)
+        self.x_buffer.copy_(out)             # BACKGROUND only: the reference returns x_buffer itself (x_in.dtype; lossless)
+        return self.x_buffer
 
     def _denoise_tile_batch(self, sd_model, x_tile: Tensor, n_rep: int, t_in: Tensor, c_in: CondDict, icond_tile, batch_id: int,
                             N: int) -> Tensor:

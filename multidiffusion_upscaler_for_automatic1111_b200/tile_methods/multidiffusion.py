@@ -154,9 +154,6 @@ class MultiDiffusion(AbstractDiffusion):
         x = self._check_input(x_in)
         self._step_token = self.__dict__.get("_step_token", 0) + 1     # memoised per-batch inputs are re-validated once per step
         regions = self.enable_custom_bbox and len(self.custom_bboxes) > 0
-        # a BACKGROUND region is added to x_buffer BEFORE the division, so the un-normalised buffer is needed
-        needs_buffer = regions and any(b.blend_mode == BlendMode.BACKGROUND for b in self.custom_bboxes)
-
         if self._shard is not None:
             if regions:
                 raise NotImplementedError("region prompt control is not combined with the multi-GPU tile shard yet")
@@ -178,10 +175,10 @@ class MultiDiffusion(AbstractDiffusion):
                 outs.append(repeat_func(views[batch_id], bboxes))
                 if self.pbar is not None:
                     self.update_pbar()
-            if needs_buffer:
-                self.reset_buffer(x)
+            if regions:
+                self.reset_buffer(x)        # the regions composite on top of the UN-normalised accumulator
             x_out = engine.blend_multidiffusion(self._grid, outs, N, C, self.tile_bs, self.weights, x.dtype,
-                                                x_buffer=self.x_buffer if needs_buffer else None, flags=self._blend_flags,
+                                                x_buffer=self.x_buffer if regions else None, flags=self._blend_flags,
                                                 rcp_weights=self._rcp_weights)
             if not regions:
                 return x_out
@@ -189,23 +186,12 @@ class MultiDiffusion(AbstractDiffusion):
             # draw_background=False: only the custom regions paint (multidiffusion.py:146 skips the grid loop)
             self.reset_buffer(x)
             self.x_buffer.zero_()
-            needs_buffer = True
 
-        if not needs_buffer:
-            self.reset_buffer(x)        # shape / dtype template of the feather buffer only
-
-        def add_background(bbox_id: int, bbox: CustomBBox, x_tile_out: Tensor):
-            self.x_buffer[bbox.slicer] += x_tile_out
-
-        feather = self._custom_region_pass(x, custom_func, add_background, poll_interrupt=True)
-        if feather is self._INTERRUPTED:
+        done = self._custom_region_pass(x, custom_func, poll_interrupt=True)
+        if done is self._INTERRUPTED:
             return x_in
-        if needs_buffer:
-            # multidiffusion.py:208 on the buffer that now holds grid tiles + BACKGROUND regions
-            x_out = torch.where(self.weights > 1, self.x_buffer / self.weights, self.x_buffer)
-        if feather is not None:
-            x_out = self._feather_composite(x_out, feather)
-        return x_out
+        # multidiffusion.py:187-216 in one launch: BACKGROUND adds, divide where weights > 1, FOREGROUND feather overlay
+        return self._composite_regions(self.x_buffer, self.weights, done)
 
     def _sample_one_step_sharded(self, x_in: Tensor, x: Tensor, repeat_func: Callable, N: int, C: int) -> Tensor:
         """This rank's tiles, then the exchange + deterministic blend (init_tile_shard).

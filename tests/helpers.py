@@ -35,6 +35,34 @@ def assert_bit_equal(a: torch.Tensor, b: torch.Tensor, what: str = "", allow_sig
         raise AssertionError(f"{what}: values equal but {nz} elements differ in bit pattern (sign of zero / NaN payload)")
 
 
+def region_composite_reference(x_buffer, weights, regions, out=None):
+    """The reference's tensor expressions (multidiffusion.py:187-216, mixtureofdiffusers.py:145-175) on CPU tensors:
+    what td_region_composite fuses on the device."""
+    N, C, H, W = x_buffer.shape
+    buf = x_buffer.clone()
+    fb = fm = fc = None
+    for (x, y, w, h, mode, r_out, aux) in regions:
+        sl = (slice(None), slice(None), slice(y, y + h), slice(x, x + w))
+        if mode == 0:
+            buf[sl] += r_out if aux is None else r_out * aux
+        else:
+            if fb is None:
+                fb, fm, fc = torch.zeros_like(buf), torch.zeros((1, 1, H, W)), torch.zeros((1, 1, H, W))
+            fb[sl] += r_out
+            fm[sl] += aux
+            fc[sl] += 1
+    res = buf
+    if weights is not None:
+        wv = weights.view(1, 1, H, W)
+        res = torch.where(wv > 1, buf / wv, buf)
+    if fb is not None:
+        fb = torch.where(fc > 1, fb / fc, fb)
+        fm = torch.where(fc > 1, fm / fc, fm)
+        res = torch.where(fc > 0, res * (1 - fm) + fb * fm, res)
+    return res.float()
+
+
+
 def install_demofusion_stand_ins(set_attr=setattr):
     """Swap every device entry point DemoFusion.sample_one_step uses for torch-CPU stand-ins (the kernels themselves are
     pinned by the gpu tests): what remains under test is the delegate's plumbing -- window / view order, the mixture

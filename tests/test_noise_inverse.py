@@ -94,6 +94,8 @@ def _oracle_engine(monkeypatch):
             x_buffer.copy_(buf)
         return blend.normalise_md(buf, weights)
 
+    from helpers import region_composite_reference
+    monkeypatch.setattr(engine, "region_composite", region_composite_reference)
     monkeypatch.setattr(engine, "scatter_tiles", scatter_tiles)
     monkeypatch.setattr(engine, "blend_multidiffusion", blend_multidiffusion)
     monkeypatch.setattr(abstractdiffusion.AbstractDiffusion, "_check_input", lambda self, x: x.contiguous())

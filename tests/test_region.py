@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import DTYPES, assert_bit_equal
+from helpers import region_composite_reference, DTYPES, assert_bit_equal
 from oracle import blend, region, synth, tiling
 from oracle.make_golden import REGION_CASES, REGION_DTYPES, REGION_GRID
 
@@ -139,6 +139,7 @@ def _oracle_engine(monkeypatch):
         blend.accumulate_mod(x_buffer, torch.cat(list(outs), dim=0), bbs(g), N, tile_weights, rescale)
         return x_buffer
 
+    monkeypatch.setattr(engine, "region_composite", region_composite_reference)
     monkeypatch.setattr(engine, "scatter_tiles", scatter_tiles)
     monkeypatch.setattr(engine, "blend_multidiffusion", blend_multidiffusion)
     monkeypatch.setattr(engine, "blend_mixture", blend_mixture)
