@@ -40,6 +40,7 @@ IMAGE_MP = 4096 * 4096 / 1e6
 SAMPLER_STEPS = 50
 CFG = dict(N=2, C=4, H=512, W=512, tile=96, overlap=48, tile_bs=4)
 METRIC = "megapixels/sec final image (SD1.5 4K MultiDiffusion)"
+METRIC_MOD = "megapixels/sec final image (SD1.5 4K Mixture of Diffusers, gaussian tile weights)"
 
 
 def mp_per_s(sec_per_step: float) -> float:
@@ -109,7 +110,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_reference_step_fn():
+def cpu_reference_step_fn(method: str = "md"):
     """One sampler step of the reference's PyTorch tile path on the host cores, identity denoiser.
 
     When the reference tree is present (build container) this is the UNMODIFIED reference:
@@ -120,6 +121,9 @@ def cpu_reference_step_fn():
     from oracle import blend, ref_shim, synth, tiling
     c = CFG
     x = synth.latent(0, (c["N"], c["C"], c["H"], c["W"]), torch.float16)
+    if method == "mod":      # Mixture of Diffusers: op-for-op restatement (mixtureofdiffusers.py:61-179 grid part)
+        plan = tiling.GridPlan(c["W"], c["H"], c["tile"], c["tile"], c["overlap"], c["tile_bs"], True)
+        return (lambda: blend.mixture_step(x, plan.batched_bboxes, plan.tile_weights, plan.rescale_factor, lambda t, bb: t)), "port"
     if ref_shim.available():
         ref = ref_shim.load()
         p = ref_shim.make_p(c["W"] * 8, c["H"] * 8)
@@ -152,8 +156,8 @@ def pick_cpu_threads(step) -> int:
     return best
 
 
-def run_cpu(steps: int, warmup: int, budget_s: float = None):
-    step, kind = cpu_reference_step_fn()
+def run_cpu(steps: int, warmup: int, budget_s: float = None, method: str = "md"):
+    step, kind = cpu_reference_step_fn(method)
     threads = pick_cpu_threads(step)
     torch.set_num_threads(threads)
     for _ in range(max(warmup, 1)):
@@ -172,10 +176,11 @@ def run_cpu(steps: int, warmup: int, budget_s: float = None):
 def reference_arm(args, rank):
     if rank != 0:
         return
-    dt, done, threads, kind = run_cpu(args.steps, args.warmup)
+    mod = args.config == "cfg3"
+    dt, done, threads, kind = run_cpu(args.steps, args.warmup, method="mod" if mod else "md")
     v = mp_per_s(dt)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "MP/s", "n_gpus": args.gpus, "steps": done,
+        "impl": "reference", "metric": METRIC_MOD if mod else METRIC, "value": v, "unit": "MP/s", "n_gpus": args.gpus, "steps": done,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(),
         "cpu_baseline": {"value": v, "unit": "MP/s", "cores": threads, "kind": kind,
@@ -338,10 +343,13 @@ class Workload:
         es = 2
         self.bytes_scatter = (self.N * self.C * g.H * g.W + (self.t1 - self.t0) * self.N * self.C * g.tile_h * g.tile_w) * es
         self.bytes_blend = self.T * self.N * self.C * g.tile_h * g.tile_w * es + self.N * self.C * g.H * g.W * 4 + g.H * g.W * 4
+        # Mixture of Diffusers: tiles + x_buffer in the latent dtype + rescale canvas + gaussian tile weights
+        self.bytes_blend_mod = self.T * self.N * self.C * g.tile_h * g.tile_w * es + self.N * self.C * g.H * g.W * es + g.H * g.W * 4 + g.tile_h * g.tile_w * 4
         self.set_mb = (self.x[0].numel() * 2 + self.tiles_in[0].numel() * 2 + sum(o.numel() for o in self.outs[0]) * 2 +
                        self.x_out[0].numel() * 4 + (self.gathered[0].numel() * 2 if self.gathered else 0)) / 1e6
         self.stream = ctypes.c_void_p(0)
         self.exchange_mode = exchange if world > 1 else "none"
+        self.method = "md"
         self.peer = None
         self.step_no = 0
         if self.exchange_mode == "peer":
@@ -414,7 +422,10 @@ class Workload:
                                                     torch.float16, out=self.x_out[s])
             return
         self.exchange(s)
-        self.blend(s)
+        if self.method == "mod":
+            self.blend_mod(s)
+        else:
+            self.blend(s)
 
 
 def vae_kernel_rooflines(dev, stream, peak):
@@ -481,6 +492,12 @@ def gpu_arm(args, rank, world, local_rank):
         args.steps += args.steps & 1
         args.warmup = max(args.warmup, 4) + (max(args.warmup, 4) & 1)
     wl = Workload(dev, rank, world, nsets, args.exchange)
+    mod = args.config == "cfg3"
+    if mod:
+        if world > 1:
+            sys.exit("--config cfg3 is measured on one GPU (the Mixture-of-Diffusers delegate shards by all-gather: see tests/test_multi_rank.py)")
+        wl.method = "mod"
+        wl.blend_mod(0)
     stream = torch.cuda.Stream(dev)
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
 
@@ -521,6 +538,8 @@ def gpu_arm(args, rank, world, local_rank):
                 return event_time_ms(r, stream) / reps * 1e-3
             t_blend = only(wl.blend)
             t_scatter = only(wl.scatter)
+            wl.blend_mod(0)
+            t_mod = only(lambda s: wl.blend_mod(s, 0))
             t_blend_ser = only(lambda s: wl.blend(s, 32))      # TD_FLAG_NO_PDL: fully serialised launches
             t_scatter_ser = only(lambda s: wl.scatter(s, 32))
             if args.variants:
@@ -558,6 +577,9 @@ def gpu_arm(args, rank, world, local_rank):
                             "frac": wl.bytes_scatter / t_scatter / 1e9 / peak, "algorithmic_bytes": wl.bytes_scatter,
                             "avg_launch_us": t_scatter * 1e6, "avg_launch_us_no_pdl": t_scatter_ser * 1e6,
                             "traffic": load_traffic("scatter")},
+                "mixture": {"kernel": "blend_mod_async_kernel<half> (td_blend_mixture, Mixture of Diffusers, BASELINE cfg3's method)",
+                            "achieved": wl.bytes_blend_mod / t_mod / 1e9, "frac": wl.bytes_blend_mod / t_mod / 1e9 / peak,
+                            "algorithmic_bytes": wl.bytes_blend_mod, "avg_launch_us": t_mod * 1e6},
                 "note": "back-to-back launches inside a CUDA graph, programmatic dependent launch on (the next launch becomes "
                         "resident while this one drains; every global access still waits for completion); avg includes the "
                         "inter-kernel gap; *_no_pdl = same loop with plain stream serialisation",
@@ -572,9 +594,9 @@ def gpu_arm(args, rank, world, local_rank):
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
-        cpu_dt, cpu_done, cpu_threads, cpu_kind = run_cpu(10 ** 9, 2, budget_s=args.cpu_budget)
+        cpu_dt, cpu_done, cpu_threads, cpu_kind = run_cpu(10 ** 9, 2, budget_s=args.cpu_budget, method="mod" if mod else "md")
         line = {
-            "metric": METRIC, "value": mp_per_s(sec_per_step), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC_MOD if mod else METRIC, "value": mp_per_s(sec_per_step), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {**workload_config(), "buffer_sets": nsets, "set_mb": round(wl.set_mb, 1),
@@ -1051,8 +1073,8 @@ def main():
     ap.add_argument("--profile-e2e", action="store_true")
     ap.add_argument("--variants", action="store_true", help="print a table of per-kernel micro-timings to stderr")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg4"], help="BASELINE.json config: cfg2 = MultiDiffusion hot path "
-                    "(default, the headline), cfg4 = tiled VAE decode only")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"], help="BASELINE.json config: cfg2 = MultiDiffusion hot path "
+                    "(default, the headline), cfg3 = Mixture of Diffusers hot path, cfg4 = tiled VAE decode only")
     ap.add_argument("--vae-latent", type=int, default=1024, help="cfg4: latent edge (1024 -> 8192^2 image)")
     ap.add_argument("--vae-slow", action="store_true", help="cfg4: slow mode (GroupNorm statistics merged over all tiles at every site)")
     args = ap.parse_args()
