@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TD_ABI_VERSION 3
+#define TD_ABI_VERSION 4
 
 typedef enum td_status {
     TD_OK = 0,
@@ -336,6 +336,11 @@ typedef struct td_conv_desc {
     int32_t bias_per_row;
     float alpha;
     int64_t x_pitch, w_pitch, y_pitch, res_pitch;
+    /* optional epilogue stage: y = act(y * post_scale[co] + post_shift[co]) (fp32 [Cout] each, device; act 1 = SiLU) --
+     * the GroupNorm (+ SiLU) that follows the convolution when its statistics are already known (fast mode) */
+    const float* post_scale;
+    const float* post_shift;
+    int32_t post_act;
 } td_conv_desc;
 int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
                    void* y, void* stream);

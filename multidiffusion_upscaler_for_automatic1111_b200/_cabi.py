@@ -32,7 +32,7 @@ TD_MAX_GRID_DIM = 256
 TD_MAX_BATCH_PTRS = 128
 TD_MAX_PEERS = 16
 TD_IPC_HANDLE_BYTES = 64
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 DTYPE_CODE = {torch.float16: TD_F16, torch.bfloat16: TD_BF16, torch.float32: TD_F32}
 
@@ -72,6 +72,7 @@ class TdConvDesc(ctypes.Structure):
         ("OH", c_int32), ("OW", c_int32), ("dtype", c_int32), ("bias_per_row", c_int32),
         ("alpha", c_float),
         ("x_pitch", c_int64), ("w_pitch", c_int64), ("y_pitch", c_int64), ("res_pitch", c_int64),
+        ("post_scale", c_void_p), ("post_shift", c_void_p), ("post_act", c_int32),
     ]
 
 

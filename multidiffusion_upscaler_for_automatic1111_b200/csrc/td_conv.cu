@@ -65,6 +65,7 @@ struct ConvParams {
     int chunk_cols;            // columns per store chunk: min(64, BN)
     int is_bf16;
     int bias_per_row;          // bias indexed by output pixel (GEMM row) instead of channel
+    int post_act;              // with post_scale / post_shift: 1 = SiLU after the per-channel affine
     int cluster;               // CTAs per cluster (1, 2 or 4): consecutive pixel tiles share the weight tile by TMA multicast
     int m_tiles;               // NI * tiles_y * tiles_x
     int m_groups;              // ceil(m_tiles / cluster)
@@ -204,7 +205,8 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int g, int
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_d, const __grid_constant__ ConvParams p,
-                 const float* __restrict__ bias, const uint16_t* __restrict__ residual) {
+                 const float* __restrict__ bias, const uint16_t* __restrict__ residual, const float* __restrict__ post_scale,
+                 const float* __restrict__ post_shift) {
     extern __shared__ unsigned char conv_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kConvMaxStages], empty_bar[kConvMaxStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
@@ -362,6 +364,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             for (int j = 0; j < 8; ++j) {
                                 v[2 * j] += unpack_lo(rw[j], p.is_bf16);
                                 v[2 * j + 1] += unpack_hi(rw[j], p.is_bf16);
+                            }
+                        }
+                        if (post_scale != nullptr && cb + 16 <= p.Cout) {
+                            // the GroupNorm (+ SiLU) that follows this convolution, statistics frozen (fast mode):
+                            // y = act(v * scale[c] + shift[c]) on the fp32 accumulator, before the one rounding to fp16
+                            const float4* sc4 = reinterpret_cast<const float4*>(post_scale + cb);
+                            const float4* sh4 = reinterpret_cast<const float4*>(post_shift + cb);
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 sc = __ldg(sc4 + j4), sh = __ldg(sh4 + j4);
+                                v[4 * j4 + 0] = __fmaf_rn(v[4 * j4 + 0], sc.x, sh.x);
+                                v[4 * j4 + 1] = __fmaf_rn(v[4 * j4 + 1], sc.y, sh.y);
+                                v[4 * j4 + 2] = __fmaf_rn(v[4 * j4 + 2], sc.z, sh.z);
+                                v[4 * j4 + 3] = __fmaf_rn(v[4 * j4 + 3], sc.w, sh.w);
+                            }
+                            if (p.post_act) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
                             }
                         }
                         uint32_t o[8];
@@ -534,6 +554,8 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     p.chunk_cols = std::min(64, bn);
     p.is_bf16 = d->dtype == TD_BF16;
     p.bias_per_row = d->bias_per_row;
+    p.post_act = d->post_act;
+    if ((d->post_scale == nullptr) != (d->post_shift == nullptr)) { td_set_error("td_conv2d_nhwc: post_scale and post_shift come together"); return TD_ERR_INVALID_ARG; }
     p.alpha = d->alpha;
     p.res_pitch = residual != nullptr ? d->res_pitch : 0;
     const int stage_bytes = p.MT * kConvStageA + bn * 128;
@@ -580,7 +602,7 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = cl > 1 ? 1 : 0;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_kernel, ma, mb, md, p, bias, (const uint16_t*)residual);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_kernel, ma, mb, md, p, bias, (const uint16_t*)residual, d->post_scale, d->post_shift);
     if (le != cudaSuccess) { td_set_error("td_conv2d_nhwc: launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return TD_ERR_CUDA; }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { td_set_error("td_conv2d_nhwc: launch failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }

@@ -243,15 +243,30 @@ class TensorCoreBackend:
     def pixels(self, a) -> int:
         return a.shape[1] * a.shape[2]
 
-    def conv(self, a, op: Conv, skip):
+    fuses_norm = True      # conv(..., post=...) applies a following frozen GroupNorm (+ SiLU) in the epilogue
+
+    def conv(self, a, op: Conv, skip, post=None):
         wp, b, co, cout_rows, k = self._conv_w(op.module)
         if op.upsample_first:
             a = ops.upsample2x_nhwc(a)
         _, H, W, _ = a.shape
         if op.downsample:
             oh, ow = (H + 1 - 3) // 2 + 1, (W + 1 - 3) // 2 + 1
-            return ops.conv2d_nhwc(a, wp, b, ksize=3, stride=2, pad=(0, 0), out_hw=(oh, ow), residual=skip, cout=cout_rows)
-        return ops.conv2d_nhwc(a, wp, b, ksize=k, pad=(k // 2, k // 2), residual=skip, cout=cout_rows)
+            return ops.conv2d_nhwc(a, wp, b, ksize=3, stride=2, pad=(0, 0), out_hw=(oh, ow), residual=skip, cout=cout_rows, post=post)
+        return ops.conv2d_nhwc(a, wp, b, ksize=k, pad=(k // 2, k // 2), residual=skip, cout=cout_rows, post=post)
+
+    def norm_affine(self, op: Norm, mean, var):
+        """Per-channel (scale, shift, act) equivalent to custom_group_norm (+ SiLU) with these statistics:
+        y = x * gamma[c] / sqrt(var[g] + eps) + (beta[c] - mean[g] * gamma[c] / sqrt(var[g] + eps))."""
+        gamma, beta = self._affine(op.module)
+        c = op.module.num_channels
+        cpg = c // NUM_GROUPS
+        rstd = (1.0 / torch.sqrt(var.float() + GN_EPS)).repeat_interleave(cpg)
+        scale = rstd * gamma if gamma is not None else rstd
+        shift = -mean.float().repeat_interleave(cpg) * scale
+        if beta is not None:
+            shift = shift + beta
+        return scale.contiguous(), shift.contiguous(), bool(op.act)
 
     def shortcut(self, a, op: Skip):
         if op.module is None:
@@ -332,6 +347,7 @@ class Executor:
     def __init__(self, program: Program, backend):
         self.program, self.be = program, backend
         self.frozen: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = [None] * program.num_sites
+        self._affine_cache: Dict[int, tuple] = {}
 
     def _step(self, st: TileState, op) -> None:
         be = self.be
@@ -353,6 +369,7 @@ class Executor:
         """Advance until the next barrier site (returned; st.pc stays ON the Norm op) or the end / `stop` (None)."""
         opsq = self.program.ops
         end = len(opsq) if stop is None else stop
+        fuse = getattr(self.be, "fuses_norm", False)
         while st.pc < end:
             op = opsq[st.pc]
             if isinstance(op, Norm):
@@ -360,6 +377,17 @@ class Executor:
                 if fz is None:
                     return op
                 st.act = self.be.norm(st.act, op, fz[0], fz[1])
+            elif fuse and isinstance(op, Conv) and st.pc + 1 < end and isinstance(opsq[st.pc + 1], Norm) \
+                    and self.frozen[opsq[st.pc + 1].site] is not None:
+                # conv -> GroupNorm (+ SiLU) with frozen statistics: the norm rides in the conv's epilogue (the raw conv
+                # output has no other reader: a residual source is always separated from its norm by a Skip op)
+                nxt = opsq[st.pc + 1]
+                if nxt.site not in self._affine_cache:
+                    self._affine_cache[nxt.site] = self.be.norm_affine(nxt, *self.frozen[nxt.site])
+                st.act = self.be.conv(st.act, op, st.skip if op.add_skip else None, post=self._affine_cache[nxt.site])
+                if op.add_skip:
+                    st.skip = None
+                st.pc += 1
             else:
                 self._step(st, op)
             st.pc += 1
@@ -398,6 +426,7 @@ class Executor:
             print("Nan detected in fast mode estimation. Fast mode disabled.")
             return False
         self.frozen = frozen
+        self._affine_cache = {}
         return True
 
     def barrier_sites(self) -> int:

@@ -41,7 +41,7 @@ def pack_conv_weight(weight: torch.Tensor, dtype: torch.dtype, cin_pad: Optional
 def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, ksize: int, stride: int = 1,
                 pad: Tuple[int, int] = (0, 0), out_hw: Optional[Tuple[int, int]] = None, residual: Optional[torch.Tensor] = None,
                 alpha: float = 1.0, cout: Optional[int] = None, out: Optional[torch.Tensor] = None,
-                bias_per_row: bool = False) -> torch.Tensor:
+                bias_per_row: bool = False, post: Optional[Tuple[torch.Tensor, torch.Tensor, bool]] = None) -> torch.Tensor:
     """One convolution on the tensor cores.  x: [N, H, W, Cin] NHWC; w: packed [ksize*ksize, Cout_rows, Cin];
     bias: fp32 [Cout] (or [N*OH*OW] with bias_per_row); residual: [N, OH, OW, Cout] added in the epilogue.
     pad = (top, left) zero padding; out_hw defaults to the 'same' size for stride 1."""
@@ -56,8 +56,12 @@ def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] =
     d = TdConvDesc(N=N, H=H, W=W, Cin=Cin, Cout=Cout, kh=ksize, kw=ksize, stride=stride, pad_top=pad[0], pad_left=pad[1],
                    OH=OH, OW=OW, dtype=dtype_code(x.dtype), bias_per_row=int(bias_per_row), alpha=float(alpha),
                    x_pitch=x.stride(2), w_pitch=w.stride(1), y_pitch=out.stride(2),
-                   res_pitch=residual.stride(2) if residual is not None else 0)
+                   res_pitch=residual.stride(2) if residual is not None else 0,
+                   post_scale=post[0].data_ptr() if post is not None else None, post_shift=post[1].data_ptr() if post is not None else None,
+                   post_act=int(bool(post[2])) if post is not None else 0)
     assert x.stride(3) == 1 and out.stride(3) == 1 and w.stride(2) == 1
+    if post is not None:
+        assert post[0].dtype == torch.float32 and post[1].dtype == torch.float32 and post[0].numel() >= Cout and post[1].numel() >= Cout
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_cuda
     with torch.cuda.device(x.device):
