@@ -1034,6 +1034,8 @@ def vae_arm(args, rank, world, local_rank):
 def vae_cpu_baseline(budget_s: float):
     """The reference's tiled VAE algorithm on the host cores (oracle restatement, fp32 torch CPU) on a bounded sample:
     a 96 x 96 latent (768 x 768 px image), decoder tile 48, fast mode."""
+    if budget_s <= 1.0:      # measurement runs that only want the GPU numbers
+        return {"value": None, "unit": "MP/s", "cores": 0, "kind": "port", "seconds": 0.0, "sample": "skipped (--cpu-budget <= 1)"}
     from oracle import ldm_vae, vae
     torch.set_num_threads(os.cpu_count() or 1)
     net = ldm_vae.seeded_init(ldm_vae.Decoder(), 1).eval()

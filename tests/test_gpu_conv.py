@@ -183,3 +183,27 @@ def test_gemm_large_m(ops, monkeypatch, mt):
     bias = _rand((M,), torch.float32, 5)
     got = ops.gemm_nt(a, b, bias=bias, bias_per_row=True)
     _check(got, a.float() @ b.float().t() + bias[:, None], dtype, f"gemm large M, MT={mt}")
+
+
+@pytest.mark.parametrize("act", [False, True])
+def test_conv_with_fused_frozen_group_norm(ops, act):
+    """conv -> GroupNorm(statistics given) (+ SiLU) in the conv's epilogue == the two ops in fp32."""
+    dtype = torch.float16
+    N, H, W, Cin, Cout = 1, 37, 45, 128, 256
+    x = _rand((N, Cin, H, W), dtype, 300, 0.7)
+    w = _rand((Cout, Cin, 3, 3), dtype, 301, 1.0 / (Cin * 9) ** 0.5)
+    bias = _rand((Cout,), torch.float32, 302, 0.3)
+    res = _rand((N, H, W, Cout), dtype, 303, 0.5)
+    gamma, beta = _rand((Cout,), torch.float32, 304, 0.4) + 1.0, _rand((Cout,), torch.float32, 305, 0.2)
+    mean, var = _rand((32,), torch.float32, 306, 0.3), _rand((32,), torch.float32, 307, 0.2).abs() + 0.5
+    y = F.conv2d(x.float(), w.float(), bias, padding=1) + res.float().permute(0, 3, 1, 2)
+    cpg = Cout // 32
+    want = (y - mean.repeat_interleave(cpg).view(1, -1, 1, 1)) / torch.sqrt(var.repeat_interleave(cpg).view(1, -1, 1, 1) + 1e-6)
+    want = want * gamma.view(1, -1, 1, 1) + beta.view(1, -1, 1, 1)
+    if act:
+        want = F.silu(want)
+    rstd = (1.0 / torch.sqrt(var + 1e-6)).repeat_interleave(cpg)
+    scale = (rstd * gamma).contiguous()
+    shift = (beta - mean.repeat_interleave(cpg) * scale).contiguous()
+    got = ops.conv2d_nhwc(ops.nchw_to_nhwc(x, Cin), ops.pack_conv_weight(w, dtype), bias, ksize=3, pad=(1, 1), residual=res, post=(scale, shift, act))
+    _check(got.permute(0, 3, 1, 2), want, dtype, f"conv + frozen GroupNorm act={act}")
