@@ -66,6 +66,9 @@ struct ConvParams {
     int is_bf16;
     int bias_per_row;          // bias indexed by output pixel (GEMM row) instead of channel
     int post_act;              // with post_scale / post_shift: 1 = SiLU after the per-channel affine
+    int pair;                  // 1: CTA pair (cluster of 2) on ONE 256-pixel patch with tcgen05.mma.cta_group::2 -- each CTA stages its
+                               // own 128-pixel sub-tile and HALF of the weight tile, the pair's tensor cores read both halves:
+                               // 32 KB instead of 48 KB into each SM per k-step at BN = 256
     int cluster;               // CTAs per cluster (1, 2 or 4): consecutive pixel tiles share the weight tile by TMA multicast
     int m_tiles;               // NI * tiles_y * tiles_x
     int m_groups;              // ceil(m_tiles / cluster)
@@ -100,6 +103,22 @@ __device__ __forceinline__ void tma_load_3d_mcast(uint32_t dst, const CUtensorMa
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+// CTA-pair forms: the copy lands in the executing CTA's shared memory, its bytes complete on the LEADER CTA's barrier
+// (shared::cluster address with the pair's rank bit cleared, as CUTLASS's Sm100MmaPeerBitMask does)
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_rank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -133,6 +152,18 @@ __device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+__device__ __forceinline__ void tc_commit_2sm_mcast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// the pair's MMA: M = 256 (128 rows from each CTA's A tile), N = BN (BN / 2 weight rows from each CTA), issued by the leader
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers fp16 and bf16 inputs with fp32 accumulation
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -161,13 +192,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 // instruction descriptor: fp32 accumulate, A / B both K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t umma_idesc(int n, int is_bf16) {
+__device__ __forceinline__ uint32_t umma_idesc(int n, int is_bf16, int m = kConvBM) {
     uint32_t d = 0;
     d |= 1u << 4;                           // D format: F32
     d |= (is_bf16 ? 1u : 0u) << 7;          // A format
     d |= (is_bf16 ? 1u : 0u) << 10;         // B format
     d |= (uint32_t)(n >> 3) << 17;          // N / 8
-    d |= (uint32_t)(kConvBM >> 4) << 24;    // M / 16
+    d |= (uint32_t)(m >> 4) << 24;          // M / 16
     return d;
 }
 
@@ -195,7 +226,7 @@ struct TileCoord { int img, py, px, nb; };
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int g, int crank) {
     TileCoord c;
     c.nb = g % p.n_blocks;
-    int m = (g / p.n_blocks) * p.cluster + crank;
+    int m = p.pair ? g / p.n_blocks : (g / p.n_blocks) * p.cluster + crank;   // a pair works on ONE patch
     c.px = m % p.tiles_x; m /= p.tiles_x;
     c.py = m % p.tiles_y;
     c.img = m / p.tiles_y;          // >= NI for a dummy tile
@@ -211,7 +242,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __shared__ __align__(8) uint64_t full_bar[kConvMaxStages], empty_bar[kConvMaxStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
     const uint32_t smem0 = (smem_u32(conv_smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
-    const int stage_b = p.BN * 128;
+    const int stage_b = (p.pair ? p.BN / 2 : p.BN) * 128;                   // pair: half of the weight tile per CTA
     const uint32_t stage_a = (uint32_t)(p.MT * kConvStageA);
     const uint32_t stage_bytes = stage_a + (uint32_t)stage_b;
     const uint32_t acc_cols = (uint32_t)(p.MT * p.BN);                      // TMEM columns of one accumulator stage
@@ -225,14 +256,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_d);
         // a stage is free when the MMAs of EVERY CTA of the cluster have read it (peers multicast into it)
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)p.cluster); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.pair ? 1u : (uint32_t)p.cluster); }
+        // pair: the leader's MMA thread waits for the epilogues of BOTH CTAs (the peer's threads arrive remotely)
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], p.pair ? 256u : 128u); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
-    if (warp == 2) {   // TMEM: 512 columns = two accumulator stages of up to 256 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == 2) {   // TMEM: 512 columns = two accumulator stages of up to 256 columns (pair: the same warp of both CTAs)
+        if (p.pair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     if (p.cluster > 1) cluster_sync_all(); else __syncthreads();     // barrier inits visible cluster-wide before any remote arrive
@@ -247,14 +284,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int slice_rows = p.BN / p.cluster;
             for (int g = cid; g < num_groups; g += nclusters) {
                 const TileCoord c = decode_tile(p, g, crank);
-                const int x0 = c.px * p.BW * p.stride - p.pad_left, y0 = c.py * p.BH * p.stride - p.pad_top;
+                // pair: this CTA stages sub-tile `crank` of the patch
+                const int x0 = (c.px * p.BW + (p.pair ? crank * p.sub_dx : 0)) * p.stride - p.pad_left;
+                const int y0 = (c.py * p.BH + (p.pair ? crank * p.sub_dy : 0)) * p.stride - p.pad_top;
                 int tap = 0;
                 for (int ty = 0; ty < p.taps_y; ++ty)
                     for (int tx = 0; tx < p.taps_x; ++tx, ++tap)
                         for (int kc = 0; kc < p.Cin_chunks; ++kc) {
                             mbar_wait(&empty_bar[stage], phase ^ 1u);
-                            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                             const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
+                            if (p.pair) {
+                                // both CTAs' copies complete on the leader's barrier, which expects the bytes of the pair
+                                const uint32_t lbar = smem_u32(&full_bar[stage]) & kPeerBitMask;
+                                if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * stage_bytes);
+                                tma_load_4d_2sm(sa, &map_a, kc * kConvBK, x0 + tx, y0 + ty, c.img, lbar);
+                                tma_load_3d_2sm(sa + stage_a, &map_b, kc * kConvBK, c.nb * p.BN + crank * (p.BN / 2), tap, lbar);
+                                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                                continue;
+                            }
+                            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                             tma_load_4d(sa, &map_a, kc * kConvBK, x0 + tx, y0 + ty, c.img, &full_bar[stage]);
                             if (p.cluster == 1)
                                 tma_load_3d_u32(sa + stage_a, &map_b, kc * kConvBK, c.nb * p.BN, tap, &full_bar[stage]);
@@ -265,10 +313,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
+    } else if (warp == 1 && (!p.pair || crank == 0)) {
+        // ===================== MMA issuer (one thread; pair: of the leader CTA) =====================
         if (elect_one()) {
-            const uint32_t idesc = umma_idesc(p.BN, p.is_bf16);
+            const uint32_t idesc = umma_idesc(p.BN, p.is_bf16, p.pair ? 2 * kConvBM : kConvBM);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             for (int g = cid; g < num_groups; g += nclusters) {
@@ -283,14 +331,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     for (int mt = 0; mt < p.MT; ++mt) {             // the sub-tiles of the patch share this k-step's weight tile
                         const uint64_t da = umma_desc_sw128(sa + (uint32_t)(mt * kConvStageA));
 #pragma unroll
-                        for (int k = 0; k < kConvBK / 16; ++k)      // +32 bytes along K inside the swizzle row = +2 in the address field
-                            tc_mma_f16(d_tmem + (uint32_t)(mt * p.BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kConvBK / 16; ++k) {    // +32 bytes along K inside the swizzle row = +2 in the address field
+                            if (p.pair) tc_mma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+                            else tc_mma_f16(d_tmem + (uint32_t)(mt * p.BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+                        }
                     }
-                    if (p.cluster == 1) tc_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs have read it
-                    else tc_commit_mcast(&empty_bar[stage], cmask);    // ... in every CTA of the cluster
+                    if (p.pair) tc_commit_2sm_mcast(&empty_bar[stage], 3);  // frees the stage in both CTAs of the pair
+                    else if (p.cluster == 1) tc_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs have read it
+                    else tc_commit_mcast(&empty_bar[stage], cmask);         // ... in every CTA of the cluster
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(&acc_full[as]);                             // accumulator complete -> epilogue
+                if (p.pair) tc_commit_2sm_mcast(&acc_full[as], 3);    // accumulators of both CTAs complete -> both epilogues
+                else tc_commit(&acc_full[as]);                        // accumulator complete -> epilogue
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
             }
         }
@@ -306,7 +358,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_wait(&acc_full[as], aphase);
             tc_fence_after();
             const int nchunks = p.BN / p.chunk_cols;
-            for (int mt = 0; mt < p.MT; ++mt) {
+            for (int mt0 = 0; mt0 < p.MT; ++mt0) {
+                const int mt = p.pair ? crank : mt0;          // pair: this CTA's accumulator holds sub-tile `crank` (TMEM columns as mt 0)
                 const int pidx = mt * kConvBM + row;          // pixel index inside the patch (= shared-memory row of the A box)
                 const int ly = pidx / p.BW, lx = pidx - ly * p.BW;
                 const int ox = c.px * p.BW + lx, oy = c.py * p.BH + ly;
@@ -322,7 +375,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     uint32_t racc[4][16];
                     const int ng = p.chunk_cols / 16;
                     __syncwarp();
-                    const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * acc_cols + (uint32_t)(mt * p.BN + ch * p.chunk_cols);
+                    const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * acc_cols + (uint32_t)(mt0 * p.BN + ch * p.chunk_cols);
                     tc_ld16(tcol, racc[0]);
                     if (ng > 1) tc_ld16(tcol + 16u, racc[1]);
                     if (ng > 2) { tc_ld16(tcol + 32u, racc[2]); tc_ld16(tcol + 48u, racc[3]); }
@@ -399,9 +452,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb + 16u), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
                         }
                     }
-                    if (mt == p.MT - 1 && ch == nchunks - 1) {   // every TMEM read of this accumulator stage is done: hand it back
+                    if (mt0 == p.MT - 1 && ch == nchunks - 1) {   // every TMEM read of this accumulator stage is done: hand it back
                         tc_fence_before();
-                        mbar_arrive(&acc_empty[as]);
+                        if (p.pair) mbar_arrive_cluster(smem_u32(&acc_empty[as]) & kPeerBitMask);   // on the leader's barrier
+                        else mbar_arrive(&acc_empty[as]);
                     }
                     fence_proxy_async();
                     named_bar_sync(1, 128);
@@ -421,7 +475,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (p.cluster > 1) cluster_sync_all(); else __syncthreads();     // no CTA leaves while a peer may still write into it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (p.pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -533,8 +588,18 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
         const bool fits2 = 2 * 2 * bn <= 512 || want_mt >= 3;
         p.MT = (want_mt >= 2 && fits2 && sub_tiles >= 4LL * dev.sms && bn >= 32 && (p.BWs + p.sub_dx) * d->stride <= 256 && (p.BHs + p.sub_dy) * d->stride <= 256) ? 2 : 1;
     }
-    p.BW = p.BWs + (p.MT - 1) * p.sub_dx;
-    p.BH = p.BHs + (p.MT - 1) * p.sub_dy;
+    // CTA pair (tcgen05.mma.cta_group::2) for the full-width Cout blocks: the two CTAs of a cluster take the two sub-tiles
+    // of ONE 256-pixel patch and half of the weight tile each (TD_CONV_PAIR=0 disables)
+    {
+        const char* fp = getenv("TD_CONV_PAIR");
+        const int want_pair = fp != nullptr ? atoi(fp) : 1;
+        const long long sub_tiles = (long long)d->N * ((d->OW + p.BWs - 1) / p.BWs) * ((d->OH + p.BHs - 1) / p.BHs) * p.n_blocks;
+        p.pair = (want_pair >= 1 && bn == 256 && p.MT == 1 && dev.sms % 2 == 0 && sub_tiles >= 4LL * dev.sms &&
+                  (p.BWs + p.sub_dx) * d->stride <= 256 && (p.BHs + p.sub_dy) * d->stride <= 256) ? 1 : 0;
+    }
+    const int patch_subs = (p.MT == 2 || p.pair) ? 2 : 1;       // sub-tiles per patch
+    p.BW = p.BWs + (patch_subs - 1) * p.sub_dx;
+    p.BH = p.BHs + (patch_subs - 1) * p.sub_dy;
     p.acc_stages = std::min(2, 512 / (p.MT * bn));
     p.tiles_x = (d->OW + p.BW - 1) / p.BW;
     p.tiles_y = (d->OH + p.BH - 1) / p.BH;
@@ -548,8 +613,9 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     const int want = force != nullptr ? atoi(force) : 1;   // measured: no gain on B200 (the bound is bytes INTO the SM, which multicast does not cut)
     if (want >= 2 && bn >= 64 && dev.sms % 2 == 0 && mt >= 2 * (long long)dev.sms) cl = 2;
     if (want >= 4 && bn >= 128 && dev.sms % 4 == 0 && mt >= 4 * (long long)dev.sms) cl = 4;
+    if (p.pair) cl = 2;
     p.cluster = cl;
-    p.m_groups = (int)((mt + cl - 1) / cl);
+    p.m_groups = p.pair ? (int)mt : (int)((mt + cl - 1) / cl);
     p.num_tiles = p.m_groups * p.n_blocks;
     p.chunk_cols = std::min(64, bn);
     p.is_bf16 = d->dtype == TD_BF16;
@@ -558,7 +624,7 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     if ((d->post_scale == nullptr) != (d->post_shift == nullptr)) { td_set_error("td_conv2d_nhwc: post_scale and post_shift come together"); return TD_ERR_INVALID_ARG; }
     p.alpha = d->alpha;
     p.res_pitch = residual != nullptr ? d->res_pitch : 0;
-    const int stage_bytes = p.MT * kConvStageA + bn * 128;
+    const int stage_bytes = p.MT * kConvStageA + (p.pair ? bn / 2 : bn) * 128;
     const int avail = dev.smem_optin - 1024 - 2 * kConvStoreBuf;
     p.stages = std::min(kConvMaxStages, avail / stage_bytes);
     if (p.stages < 2) { td_set_error("td_conv2d_nhwc: not enough shared memory"); return TD_ERR_UNSUPPORTED; }
@@ -568,7 +634,8 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     {
         const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
         const uint64_t str[3] = {(uint64_t)d->x_pitch * 2, (uint64_t)d->W * d->x_pitch * 2, (uint64_t)d->H * d->W * d->x_pitch * 2};
-        const uint32_t box[4] = {64, (uint32_t)(p.BW * d->stride), (uint32_t)(p.BH * d->stride), 1};
+        // pair: each CTA loads its own sub-tile; otherwise the whole patch (MT sub-tiles) is one box
+        const uint32_t box[4] = {64, (uint32_t)((p.pair ? p.BWs : p.BW) * d->stride), (uint32_t)((p.pair ? p.BHs : p.BH) * d->stride), 1};
         const uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
         const int rc = encode_map(&ma, x, p.is_bf16, 4, dims, str, box, es, true, "activations");
         if (rc != TD_OK) return rc;
@@ -576,7 +643,7 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     {
         const uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout, (uint64_t)(d->kh * d->kw)};
         const uint64_t str[2] = {(uint64_t)d->w_pitch * 2, (uint64_t)d->Cout * d->w_pitch * 2};
-        const uint32_t box[3] = {64, (uint32_t)(bn / p.cluster), 1};
+        const uint32_t box[3] = {64, (uint32_t)(bn / p.cluster), 1};      // cluster multicast slices and the pair's halves alike
         const uint32_t es[3] = {1, 1, 1};
         const int rc = encode_map(&mb, w, p.is_bf16, 3, dims, str, box, es, true, "weights");
         if (rc != TD_OK) return rc;

@@ -161,17 +161,20 @@ def test_softmax_rows(ops):
     assert float(y[:, cols:].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("cluster", ["1", "2", "4"])
-@pytest.mark.parametrize("mt", ["1", "2"])
-def test_conv3x3_large_grid_forms(ops, monkeypatch, cluster, mt):
+@pytest.mark.parametrize("cluster,mt,pair", [("1", "1", "0"), ("1", "2", "0"), ("2", "1", "0"), ("4", "1", "0"), ("1", "1", "1"), ("1", "2", "1")])
+def test_conv3x3_large_grid_forms(ops, monkeypatch, cluster, mt, pair):
     """Enough pixel tiles (>= 4 per SM) for the large-grid forms: two 128-pixel sub-tiles per CTA sharing the weight tile
-    of a k-step (TD_CONV_MT), CTA clusters with the weight tile multicast (TD_CONV_CLUSTER); odd sizes leave partial
-    and dummy tiles at the end of the list."""
+    of a k-step (TD_CONV_MT), CTA pairs with tcgen05.mma.cta_group::2 on one 256-pixel patch (TD_CONV_PAIR, Cout blocks of
+    256), CTA clusters with the weight tile multicast (TD_CONV_CLUSTER); odd sizes leave partial and dummy tiles."""
     monkeypatch.setenv("TD_CONV_CLUSTER", cluster)
     monkeypatch.setenv("TD_CONV_MT", mt)
-    _conv_case(ops, torch.float16, 1, 259, 333, 128, 256, 3, 1, 200, residual=True)   # 21 x 33 = 693 sub-tiles, BN 256 (one TMEM stage at MT 2)
+    monkeypatch.setenv("TD_CONV_PAIR", pair)
+    _conv_case(ops, torch.float16, 1, 259, 333, 128, 256, 3, 1, 200, residual=True)   # 21 x 33 = 693 sub-tiles, BN 256
     _conv_case(ops, torch.float16, 1, 253, 336, 64, 128, 3, 1, 210)                   # BN 128: two TMEM stages at MT 2
     _conv_case(ops, torch.float16, 1, 663, 541, 64, 64, 3, 2, 220)                    # stride 2 with the doubled box (714 output sub-tiles)
+    _conv_case(ops, torch.float16, 1, 200, 248, 64, 512, 3, 1, 230)                   # two Cout blocks of 256
+    _conv_case(ops, torch.float16, 1, 330, 270, 128, 256, 3, 2, 240)                  # stride 2, BN 256 (pair on the strided box)... small grid
+    _conv_case(ops, torch.float16, 1, 660, 540, 64, 256, 3, 2, 250)                   # stride 2, BN 256, 714 sub-tiles
 
 
 @pytest.mark.parametrize("mt", ["1", "2"])
