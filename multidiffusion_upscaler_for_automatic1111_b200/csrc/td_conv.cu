@@ -233,6 +233,9 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int g, int
     return c;
 }
 
+// PAIR selects the CTA-pair form at compile time: every tcgen05 instruction of one kernel must carry the same
+// .cta_group (mixing ::1 and ::2 in one kernel is rejected at launch: "cluster misconfiguration").
+template <bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_d, const __grid_constant__ ConvParams p,
@@ -263,7 +266,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         fence_proxy_async();
     }
     if (warp == 2) {   // TMEM: 512 columns = two accumulator stages of up to 256 columns (pair: the same warp of both CTAs)
-        if (p.pair) {
+        if constexpr (PAIR) {
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         } else {
@@ -293,7 +296,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         for (int kc = 0; kc < p.Cin_chunks; ++kc) {
                             mbar_wait(&empty_bar[stage], phase ^ 1u);
                             const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
-                            if (p.pair) {
+                            if constexpr (PAIR) {
                                 // both CTAs' copies complete on the leader's barrier, which expects the bytes of the pair
                                 const uint32_t lbar = smem_u32(&full_bar[stage]) & kPeerBitMask;
                                 if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * stage_bytes);
@@ -303,13 +306,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 continue;
                             }
                             mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-                            tma_load_4d(sa, &map_a, kc * kConvBK, x0 + tx, y0 + ty, c.img, &full_bar[stage]);
-                            if (p.cluster == 1)
-                                tma_load_3d_u32(sa + stage_a, &map_b, kc * kConvBK, c.nb * p.BN, tap, &full_bar[stage]);
-                            else
-                                tma_load_3d_mcast(sa + stage_a + (uint32_t)(crank * slice_rows * 128), &map_b, kc * kConvBK,
-                                                  c.nb * p.BN + crank * slice_rows, tap, &full_bar[stage], cmask);
-                            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                            if constexpr (!PAIR) {
+                                tma_load_4d(sa, &map_a, kc * kConvBK, x0 + tx, y0 + ty, c.img, &full_bar[stage]);
+                                if (p.cluster == 1)
+                                    tma_load_3d_u32(sa + stage_a, &map_b, kc * kConvBK, c.nb * p.BN, tap, &full_bar[stage]);
+                                else
+                                    tma_load_3d_mcast(sa + stage_a + (uint32_t)(crank * slice_rows * 128), &map_b, kc * kConvBK,
+                                                      c.nb * p.BN + crank * slice_rows, tap, &full_bar[stage], cmask);
+                                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                            }
                         }
             }
         }
@@ -332,17 +337,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         const uint64_t da = umma_desc_sw128(sa + (uint32_t)(mt * kConvStageA));
 #pragma unroll
                         for (int k = 0; k < kConvBK / 16; ++k) {    // +32 bytes along K inside the swizzle row = +2 in the address field
-                            if (p.pair) tc_mma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+                            if constexpr (PAIR) tc_mma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
                             else tc_mma_f16(d_tmem + (uint32_t)(mt * p.BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
                         }
                     }
-                    if (p.pair) tc_commit_2sm_mcast(&empty_bar[stage], 3);  // frees the stage in both CTAs of the pair
-                    else if (p.cluster == 1) tc_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs have read it
-                    else tc_commit_mcast(&empty_bar[stage], cmask);         // ... in every CTA of the cluster
+                    if constexpr (PAIR) tc_commit_2sm_mcast(&empty_bar[stage], 3);   // frees the stage in both CTAs of the pair
+                    else {
+                        if (p.cluster == 1) tc_commit(&empty_bar[stage]);   // frees the smem stage when these MMAs have read it
+                        else tc_commit_mcast(&empty_bar[stage], cmask);     // ... in every CTA of the cluster
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
-                if (p.pair) tc_commit_2sm_mcast(&acc_full[as], 3);    // accumulators of both CTAs complete -> both epilogues
-                else tc_commit(&acc_full[as]);                        // accumulator complete -> epilogue
+                if constexpr (PAIR) tc_commit_2sm_mcast(&acc_full[as], 3);   // accumulators of both CTAs complete -> both epilogues
+                else tc_commit(&acc_full[as]);                               // accumulator complete -> epilogue
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
             }
         }
@@ -475,7 +482,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (p.cluster > 1) cluster_sync_all(); else __syncthreads();     // no CTA leaves while a peer may still write into it
     if (warp == 2) {
         tc_fence_after();
-        if (p.pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
@@ -529,10 +536,11 @@ ConvDev conv_dev() {
                cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess;
         if (d.ok) {   // the opt-in limit covers static + dynamic shared memory: leave room for the kernel's static part
             cudaFuncAttributes fa;
-            if (cudaFuncGetAttributes(&fa, conv_gemm_kernel) != cudaSuccess) { cudaGetLastError(); d.ok = false; }
+            if (cudaFuncGetAttributes(&fa, conv_gemm_kernel<false>) != cudaSuccess) { cudaGetLastError(); d.ok = false; }
             else {
                 d.smem_optin -= (int)fa.sharedSizeBytes;
-                if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin) != cudaSuccess) {
+                if (cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin) != cudaSuccess ||
+                    cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin) != cudaSuccess) {
                     cudaGetLastError();
                     d.ok = false;
                 }
@@ -669,7 +677,9 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = cl > 1 ? 1 : 0;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_kernel, ma, mb, md, p, bias, (const uint16_t*)residual, d->post_scale, d->post_shift);
+    const cudaError_t le = p.pair
+        ? cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, ma, mb, md, p, bias, (const uint16_t*)residual, d->post_scale, d->post_shift)
+        : cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false>, ma, mb, md, p, bias, (const uint16_t*)residual, d->post_scale, d->post_shift);
     if (le != cudaSuccess) { td_set_error("td_conv2d_nhwc: launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return TD_ERR_CUDA; }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { td_set_error("td_conv2d_nhwc: launch failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
