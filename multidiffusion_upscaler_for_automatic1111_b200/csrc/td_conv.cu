@@ -288,8 +288,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int g = cid; g < num_groups; g += nclusters) {
                 const TileCoord c = decode_tile(p, g, crank);
                 // pair: this CTA stages sub-tile `crank` of the patch
-                const int x0 = (c.px * p.BW + (p.pair ? crank * p.sub_dx : 0)) * p.stride - p.pad_left;
-                const int y0 = (c.py * p.BH + (p.pair ? crank * p.sub_dy : 0)) * p.stride - p.pad_top;
+                const int x0 = (c.px * p.BW + (p.pair ? crank * p.MT * p.sub_dx : 0)) * p.stride - p.pad_left;
+                const int y0 = (c.py * p.BH + (p.pair ? crank * p.MT * p.sub_dy : 0)) * p.stride - p.pad_top;
                 int tap = 0;
                 for (int ty = 0; ty < p.taps_y; ++ty)
                     for (int tx = 0; tx < p.taps_x; ++tx, ++tap)
@@ -337,7 +337,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         const uint64_t da = umma_desc_sw128(sa + (uint32_t)(mt * kConvStageA));
 #pragma unroll
                         for (int k = 0; k < kConvBK / 16; ++k) {    // +32 bytes along K inside the swizzle row = +2 in the address field
-                            if constexpr (PAIR) tc_mma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+                            if constexpr (PAIR) tc_mma_f16_2sm(d_tmem + (uint32_t)(mt * p.BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
                             else tc_mma_f16(d_tmem + (uint32_t)(mt * p.BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
                         }
                     }
@@ -366,7 +366,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tc_fence_after();
             const int nchunks = p.BN / p.chunk_cols;
             for (int mt0 = 0; mt0 < p.MT; ++mt0) {
-                const int mt = p.pair ? crank : mt0;          // pair: this CTA's accumulator holds sub-tile `crank` (TMEM columns as mt 0)
+                const int mt = p.pair ? crank * p.MT + mt0 : mt0;   // pair: this CTA holds sub-tiles [crank * MT, (crank + 1) * MT) of the patch
                 const int pidx = mt * kConvBM + row;          // pixel index inside the patch (= shared-memory row of the A box)
                 const int ly = pidx / p.BW, lx = pidx - ly * p.BW;
                 const int ox = c.px * p.BW + lx, oy = c.py * p.BH + ly;
@@ -596,16 +596,15 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
         const bool fits2 = 2 * 2 * bn <= 512 || want_mt >= 3;
         p.MT = (want_mt >= 2 && fits2 && sub_tiles >= 4LL * dev.sms && bn >= 32 && (p.BWs + p.sub_dx) * d->stride <= 256 && (p.BHs + p.sub_dy) * d->stride <= 256) ? 2 : 1;
     }
-    // CTA pair (tcgen05.mma.cta_group::2) for the full-width Cout blocks: the two CTAs of a cluster take the two sub-tiles
-    // of ONE 256-pixel patch and half of the weight tile each (TD_CONV_PAIR=0 disables)
+    // CTA pair (tcgen05.mma.cta_group::2): the two CTAs of a cluster take halves of ONE patch (MT sub-tiles each) and half
+    // of the weight tile each (TD_CONV_PAIR=0 disables)
     {
         const char* fp = getenv("TD_CONV_PAIR");
         const int want_pair = fp != nullptr ? atoi(fp) : 1;
         const long long sub_tiles = (long long)d->N * ((d->OW + p.BWs - 1) / p.BWs) * ((d->OH + p.BHs - 1) / p.BHs) * p.n_blocks;
-        p.pair = (want_pair >= 1 && bn == 256 && p.MT == 1 && dev.sms % 2 == 0 && sub_tiles >= 4LL * dev.sms &&
-                  (p.BWs + p.sub_dx) * d->stride <= 256 && (p.BHs + p.sub_dy) * d->stride <= 256) ? 1 : 0;
+        p.pair = (want_pair >= 1 && bn >= 128 && dev.sms % 2 == 0 && sub_tiles >= 4LL * p.MT * dev.sms) ? 1 : 0;
     }
-    const int patch_subs = (p.MT == 2 || p.pair) ? 2 : 1;       // sub-tiles per patch
+    const int patch_subs = p.MT * (p.pair ? 2 : 1);             // sub-tiles per patch
     p.BW = p.BWs + (patch_subs - 1) * p.sub_dx;
     p.BH = p.BHs + (patch_subs - 1) * p.sub_dy;
     p.acc_stages = std::min(2, 512 / (p.MT * bn));
@@ -642,8 +641,8 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     {
         const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
         const uint64_t str[3] = {(uint64_t)d->x_pitch * 2, (uint64_t)d->W * d->x_pitch * 2, (uint64_t)d->H * d->W * d->x_pitch * 2};
-        // pair: each CTA loads its own sub-tile; otherwise the whole patch (MT sub-tiles) is one box
-        const uint32_t box[4] = {64, (uint32_t)((p.pair ? p.BWs : p.BW) * d->stride), (uint32_t)((p.pair ? p.BHs : p.BH) * d->stride), 1};
+        // one box = the MT sub-tiles of one CTA (a pair's patch holds two of them)
+        const uint32_t box[4] = {64, (uint32_t)((p.BWs + (p.MT - 1) * p.sub_dx) * d->stride), (uint32_t)((p.BHs + (p.MT - 1) * p.sub_dy) * d->stride), 1};
         const uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
         const int rc = encode_map(&ma, x, p.is_bf16, 4, dims, str, box, es, true, "activations");
         if (rc != TD_OK) return rc;

@@ -175,17 +175,19 @@ def test_conv3x3_large_grid_forms(ops, monkeypatch, cluster, mt, pair):
     _conv_case(ops, torch.float16, 1, 200, 248, 64, 512, 3, 1, 230)                   # two Cout blocks of 256
     _conv_case(ops, torch.float16, 1, 330, 270, 128, 256, 3, 2, 240)                  # stride 2, BN 256 (pair on the strided box)... small grid
     _conv_case(ops, torch.float16, 1, 660, 540, 64, 256, 3, 2, 250)                   # stride 2, BN 256, 714 sub-tiles
+    _conv_case(ops, torch.float16, 1, 397, 403, 64, 128, 3, 1, 260, residual=True)    # BN 128, 1300 sub-tiles: pair + two sub-tiles per CTA
 
 
 @pytest.mark.parametrize("mt", ["1", "2"])
 def test_gemm_large_m(ops, monkeypatch, mt):
     monkeypatch.setenv("TD_CONV_MT", mt)
     dtype = torch.float16
-    M, K, N = 80003, 64, 128
-    a, b = _rand((M, K), dtype, 1, 0.5), _rand((N, K), dtype, 2, 0.5)
-    bias = _rand((M,), torch.float32, 5)
-    got = ops.gemm_nt(a, b, bias=bias, bias_per_row=True)
-    _check(got, a.float() @ b.float().t() + bias[:, None], dtype, f"gemm large M, MT={mt}")
+    for M in (80003, 160001):       # 626 / 1251 sub-tiles: two sub-tiles per CTA; also the CTA-pair form
+        K, N = 64, 128
+        a, b = _rand((M, K), dtype, 1, 0.5), _rand((N, K), dtype, 2, 0.5)
+        bias = _rand((M,), torch.float32, 5)
+        got = ops.gemm_nt(a, b, bias=bias, bias_per_row=True)
+        _check(got, a.float() @ b.float().t() + bias[:, None], dtype, f"gemm M={M}, MT={mt}")
 
 
 @pytest.mark.parametrize("act", [False, True])
