@@ -1060,6 +1060,186 @@ def vae_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- cfg5: DemoFusion dilated sampling
+DEMO_METRIC = "demofusion_step_throughput"
+DEMO = dict(N=2, C=4, lat=768, window=128, overlap=64, scale=4, tile_bs=8, tile_bs_g=4, sig=0.6, cs1=3.0, cs2=1.0, cs3=1.0,
+            current_step=10, t_enc=40)
+
+
+def _demo_job(dev, dtype, mixture, jitter):
+    """A DemoFusion delegate at BASELINE cfg5's final phase (SDXL, 6144^2 px = latent 768^2, x4 over the 1536^2 base:
+    current_scale_num 4, window 128 = SDXL's 1024 px) with an identity UNet stand-in: the step is the hot path alone."""
+    import types
+    from multidiffusion_upscaler_for_automatic1111_b200 import DemoFusion
+    c = DEMO
+    p = types.SimpleNamespace(width=c["lat"] * 8, height=c["lat"] * 8, sampler_name="Euler a", current_scale_num=c["scale"], mixture=mixture,
+                              gaussian_filter=True, random_jitter=jitter, cosine_scale_1=c["cs1"], cosine_scale_2=c["cs2"],
+                              cosine_scale_3=c["cs3"], current_step=c["current_step"], steps=50, t_enc=c["t_enc"], sd_model=None)
+    calls = [0]
+
+    def fwd(x_tile, sigma, cond=None):
+        calls[0] += 1
+        return x_tile
+    inner = types.SimpleNamespace(forward=fwd)
+    sampler = types.SimpleNamespace(model_wrap_cfg=types.SimpleNamespace(inner_model=inner, image_cfg_scale=None, forward=None))
+    d = DemoFusion(p, sampler)
+    d.window_size, d.sig = c["window"], c["sig"]
+    return d, fwd, calls
+
+
+def demofusion_arm(args, rank, world, local_rank):
+    """BASELINE cfg5: one DemoFusion `sample_one_step` at the x4 phase of an SDXL 6144^2 upscale: latent [2,4,768,768] fp16,
+    121 local windows of 128^2 (stride 64) count-blended, 7x7 gaussian blur + renormalise, 32 dilated global views (mixture),
+    add-back + cosine mix.  UNet stand-in = identity, so the timed region is the tile path only.  N>1: windows and views
+    sharded over the ranks (all-gather form, DemoFusion.init_tile_shard)."""
+    import math
+    import random
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    c = DEMO
+    d, fwd, calls = _demo_job(dev, torch.float16, True, False)
+    if world > 1:
+        d.init_tile_shard(None)
+    d.get_views(c["overlap"], c["tile_bs"], c["tile_bs_g"])
+    d.sampler_forward = fwd
+    d.cosine_factor = 0.5 * (1 + math.cos(math.pi * (c["t_enc"] - c["current_step"]) / c["t_enc"]))
+    N, C, L = c["N"], c["C"], c["lat"]
+    x_host = synthetic_latent(11, (N, C, L, L)).pin_memory()
+    x = x_host.to(dev)
+    out_host = torch.empty_like(x_host).pin_memory()
+    sigma = torch.ones(N, device=dev)
+    cond = {"c_crossattn": [torch.zeros(N, 77, 2048, device=dev, dtype=torch.float16)], "c_concat": [torch.zeros(N, 5, 1, 1, device=dev, dtype=torch.float16)]}
+    stream = torch.cuda.current_stream(dev)
+    steps, warm = max(1, min(args.steps, 200)), max(3, min(args.warmup, 10))
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    for _ in range(warm):
+        y = d.sample_one_step(x, sigma, cond)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    calls[0] = 0
+    ms = event_time_ms(lambda: [d.sample_one_step(x, sigma, cond) for _ in range(steps)], stream)
+    unet_calls = calls[0] // steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    sec = float(t.item()) / 1e3 / steps
+
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        out_host.copy_(d.sample_one_step(xd, sigma, cond), non_blocking=True)
+    e2e_step(); torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    e2e_ms = event_time_ms(lambda: [e2e_step() for _ in range(steps)], stream)
+    te = torch.tensor([max(e2e_ms / 1e3, time.perf_counter() - t0)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
+    e2e_sec = float(te.item()) / steps
+    clocks = sampler.stop() if sampler else None
+
+    # property checks at full size (the oracle comparison at this size is tests/test_demofusion.py::test_cfg5_size):
+    #  * identity UNet + count-normalised blend: the local result equals the input wherever fp16 (sum/count) is exact, i.e.
+    #    everywhere (count*x/count rounds back to x for count in {1,2,4}); so out = (1-c2)*x + c2*(global add-back)/2
+    #  * all ranks hold the same bits
+    y = d.sample_one_step(x, sigma, cond)
+    digest = torch.tensor([float(y.float().sum().item()), float(y.float().abs().max().item())], device=dev, dtype=torch.float64)
+    same = True
+    if world > 1:
+        lo, hi = digest.clone(), digest.clone()
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+        torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+        same = bool(torch.equal(lo, hi))
+    finite = bool(torch.isfinite(y).all().item())
+    if rank != 0:
+        if world > 1:
+            torch.distributed.barrier()
+        return
+    peak, peak_src = load_peaks()
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs_sustained"])
+        peak_src = "measured (MEASURED_PEAKS.json, sustained copy: the step is many kernels back to back)"
+    except Exception:
+        pass
+    esz = 2
+    canvas = N * C * L * L * esz
+    windows = d.num_tiles * N * C * c["window"] ** 2 * esz
+    views = d.global_num_tiles * canvas // (c["scale"] ** 2)
+    # scatter: canvas in, windows out | blend: windows in, canvas out | blur: canvas in/out | stats: 2 x canvas in |
+    # affine: canvas in/out | gather: x + x_g in, views out | combine: views + x_local in, canvas out
+    algo = (canvas + windows) + (windows + canvas) + 2 * canvas + 2 * canvas + 2 * canvas + (2 * canvas + views) + (views + canvas + canvas)
+    mp = (L * 8) ** 2 / 1e6
+    line = {
+        "metric": DEMO_METRIC, "value": mp / sec, "unit": "MP/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"BASELINE cfg5: SDXL-shaped 6144x6144 img2img x4 upscale, DemoFusion final phase: latent [{N},{C},{L},{L}] fp16, "
+                               f"{d.num_tiles} local windows {c['window']}^2 stride {c['window'] - c['overlap']} (batches of {d.tile_bs}), scale {c['scale']}, "
+                               f"{d.global_num_tiles} dilated views (mixture), gaussian filter k={2 * c['scale'] - 1}, identity UNet stand-in "
+                               f"({unet_calls} calls / step)",
+                   "l2": f"per-step working set {algo / 1e6:.0f} MB of algorithmic traffic; window batches ({windows / 1e6:.0f} MB) exceed nothing but stream once",
+                   "parallelism": "single GPU" if world == 1 else f"windows + views sharded over {world} ranks, two all-gathers per step (NCCL)"},
+        "clocks": clocks,
+        "e2e": {"value": mp / e2e_sec, "unit": "MP/s", "h2d_bytes_per_step": canvas, "d2h_bytes_per_step": canvas, "ms_per_step": e2e_sec * 1e3,
+                "api": "DemoFusion.sample_one_step, pinned-host latent in, pinned-host latent out"},
+        "gpu_launches": None,
+        "roofline": {"bound": "hbm", "kernel": "whole step (scatter_tma, blend_md_async, depthwise_conv2d, gn_stats, affine_clamp, "
+                                               "dilated_gather, demofusion_combine): eager launches, host-launch bound",
+                     "achieved": algo / sec / 1e9, "peak": peak, "unit": "GB/s", "frac": algo / sec / 1e9 / peak,
+                     "traffic": None, "algorithmic_bytes": algo, "peak_source": peak_src},
+        "parity": {"finite": finite, "ranks_identical": same,
+                   "full_size_oracle_check": "tests/test_demofusion.py::test_demofusion_cfg5_size_matches_oracle"},
+        "impl": "b200",
+    }
+    line["cpu_baseline"] = demofusion_cpu_baseline(args.cpu_budget)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+
+
+def demofusion_cpu_baseline(budget_s: float):
+    """The reference's DemoFusion step (oracle restatement, torch CPU) on the cfg5 latent in fp32, identity UNet stand-in."""
+    if budget_s <= 1.0:
+        return {"value": None, "unit": "MP/s", "cores": 0, "kind": "port", "seconds": 0.0, "sample": "skipped (--cpu-budget <= 1)"}
+    from oracle import demofusion as odf
+    from oracle import tiling
+    c = DEMO
+    torch.set_num_threads(os.cpu_count() or 1)
+    L = c["lat"]
+    x = synthetic_latent(11, (c["N"], c["C"], L, L)).float()
+    local, _, _ = tiling.demofusion_views(L, L, c["window"], c["overlap"])
+    nb = -(-len(local) // c["tile_bs"]); tbs = -(-len(local) // nb)
+    lb = [local[i * tbs:(i + 1) * tbs] for i in range(nb)]
+    views = odf.global_views(c["scale"], True)
+    gnb = -(-len(views) // c["tile_bs_g"]); gtbs = -(-len(views) // gnb)
+    gb = [views[i * gtbs:(i + 1) * gtbs] for i in range(gnb)]
+    cf = odf.cosine_factor(c["current_step"], c["t_enc"])
+    ident = lambda t, b: t
+    n, t0 = 0, time.perf_counter()
+    with torch.no_grad():
+        while True:
+            odf.sample_one_step(x, lb, gb, c["scale"], True, True, c["sig"], cf, c["cs2"], c["cs3"], ident, ident)
+            n += 1
+            if time.perf_counter() - t0 > budget_s or n >= 50:
+                break
+    dt = (time.perf_counter() - t0) / n
+    return {"value": (L * 8) ** 2 / 1e6 / dt, "unit": "MP/s", "cores": torch.get_num_threads(), "kind": "port", "seconds": dt * n,
+            "sample": f"{n} whole cfg5 steps (latent [2,4,{L},{L}], fp32 on the host cores), oracle restatement of tile_methods/demofusion.py:219-324"}
+
+
+def demofusion_reference_arm(args, rank):
+    if rank != 0:
+        return
+    cpu = demofusion_cpu_baseline(max(args.cpu_budget, 5.0))
+    line = {"impl": "reference", "metric": DEMO_METRIC, "value": cpu["value"], "unit": "MP/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+            "ms_per_step": (DEMO["lat"] * 8) ** 2 / 1e6 / cpu["value"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": cpu["sample"]}, "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -1075,8 +1255,8 @@ def main():
     ap.add_argument("--profile-e2e", action="store_true")
     ap.add_argument("--variants", action="store_true", help="print a table of per-kernel micro-timings to stderr")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"], help="BASELINE.json config: cfg2 = MultiDiffusion hot path "
-                    "(default, the headline), cfg3 = Mixture of Diffusers hot path, cfg4 = tiled VAE decode only")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"], help="BASELINE.json config: cfg2 = MultiDiffusion hot path "
+                    "(default, the headline), cfg3 = Mixture of Diffusers hot path, cfg4 = tiled VAE decode only, cfg5 = DemoFusion step")
     ap.add_argument("--vae-latent", type=int, default=1024, help="cfg4: latent edge (1024 -> 8192^2 image)")
     ap.add_argument("--vae-slow", action="store_true", help="cfg4: slow mode (GroupNorm statistics merged over all tiles at every site)")
     args = ap.parse_args()
@@ -1084,7 +1264,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        (vae_reference_arm if args.config == "cfg4" else reference_arm)(args, rank)
+        {"cfg4": vae_reference_arm, "cfg5": demofusion_reference_arm}.get(args.config, reference_arm)(args, rank)
+        return
+    if args.config == "cfg5":
+        demofusion_arm(args, rank, world, local_rank)
         return
     if args.config == "cfg4":
         vae_arm(args, rank, world, local_rank)

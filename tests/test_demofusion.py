@@ -76,6 +76,36 @@ def test_demofusion_class_matches_oracle(case):
 
 
 @pytest.mark.gpu
+def test_demofusion_cfg5_size_matches_oracle():
+    """BASELINE cfg5's step (bench.py --config cfg5): latent [2,4,768,768] fp16, 121 windows of 128^2, scale 4, mixture --
+    the class on the sm_100a kernels against the oracle run on the host at the same size."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    c = bench.DEMO
+    d, fwd, calls = bench._demo_job(torch.device("cuda"), torch.float16, True, False)
+    d.get_views(c["overlap"], c["tile_bs"], c["tile_bs_g"])
+    half = lambda x_tile, sigma=None, cond=None: demo_denoise(x_tile)
+    d.sampler_forward = half
+    cf = odf.cosine_factor(c["current_step"], c["t_enc"])
+    d.cosine_factor = cf
+    L = c["lat"]
+    x = synth.latent(77, (c["N"], c["C"], L, L), torch.float16)
+    local, _, _ = tiling.demofusion_views(L, L, c["window"], c["overlap"])
+    assert [(b.x, b.y, b.w, b.h) for bb in d.batched_bboxes for b in bb] == local and len(local) == 121
+    lb = [local[i * d.tile_bs:(i + 1) * d.tile_bs] for i in range(d.num_batches)]
+    views = odf.global_views(c["scale"], True)
+    gb = [views[i * d.global_tile_bs:(i + 1) * d.global_tile_bs] for i in range(d.global_num_batches)]
+    want = odf.sample_one_step(x, lb, gb, c["scale"], True, True, c["sig"], cf, c["cs2"], c["cs3"],
+                               lambda t, b: demo_denoise(t), lambda t, b: demo_denoise(t))
+    cond = {"c_crossattn": [torch.zeros(c["N"], 77, 8, device="cuda")], "c_concat": [torch.zeros(c["N"], 5, 1, 1, device="cuda")]}
+    got = d.sample_one_step(x.cuda(), torch.ones(c["N"], device="cuda"), cond)
+    assert got.dtype == torch.float16 and got.shape == want.shape
+    err = (got.cpu().float() - want.float()).abs().max().item()
+    assert err <= 2e-3 * max(1.0, want.float().abs().max().item()), f"max err {err}"
+
+
+@pytest.mark.gpu
 def test_dilated_gather_and_combine_are_exact():
     """Index work is bit-exact: gather == strided slices; combine == the eager add-back + mix in fp16."""
     import ctypes
