@@ -274,13 +274,18 @@ class StripWorkload:
 
     def launches_per_step(self):
         sh = self.shard
-        return 1 + len(sh.halo_out()) + 1 + 1 + len(sh.x_out()) + 1 + (1 if sh.x_in() else 0)
+        return 4          # scatter, tile-halo push (+ signal), strip blend (+ in-kernel wait), latent-halo push (+ signal + wait)
 
     def parity(self):
         """One more step, then: every rank's strip == the single-GPU blend of ALL ranks' tile outputs (computed on every
         rank from the gathered outputs; compared on the gathered latent).  Bit patterns."""
         import torch.distributed as dist
         g, sh = self.g, self.shard
+        # fresh tile outputs first: a halo left over from the timed steps (same values every step) must not pass
+        own_now = self.ex.own_tiles()
+        own_now.copy_((torch.randn(own_now.shape, device=self.dev, dtype=torch.float32) * 0.8 + 0.1 * (self.rank + 1)).half())
+        torch.cuda.synchronize()
+        dist.barrier()
         self.step(0)
         torch.cuda.synchronize()
         full = self.ex.gather_latent(self.ex.x_out)
@@ -663,6 +668,27 @@ def strip_arm(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sec = float(t.item()) / 1e3 / args.steps
             ok = wl.parity()
+            if args.variants:      # where the step goes: graphs of growing prefixes of the step (every rank replays the same prefix)
+                def prefix(n):
+                    def run(i):
+                        wl.scatter()
+                        if n >= 2: wl.ex.push_tile_halos()
+                        if n >= 3: wl.ex.blend(wl.g, wl.weights, wl.rcp_weights)
+                        if n >= 4: wl.ex.push_x_halos_and_wait()
+                        else: wl.ex.join_side()
+                    return run
+                table = {}
+                for n, name in ((1, "scatter"), (2, "+push_tiles"), (3, "+blend"), (4, "+push_x_wait")):
+                    torch.cuda.synchronize(); dist.barrier()
+                    rp = timed_graph_loop(prefix(n), 500, stream)
+                    rp(); torch.cuda.synchronize(); dist.barrier()
+                    tt = torch.tensor([event_time_ms(rp, stream)], device=dev)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    table[name] = round(float(tt.item()) / 500 * 1e3, 2)
+                    if n in (2, 3):    # the x flags' counters must stay level on every rank for the later prefixes: they are (same replays everywhere)
+                        pass
+                if rank == 0:
+                    print(f"[strip variants {scaling}] cumulative us/step: {table}", file=sys.stderr, flush=True)
             e2e = strip_e2e(args, dev, stream, world, rank) if scaling == "strong" else None
         mp_img = wl.H * wl.W * 64 / 1e6
         results[scaling] = {"value": mp_img / (SAMPLER_STEPS * sec), "ms_per_step": sec * 1e3, "canvas": [wl.H, wl.W], "tiles": wl.T,

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TD_ABI_VERSION 4
+#define TD_ABI_VERSION 5
 
 typedef enum td_status {
     TD_OK = 0,
@@ -240,15 +240,38 @@ int td_blend_multidiffusion_peer(const td_grid* g, const void* const* batch_ptrs
  * preceded in-kernel by the acquire wait of td_blend_multidiffusion_peer on wait_flags[0 .. wait_count) (wait_count 0: no
  * wait).  A rank blends only the rows it owns; batch_ptrs has one entry per tile ROW (tile_bs = cols): the rank's own tile
  * outputs or the halo buffer its neighbours pushed the overlapping tile rows into (entries of tile rows that do not
- * touch the range are never dereferenced).  Same arithmetic, same tile order: bit-identical to the whole-canvas blend. */
+ * touch the range are never dereferenced).  Same arithmetic, same tile order: bit-identical to the whole-canvas blend.
+ * own_band_begin / own_band_end: tile rows whose batch_ptrs entries are LOCAL outputs -- CTAs that read only those skip the
+ * wait and are scheduled ahead of the ones that need a neighbour's halo (begin == end: every CTA waits). */
 int td_blend_multidiffusion_rows(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs,
                                  int N, int C, int tile_dtype, int acc_dtype, const float* weights,
                                  const float* rcp_weights, float* x_out, void* x_buffer, int row_begin, int row_end,
                                  const uint32_t* wait_flags, int wait_count, const uint32_t* wait_value,
-                                 uint32_t flags, void* stream);
+                                 int own_band_begin, int own_band_end, uint32_t flags, void* stream);
 /* One warp spins (acquire, system scope, bounded) until flags[i] >= *value for i < count: stream-ordered work after it
  * sees what the signalling ranks wrote before their td_peer_signal. */
 int td_peer_wait(const uint32_t* flags, int count, const uint32_t* value, void* stream);
+
+/* Halo push of the row-strip shard in one launch of TD_PUSH_CTAS CTAs: copies up to TD_MAX_PUSH_REGIONS strided 2-D regions
+ * (16-byte aligned pointers / pitches / row lengths; dst usually IPC-mapped peer memory); every CTA then adds 1 (release,
+ * system scope) to each target_slots[i] -- DEVICE pointers to slot `rank` of the targets' flag arrays -- so a slot advances by
+ * TD_PUSH_CTAS per push and "slot >= expect" means the whole push has landed (one NVLink round trip for data + signal).
+ * expect_own (NULL: untouched): this rank's expect counter of the set, advanced by TD_PUSH_CTAS when the launch starts; with
+ * wait_count > 0 the launch then waits until wait_flags[i] >= *expect_own for i < wait_count (as td_peer_wait).
+ * bump_next (NULL: none): a second expect counter advanced by TD_PUSH_CTAS at the end of the launch -- the tile-halo set's,
+ * by the latent-halo push that closes a step, so that the next step's blend (td_blend_multidiffusion_rows: wait_value) reads a
+ * value written on ITS stream while the tile-halo push itself may run on a side stream.  Expect counters of a set that is
+ * only ever waited on through bump_next start at TD_PUSH_CTAS. */
+#define TD_MAX_PUSH_REGIONS 8
+#define TD_PUSH_CTAS 32
+typedef struct td_push_region {
+    const void* src;
+    void* dst;
+    int32_t planes, rows;
+    int64_t row_bytes, src_plane_bytes, src_pitch_bytes, dst_plane_bytes, dst_pitch_bytes;
+} td_push_region;
+int td_push_regions(const td_push_region* regions, int n_regions, void* const* target_slots, int n_targets,
+                    uint32_t* expect_own, const uint32_t* wait_flags, int wait_count, uint32_t* bump_next, void* stream);
 
 /* Region prompt control (custom bboxes): everything after the regions' denoiser calls in ONE launch --
  * multidiffusion.py:187-216 / mixtureofdiffusers.py:145-175.  x_buffer: the grid accumulator [N,C,H,W] of `dtype`
@@ -344,6 +367,15 @@ typedef struct td_conv_desc {
 } td_conv_desc;
 int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
                    void* y, void* stream);
+
+/* ldm's Upsample block -- F.interpolate(scale_factor=2, mode="nearest") then a 3x3 / pad 1 convolution ('upsample' task +
+ * the 'conv' that follows it, tilevae.py:163-166) -- WITHOUT materialising the upsampled tensor: output pixel (2i+py, 2j+px)
+ * only ever sees the 2x2 low-resolution neighbourhood {i-1+py, i+py} x {j-1+px, j+px}, so the block is four 2x2
+ * convolutions of the low-resolution image, one per output parity, with the 3x3 taps that fall on the same source pixel
+ * summed (4/9 of the multiply-adds, no 4x intermediate in HBM).  `d` describes the block as the reference sees it:
+ * H x W input, OH = 2H, OW = 2W, kh = kw = 3, stride 1, pad 1; w16: folded taps [16 = (py*2+px)*4 + ty*2 + tx][Cout][w_pitch]
+ * (fold in fp32, round once: vae_ops.fold_upsample_weight); no residual; the post_scale / post_shift stage applies. */
+int td_upconv2x_nhwc(const td_conv_desc* d, const void* x, const void* w16, const float* bias, void* y, void* stream);
 
 /* Channels-last (NHWC) streaming kernels around the tensor-core convolutions (csrc/td_nhwc.cu).  fp16 / bf16.
  *

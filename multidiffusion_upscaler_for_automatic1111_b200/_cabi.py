@@ -32,7 +32,7 @@ TD_MAX_GRID_DIM = 256
 TD_MAX_BATCH_PTRS = 128
 TD_MAX_PEERS = 16
 TD_IPC_HANDLE_BYTES = 64
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 DTYPE_CODE = {torch.float16: TD_F16, torch.bfloat16: TD_BF16, torch.float32: TD_F32}
 
@@ -62,6 +62,16 @@ TD_MAX_REGIONS = 32
 class TdRegion(ctypes.Structure):
     """struct td_region (include/td_b200.h)."""
     _fields_ = [("x", c_int32), ("y", c_int32), ("w", c_int32), ("h", c_int32), ("mode", c_int32), ("out", c_void_p), ("aux", c_void_p)]
+
+
+class TdPushRegion(ctypes.Structure):
+    """struct td_push_region (include/td_b200.h)."""
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("planes", c_int32), ("rows", c_int32), ("row_bytes", c_int64),
+                ("src_plane_bytes", c_int64), ("src_pitch_bytes", c_int64), ("dst_plane_bytes", c_int64), ("dst_pitch_bytes", c_int64)]
+
+
+TD_MAX_PUSH_REGIONS = 8
+TD_PUSH_CTAS = 32
 
 
 class TdConvDesc(ctypes.Structure):
@@ -111,8 +121,10 @@ _SIGNATURES = {
     "td_blend_multidiffusion_peer": (c_int, [POINTER(TdGrid), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_uint32, c_void_p]),
     "td_blend_multidiffusion_rows": (c_int, [POINTER(TdGrid), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int,
-                                             c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_uint32, c_void_p]),
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
+                                             c_uint32, c_void_p]),
     "td_peer_wait": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "td_push_regions": (c_int, [POINTER(TdPushRegion), c_int, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "td_region_composite": (c_int, [c_void_p, c_void_p, POINTER(TdRegion), c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "td_dilated_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int32),
                                   POINTER(c_int32), POINTER(c_int32), c_int, c_int, c_void_p]),
@@ -126,6 +138,7 @@ _SIGNATURES = {
                                              c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
     "td_depthwise_conv2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_float), c_int, c_int, c_void_p]),
     "td_conv2d_nhwc": (c_int, [POINTER(TdConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "td_upconv2x_nhwc": (c_int, [POINTER(TdConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "td_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "td_nhwc_to_nchw_region": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int, c_int64, c_int64, c_int64, c_int64,
                                        c_int, c_void_p]),

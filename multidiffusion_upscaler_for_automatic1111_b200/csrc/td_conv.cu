@@ -37,7 +37,7 @@ namespace {
 
 using namespace td;
 
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 384;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 and 8-11: two epilogue groups
 constexpr int kConvBM = 128;              // output pixels per tile = UMMA M
 constexpr int kConvBK = 64;               // channels per stage (128 bytes of fp16 = one swizzle row)
 constexpr int kConvStageA = kConvBM * kConvBK * 2;   // 16 KB
@@ -73,6 +73,9 @@ struct ConvParams {
     int m_tiles;               // NI * tiles_y * tiles_x
     int m_groups;              // ceil(m_tiles / cluster)
     float alpha;
+    int up2;                   // 1: nearest-2x upsample folded into the 3x3 convolution -- four 2x2 convolutions of the LOW-resolution
+                               // image, one per output parity (py, px) = "image" index & 3; weights [16 taps, Cout, Cin]; the
+                               // output map is 5-D {c, x, y, px, py} over the high-resolution tensor
     long long res_pitch;       // residual: elements between pixels (0: none)
 };
 
@@ -131,6 +134,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t src) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src) : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(src) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -261,7 +268,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // a stage is free when the MMAs of EVERY CTA of the cluster have read it (peers multicast into it)
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.pair ? 1u : (uint32_t)p.cluster); }
         // pair: the leader's MMA thread waits for the epilogues of BOTH CTAs (the peer's threads arrive remotely)
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], p.pair ? 256u : 128u); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], p.pair ? 512u : 256u); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
@@ -288,9 +295,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int g = cid; g < num_groups; g += nclusters) {
                 const TileCoord c = decode_tile(p, g, crank);
                 // pair: this CTA stages sub-tile `crank` of the patch
-                const int x0 = (c.px * p.BW + (p.pair ? crank * p.MT * p.sub_dx : 0)) * p.stride - p.pad_left;
-                const int y0 = (c.py * p.BH + (p.pair ? crank * p.MT * p.sub_dy : 0)) * p.stride - p.pad_top;
-                int tap = 0;
+                // up2: output parity (py, px) shifts the 2x2 window by one low-resolution pixel and selects its 4 folded taps
+                const int par = p.up2 ? (c.img & 3) : 0;
+                const int img = p.up2 ? (c.img >> 2) : c.img;
+                const int x0 = (c.px * p.BW + (p.pair ? crank * p.MT * p.sub_dx : 0)) * p.stride - p.pad_left + (par & 1);
+                const int y0 = (c.py * p.BH + (p.pair ? crank * p.MT * p.sub_dy : 0)) * p.stride - p.pad_top + (par >> 1);
+                int tap = par * 4;
                 for (int ty = 0; ty < p.taps_y; ++ty)
                     for (int tx = 0; tx < p.taps_x; ++tx, ++tap)
                         for (int kc = 0; kc < p.Cin_chunks; ++kc) {
@@ -300,14 +310,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 // both CTAs' copies complete on the leader's barrier, which expects the bytes of the pair
                                 const uint32_t lbar = smem_u32(&full_bar[stage]) & kPeerBitMask;
                                 if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * stage_bytes);
-                                tma_load_4d_2sm(sa, &map_a, kc * kConvBK, x0 + tx, y0 + ty, c.img, lbar);
+                                tma_load_4d_2sm(sa, &map_a, kc * kConvBK, x0 + tx, y0 + ty, img, lbar);
                                 tma_load_3d_2sm(sa + stage_a, &map_b, kc * kConvBK, c.nb * p.BN + crank * (p.BN / 2), tap, lbar);
                                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                                 continue;
                             }
                             mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                             if constexpr (!PAIR) {
-                                tma_load_4d(sa, &map_a, kc * kConvBK, x0 + tx, y0 + ty, c.img, &full_bar[stage]);
+                                tma_load_4d(sa, &map_a, kc * kConvBK, x0 + tx, y0 + ty, img, &full_bar[stage]);
                                 if (p.cluster == 1)
                                     tma_load_3d_u32(sa + stage_a, &map_b, kc * kConvBK, c.nb * p.BN, tap, &full_bar[stage]);
                                 else
@@ -355,40 +365,60 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else if (warp >= 4) {
         // ===================== epilogue: TMEM -> registers -> smem -> TMA store =====================
+        // Two groups of four warps (TMEM lane quarters 0-3 each) split the (sub-tile, 64-column chunk) units of a tile
+        // between them: with one group the epilogue of a 256 x 128 tile (TMEM -> fma / residual / SiLU -> fp16 -> smem)
+        // took longer than its MMAs whenever K is short (128 -> 128 3x3: 13.8 us against 9.8 us, measured per tile)
         const int q = warp & 3;                       // TMEM lane quarter of this warp
+        const int eg = (warp - 4) >> 2;               // epilogue group
         const int row = q * 32 + lane;                // accumulator row = pixel index inside the tile
-        const int et = threadIdx.x - 128;             // 0..127
+        const int et = (threadIdx.x - 128) & 127;     // 0..127 inside the group
+        const int bar_id = 1 + eg;
+        const uint32_t sbuf = store0 + (uint32_t)eg * kConvStoreBuf;   // one staging buffer per group
         int as = 0; uint32_t aphase = 0;
-        int buf = 0;
         for (int g = cid; g < num_groups; g += nclusters) {
             const TileCoord c = decode_tile(p, g, crank);
             mbar_wait(&acc_full[as], aphase);
             tc_fence_after();
             const int nchunks = p.BN / p.chunk_cols;
-            for (int mt0 = 0; mt0 < p.MT; ++mt0) {
+            const int units = p.MT * nchunks;
+            const int last_u = units - 1 - ((units - 1 - eg) & 1);      // this group's last unit (< eg: none)
+            if (last_u < eg) {                                          // nothing to read: hand the stage straight back
+                tc_fence_before();
+                if (p.pair) mbar_arrive_cluster(smem_u32(&acc_empty[as]) & kPeerBitMask);
+                else mbar_arrive(&acc_empty[as]);
+            }
+            for (int u = eg; u < units; u += 2) {
+                const int mt0 = u / nchunks, ch = u - mt0 * nchunks;
+                {
                 const int mt = p.pair ? crank * p.MT + mt0 : mt0;   // pair: this CTA holds sub-tiles [crank * MT, (crank + 1) * MT) of the patch
                 const int pidx = mt * kConvBM + row;          // pixel index inside the patch (= shared-memory row of the A box)
                 const int ly = pidx / p.BW, lx = pidx - ly * p.BW;
                 const int ox = c.px * p.BW + lx, oy = c.py * p.BH + ly;
                 const bool pix_ok = ox < p.OW && oy < p.OH && c.img < p.NI;
                 const long long pix = ((long long)c.img * p.OH + oy) * p.OW + ox;
-                for (int ch = 0; ch < nchunks; ++ch) {
+                {
                     const int col0 = c.nb * p.BN + ch * p.chunk_cols;
-                    // the staging buffer about to be overwritten must have been read by its previous TMA store
-                    if (et == 0) bulk_wait_read<1>();
-                    named_bar_sync(1, 128);
-                    const uint32_t sbuf = store0 + (uint32_t)buf * kConvStoreBuf;
+                    const int ng = p.chunk_cols / 16;
+                    // residual row of this chunk (up to 128 bytes per thread): in flight before anything else waits
+                    const bool has_res = residual != nullptr && pix_ok;
+                    uint4 rres[8];
+                    if (has_res) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(residual + pix * p.res_pitch + col0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < 2 * ng && col0 + (j >> 1) * 16 + 16 <= p.Cout) rres[j] = __ldg(rp + j);
+                    }
                     // all TMEM loads of the chunk in flight before the single wait (up to 64 columns = 64 registers)
                     uint32_t racc[4][16];
-                    const int ng = p.chunk_cols / 16;
                     __syncwarp();
                     const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * acc_cols + (uint32_t)(mt0 * p.BN + ch * p.chunk_cols);
                     tc_ld16(tcol, racc[0]);
                     if (ng > 1) tc_ld16(tcol + 16u, racc[1]);
                     if (ng > 2) { tc_ld16(tcol + 32u, racc[2]); tc_ld16(tcol + 48u, racc[3]); }
+                    // the group's staging buffer must have been read by its previous TMA store
+                    if (et == 0) bulk_wait_read<0>();
+                    named_bar_sync(bar_id, 128);
                     tc_wait_ld();
-                    // residual rows of this chunk: issued early, consumed per group below
-                    const bool has_res = residual != nullptr && pix_ok;
 #pragma unroll
                     for (int g16 = 0; g16 < 4; ++g16) {
                         if (g16 >= ng) break;
@@ -417,8 +447,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             }
                         }
                         if (has_res && cb + 16 <= p.Cout) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(residual + pix * p.res_pitch + cb);
-                            const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                            const uint4 r0 = rres[2 * g16], r1 = rres[2 * g16 + 1];
                             const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
@@ -459,19 +488,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb + 16u), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
                         }
                     }
-                    if (mt0 == p.MT - 1 && ch == nchunks - 1) {   // every TMEM read of this accumulator stage is done: hand it back
+                    if (u == last_u) {   // this group's TMEM reads of the accumulator stage are done: hand it back
                         tc_fence_before();
                         if (p.pair) mbar_arrive_cluster(smem_u32(&acc_empty[as]) & kPeerBitMask);   // on the leader's barrier
                         else mbar_arrive(&acc_empty[as]);
                     }
                     fence_proxy_async();
-                    named_bar_sync(1, 128);
+                    named_bar_sync(bar_id, 128);
                     if (et == 0) {
-                        if (c.img < p.NI)
-                            tma_store_4d(&map_d, col0, c.px * p.BW + mt * p.sub_dx, c.py * p.BH + mt * p.sub_dy, c.img, sbuf);
+                        if (c.img < p.NI) {
+                            if (p.up2) tma_store_5d(&map_d, col0, c.px * p.BW + mt * p.sub_dx, c.py * p.BH + mt * p.sub_dy, c.img & 1, c.img >> 1, sbuf);
+                            else tma_store_4d(&map_d, col0, c.px * p.BW + mt * p.sub_dx, c.py * p.BH + mt * p.sub_dy, c.img, sbuf);
+                        }
                         bulk_commit();
                     }
-                    buf ^= 1;
+                }
                 }
             }
             if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
@@ -554,13 +585,21 @@ ConvDev conv_dev() {
 
 }  // namespace
 
-extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
-                              void* y, void* stream) {
+namespace {
+// up2 = 1: `d` describes nearest-2x upsample + 3x3 / pad 1 (OH = 2 H, OW = 2 W) of ONE image; `w` holds the 16 folded taps.
+int conv_run(const td_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y, void* stream, int up2) {
     if (d == nullptr || x == nullptr || w == nullptr || y == nullptr) { td_set_error("td_conv2d_nhwc: null argument"); return TD_ERR_INVALID_ARG; }
     if (d->dtype != TD_F16 && d->dtype != TD_BF16) { td_set_error("td_conv2d_nhwc: dtype must be fp16 or bf16"); return TD_ERR_UNSUPPORTED; }
     if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->OH <= 0 || d->OW <= 0 || d->Cin <= 0 || d->Cout <= 0) { td_set_error("td_conv2d_nhwc: non-positive size"); return TD_ERR_INVALID_ARG; }
     if (d->Cin % 8 != 0) { td_set_error("td_conv2d_nhwc: Cin (%d) must be a multiple of 8", d->Cin); return TD_ERR_UNSUPPORTED; }
     if ((d->kh != 1 && d->kh != 3) || d->kh != d->kw || (d->stride != 1 && d->stride != 2)) { td_set_error("td_conv2d_nhwc: only 1x1 / 3x3, stride 1 / 2"); return TD_ERR_UNSUPPORTED; }
+    if (up2 && (d->kh != 3 || d->stride != 1 || d->pad_top != 1 || d->pad_left != 1 || d->OH != 2 * d->H || d->OW != 2 * d->W || d->N != 1 ||
+                residual != nullptr || d->bias_per_row)) {
+        td_set_error("td_upconv2x_nhwc: describes upsample(2x nearest) + 3x3 / stride 1 / pad 1 (OH = 2H, OW = 2W), no residual, bias per channel");
+        return TD_ERR_INVALID_ARG;
+    }
+    // grid of output pixels the tiles walk: the low-resolution image (once per output parity) when the upsample is folded
+    const int gOW = up2 ? d->W : d->OW, gOH = up2 ? d->H : d->OH, gN = up2 ? 4 : d->N;
     if (d->x_pitch < d->Cin || d->x_pitch % 8 != 0 || d->y_pitch < d->Cout || d->y_pitch % 8 != 0 || d->w_pitch < d->Cin || d->w_pitch % 8 != 0 ||
         (residual != nullptr && (d->res_pitch < d->Cout || d->res_pitch % 8 != 0))) {
         td_set_error("td_conv2d_nhwc: pitches must cover the channels and be multiples of 8 elements (16 bytes)");
@@ -573,8 +612,8 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
 
     ConvParams p;
     std::memset(&p, 0, sizeof(p));
-    p.taps_x = d->kw; p.taps_y = d->kh; p.stride = d->stride; p.pad_left = d->pad_left; p.pad_top = d->pad_top;
-    p.OW = d->OW; p.OH = d->OH; p.NI = d->N;
+    p.taps_x = up2 ? 2 : d->kw; p.taps_y = up2 ? 2 : d->kh; p.stride = d->stride; p.pad_left = d->pad_left; p.pad_top = d->pad_top;
+    p.OW = gOW; p.OH = gOH; p.NI = gN; p.up2 = up2;
     p.Cin_chunks = (d->Cin + 63) / 64;   // a partial last chunk is zero-filled by the TMA unit on BOTH operands
     p.Cout = d->Cout;
     int bn = 256;
@@ -582,13 +621,13 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     p.BN = bn;
     p.n_blocks = (d->Cout + bn - 1) / bn;
     // pixel sub-tile (128 pixels = UMMA M): wide for a GEMM (H == 1), 16 x 8 for images; MT sub-tiles per CTA tile
-    if (d->OH == 1) { p.BWs = 128; p.BHs = 1; p.sub_dx = 128; p.sub_dy = 0; }
-    else if (d->OW >= 16) { p.BWs = 16; p.BHs = 8; p.sub_dx = 0; p.sub_dy = 8; }
+    if (gOH == 1) { p.BWs = 128; p.BHs = 1; p.sub_dx = 128; p.sub_dy = 0; }
+    else if (gOW >= 16) { p.BWs = 16; p.BHs = 8; p.sub_dx = 0; p.sub_dy = 8; }
     else { p.BWs = 8; p.BHs = 16; p.sub_dx = 0; p.sub_dy = 16; }
     {
         const char* fm = getenv("TD_CONV_MT");
         const int want_mt = fm != nullptr ? atoi(fm) : 2;
-        const long long sub_tiles = (long long)d->N * ((d->OW + p.BWs - 1) / p.BWs) * ((d->OH + p.BHs - 1) / p.BHs) * p.n_blocks;
+        const long long sub_tiles = (long long)gN * ((gOW + p.BWs - 1) / p.BWs) * ((gOH + p.BHs - 1) / p.BHs) * p.n_blocks;
         // two sub-tiles per CTA when the grid stays full (>= 4 sub-tiles per SM) and the box fits (<= 256 per dimension)
         // ... and while two accumulator stages still fit in TMEM (BN <= 128): with one stage the epilogue no longer overlaps
         // the next tile's MMAs (measured: 256 -> 256 at 472^2 drops from 1309 to 1110 TFLOP/s, 128 -> 128 at 944^2 rises
@@ -601,16 +640,16 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     {
         const char* fp = getenv("TD_CONV_PAIR");
         const int want_pair = fp != nullptr ? atoi(fp) : 1;
-        const long long sub_tiles = (long long)d->N * ((d->OW + p.BWs - 1) / p.BWs) * ((d->OH + p.BHs - 1) / p.BHs) * p.n_blocks;
+        const long long sub_tiles = (long long)gN * ((gOW + p.BWs - 1) / p.BWs) * ((gOH + p.BHs - 1) / p.BHs) * p.n_blocks;
         p.pair = (want_pair >= 1 && bn >= 128 && dev.sms % 2 == 0 && sub_tiles >= 4LL * p.MT * dev.sms) ? 1 : 0;
     }
     const int patch_subs = p.MT * (p.pair ? 2 : 1);             // sub-tiles per patch
     p.BW = p.BWs + (patch_subs - 1) * p.sub_dx;
     p.BH = p.BHs + (patch_subs - 1) * p.sub_dy;
     p.acc_stages = std::min(2, 512 / (p.MT * bn));
-    p.tiles_x = (d->OW + p.BW - 1) / p.BW;
-    p.tiles_y = (d->OH + p.BH - 1) / p.BH;
-    const long long mt = (long long)d->N * p.tiles_x * p.tiles_y;
+    p.tiles_x = (gOW + p.BW - 1) / p.BW;
+    p.tiles_y = (gOH + p.BH - 1) / p.BH;
+    const long long mt = (long long)gN * p.tiles_x * p.tiles_y;
     if (mt * p.n_blocks > 0x3fffffffLL) { td_set_error("td_conv2d_nhwc: too many tiles"); return TD_ERR_UNSUPPORTED; }
     p.m_tiles = (int)mt;
     // CTA clusters: the weight tile of a k-step is fetched once per cluster (each CTA loads BN / cluster rows and
@@ -648,14 +687,23 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
         if (rc != TD_OK) return rc;
     }
     {
-        const uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout, (uint64_t)(d->kh * d->kw)};
+        const uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout, (uint64_t)(up2 ? 16 : d->kh * d->kw)};
         const uint64_t str[2] = {(uint64_t)d->w_pitch * 2, (uint64_t)d->Cout * d->w_pitch * 2};
         const uint32_t box[3] = {64, (uint32_t)(bn / p.cluster), 1};      // cluster multicast slices and the pair's halves alike
         const uint32_t es[3] = {1, 1, 1};
         const int rc = encode_map(&mb, w, p.is_bf16, 3, dims, str, box, es, true, "weights");
         if (rc != TD_OK) return rc;
     }
-    {
+    if (up2) {
+        // y[2 i + py, 2 j + px, c] as {c, j, i, px, py}: the tile of one parity lands on every second pixel of every second row
+        const uint64_t row = (uint64_t)d->OW * d->y_pitch * 2;
+        const uint64_t dims[5] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, 2, 2};
+        const uint64_t str[4] = {(uint64_t)d->y_pitch * 4, row * 2, (uint64_t)d->y_pitch * 2, row};
+        const uint32_t box[5] = {(uint32_t)p.chunk_cols, (uint32_t)p.BWs, (uint32_t)p.BHs, 1, 1};
+        const uint32_t es[5] = {1, 1, 1, 1, 1};
+        const int rc = encode_map(&md, y, p.is_bf16, 5, dims, str, box, es, p.chunk_cols == 64, "output (parity view)");
+        if (rc != TD_OK) return rc;
+    } else {
         const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->OW, (uint64_t)d->OH, (uint64_t)d->N};
         const uint64_t str[3] = {(uint64_t)d->y_pitch * 2, (uint64_t)d->OW * d->y_pitch * 2, (uint64_t)d->OH * d->OW * d->y_pitch * 2};
         const uint32_t box[4] = {(uint32_t)p.chunk_cols, (uint32_t)p.BWs, (uint32_t)p.BHs, 1};
@@ -682,5 +730,24 @@ extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* 
     if (le != cudaSuccess) { td_set_error("td_conv2d_nhwc: launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return TD_ERR_CUDA; }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { td_set_error("td_conv2d_nhwc: launch failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+    return TD_OK;
+}
+}  // namespace
+
+extern "C" int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
+                              void* y, void* stream) {
+    return conv_run(d, x, w, bias, residual, y, stream, 0);
+}
+
+extern "C" int td_upconv2x_nhwc(const td_conv_desc* d, const void* x, const void* w16, const float* bias, void* y, void* stream) {
+    if (d == nullptr || x == nullptr || y == nullptr) { td_set_error("td_upconv2x_nhwc: null argument"); return TD_ERR_INVALID_ARG; }
+    td_conv_desc one = *d;
+    one.N = 1;
+    for (int n = 0; n < d->N; ++n) {
+        const uint16_t* xn = static_cast<const uint16_t*>(x) + (size_t)n * d->H * d->W * d->x_pitch;
+        uint16_t* yn = static_cast<uint16_t*>(y) + (size_t)n * d->OH * d->OW * d->y_pitch;
+        const int rc = conv_run(&one, xn, w16, bias, nullptr, yn, stream, 1);
+        if (rc != TD_OK) return rc;
+    }
     return TD_OK;
 }

@@ -52,6 +52,10 @@ struct BlendParams {
     int wait_world;
     const uint32_t* wait_value;  // this rank's device-side step counter (bumped by td_peer_signal)
     int py0, py_count;      // cp.async kernels: first patch row and patch-row count of this launch (row-range blend; 0, 0 = all)
+    int own_r_lo, own_r_hi; // row-strip shard: tile rows [lo, hi) are this rank's own outputs -- a CTA whose visits stay inside them
+                            // skips the peer wait (lo == hi: every CTA waits)
+    int sched;              // 0: blockIdx.y = patch row, .z = plane group; 1 / 2: blockIdx.z = patch row ascending / descending
+                            // (slowest-varying), so that the CTAs that must wait for a neighbour's halo are scheduled last
     long long tile_stride;  // N*C*th*tw elements
     const void* batch_ptrs[TD_MAX_BATCH_PTRS];
 };
@@ -459,8 +463,9 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
     __shared__ int s_shift[kAsMaxVisits];
     const GeomParams& g = p.g;
     const int tid = threadIdx.x;
-    const int plane = blockIdx.z * PPC;      // first plane of this CTA (the host launches PPC > 1 only if it divides N*C)
-    const int by = (int)blockIdx.y + p.py0;   // patch row (a row-range launch starts at py0)
+    const int zy = p.sched == 0 ? (int)blockIdx.y : (p.sched == 2 ? p.py_count - 1 - (int)blockIdx.z : (int)blockIdx.z);
+    const int plane = (p.sched == 0 ? (int)blockIdx.z : (int)blockIdx.y) * PPC;   // first plane of this CTA (PPC divides N*C)
+    const int by = zy + p.py0;                // patch row (a row-range launch starts at py0)
     const int x_lo = blockIdx.x * BX, y_lo = by * kAsY;
     pdl_launch_dependents();
 
@@ -482,7 +487,8 @@ blend_md_async_kernel(const __grid_constant__ BlendParams p, const float* __rest
         if constexpr (FASTDIV) rv[h] = inside ? __ldg(reinterpret_cast<const float4*>(rcp_weights + wo) + h) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
 
-    if (p.wait_flags != nullptr && tid >= kAsThreads - 32 && tid - (kAsThreads - 32) < p.wait_world) {
+    const bool reads_halo = r_lo < p.own_r_lo || r_lo + (int)p.prow_n[by] > p.own_r_hi;   // always true when own_r_lo == own_r_hi
+    if (p.wait_flags != nullptr && reads_halo && tid >= kAsThreads - 32 && tid - (kAsThreads - 32) < p.wait_world) {
         // tile shard: the peers' tile outputs must be complete before any copy reads them (last warp spins,
         // the barrier below publishes it to the CTA)
         const uint32_t want = *p.wait_value;
@@ -1401,7 +1407,8 @@ int launch_blend_async_ppc(const BlendParams& bp, const float* weights, const fl
     static SmemOptIn configured;
     int rc = ensure_dyn_smem(blend_md_async_kernel<T, WRITE_BUF, FASTDIV, PPC>, smem, &configured);
     if (rc != TD_OK) return rc;
-    dim3 grid((unsigned)px, (unsigned)(bp.py_count > 0 ? bp.py_count : py), (unsigned)(planes / PPC));
+    const unsigned gy = (unsigned)(bp.py_count > 0 ? bp.py_count : py), gz = (unsigned)(planes / PPC);
+    dim3 grid((unsigned)px, bp.sched ? gz : gy, bp.sched ? gy : gz);
     launch_pdl(blend_md_async_kernel<T, WRITE_BUF, FASTDIV, PPC>, grid, dim3(kAsThreads), (size_t)smem, st, bp, weights, rcp_weights,
                out_f32, (T*)out_buf);
     return TD_OK;
@@ -1450,6 +1457,17 @@ int launch_blend_async(const td_grid* g, const BlendParams& bp_in, const float* 
     BlendParams bp = bp_in;
     fill_patch_table(g->ys, g->rows, g->tile_h, g->H, kAsY, bp.prow_lo, bp.prow_n);
     fill_patch_table(g->xs, g->cols, g->tile_w, g->W, BX, bp.pcol_lo, bp.pcol_n);
+    if (bp.wait_flags != nullptr && bp.own_r_hi > bp.own_r_lo && bp.py_count > 0 && !pipelined) {
+        // row-strip shard: only the CTAs that read a neighbour's band wait; they sit at the end of the row range the halo
+        // enters from and are scheduled last (patch row = slowest grid dimension, walked away from that end)
+        int first_wait = -1, last_wait = -1;
+        for (int by = bp.py0; by < bp.py0 + bp.py_count; ++by) {
+            const int lo = bp.prow_lo[by], n = bp.prow_n[by];
+            if (n > 0 && (lo < bp.own_r_lo || lo + n > bp.own_r_hi)) { if (first_wait < 0) first_wait = by; last_wait = by; }
+        }
+        const int mid2 = 2 * bp.py0 + bp.py_count - 1;      // 2 x centre of the range
+        bp.sched = (first_wait >= 0 && first_wait + last_wait <= mid2) ? 2 : 1;
+    }
     if (rcp_weights != nullptr && sizeof(T) == 2)
         return launch_blend_async_impl<T, WRITE_BUF, true>(bp, weights, rcp_weights, out_f32, out_buf, nv_cap, pipelined, st);
     return launch_blend_async_impl<T, WRITE_BUF, false>(bp, weights, nullptr, out_f32, out_buf, nv_cap, pipelined, st);
@@ -1544,6 +1562,7 @@ int fill_blend(const td_grid* g, const void* const* batch_ptrs, int num_batches,
     bp->tile_bs = tile_bs;
     bp->wait_flags = nullptr; bp->wait_world = 0; bp->wait_value = nullptr;
     bp->py0 = 0; bp->py_count = 0;
+    bp->own_r_lo = 0; bp->own_r_hi = 0; bp->sched = 0;
     bp->bs_magic = magic_u16((unsigned)tile_bs);
     bp->num_batches = num_batches;
     bp->tile_stride = (long long)N * C * g->tile_h * g->tile_w;
@@ -1653,7 +1672,8 @@ extern "C" int td_blend_multidiffusion(const td_grid* g, const void* const* batc
 extern "C" int td_blend_multidiffusion_rows(const td_grid* g, const void* const* batch_ptrs, int num_batches, int tile_bs, int N,
                                             int C, int tile_dtype, int acc_dtype, const float* weights, const float* rcp_weights,
                                             float* x_out, void* x_buffer, int row_begin, int row_end, const uint32_t* wait_flags,
-                                            int wait_count, const uint32_t* wait_value, uint32_t flags, void* stream) {
+                                            int wait_count, const uint32_t* wait_value, int own_band_begin, int own_band_end,
+                                            uint32_t flags, void* stream) {
     BlendParams bp;
     tl_pdl = !(flags & TD_FLAG_NO_PDL);
     tl_ppc_max = (flags & TD_FLAG_ONE_PLANE) ? 1 : TD_AS_PPC;
@@ -1676,6 +1696,11 @@ extern "C" int td_blend_multidiffusion_rows(const td_grid* g, const void* const*
     bp.py0 = row_begin / 8;
     bp.py_count = (row_end - row_begin + 7) / 8;
     if (wait_count > 0) { bp.wait_flags = wait_flags; bp.wait_world = wait_count; bp.wait_value = wait_value; }
+    if (own_band_begin < 0 || own_band_end > g->rows || own_band_begin > own_band_end) {
+        td_set_error("td_blend_multidiffusion_rows: own bands [%d,%d) outside the %d tile rows", own_band_begin, own_band_end, g->rows);
+        return TD_ERR_INVALID_ARG;
+    }
+    if (wait_count > 0 && own_band_end > own_band_begin) { bp.own_r_lo = own_band_begin; bp.own_r_hi = own_band_end; }   // -> launch_blend_async
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     switch (tile_dtype) {

@@ -16,6 +16,7 @@ ranks and to a single-GPU run.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -257,6 +258,12 @@ class StripShard:
         return [(p, a, b) for p in range(self.world) if p != r for (q, a, b) in self.x_in(p) if q == r]
 
 
+# measurement switches (defaults = the shipped path): TD_STRIP_LATE_WAIT=0 -> every blend CTA waits for the halos (no own-band
+# test, no reordered schedule)
+_LATE_WAIT = os.environ.get("TD_STRIP_LATE_WAIT", "1") != "0"
+_OVERLAP_PUSH = os.environ.get("TD_STRIP_OVERLAP_PUSH", "1") != "0"     # 0 -> the tile-halo push stays on the caller's stream
+
+
 class _PeerFlags:
     """One flag array + device-side step counter per rank, mapped into every rank (see PeerExchange)."""
 
@@ -291,6 +298,31 @@ class _PeerFlags:
         table = (ctypes.c_void_p * self.world)(*tbl)
         with torch.cuda.device(self.device):
             check(lib.td_peer_signal(table, self.world, self.rank, ctypes.c_void_p(self.counter_ptr), _cabi.current_stream_ptr(self.device)))
+
+    def set_expect(self, value: int):
+        """Initial value of this set's expect counter (sets whose waiters are advanced through another push's bump_next)."""
+        t = self._buf.tensor(self.device)
+        t[128:132].view(torch.int32).fill_(int(value))
+        torch.cuda.synchronize(self.device)
+
+    def push(self, regions: Sequence[tuple], targets: Sequence[int], wait_first: int = 0, wait_count: int = 0, bump_own: bool = True,
+             bump_next: Optional[int] = None):
+        """Copy `regions` [(src, dst, planes, rows, row_bytes, src_plane_bytes, src_pitch_bytes, dst_plane_bytes,
+        dst_pitch_bytes)] (16-byte aligned) into peer memory and publish them in slot `rank` of the `targets`' flag arrays;
+        optionally advance this set's expect counter and wait for ranks [wait_first, wait_first + wait_count); optionally
+        advance another set's expect counter (device pointer) when done -- ONE launch (td_push_regions)."""
+        regions = list(regions)
+        if len(regions) > _cabi.TD_MAX_PUSH_REGIONS:
+            raise ValueError(f"{len(regions)} halo regions in one push (TD_MAX_PUSH_REGIONS = {_cabi.TD_MAX_PUSH_REGIONS})")
+        slots = [self.ptrs[q] + 4 * self.rank for q in targets if q != self.rank]
+        table = (ctypes.c_void_p * max(1, len(slots)))(*slots)
+        arr = (_cabi.TdPushRegion * max(1, len(regions)))()
+        for k, (src, dst, planes, rows, rb, sp, spi, dp, dpi) in enumerate(regions):
+            arr[k] = _cabi.TdPushRegion(src, dst, planes, rows, rb, sp, spi, dp, dpi)
+        with torch.cuda.device(self.device):
+            check(lib.td_push_regions(arr, len(regions), table, len(slots), ctypes.c_void_p(self.counter_ptr) if (bump_own or wait_count) else None,
+                                      ctypes.c_void_p(self.ptrs[self.rank] + 4 * wait_first) if wait_count else None, wait_count,
+                                      ctypes.c_void_p(bump_next) if bump_next else None, _cabi.current_stream_ptr(self.device)))
 
     def wait_args(self, first: int, count: int):
         """(flags pointer, count, value pointer) for a wait on ranks [first, first + count)."""
@@ -345,6 +377,8 @@ class StripExchange:
         self.flags_tiles.open([e[2] for e in everyone])
         self.flags_x.open([e[3] for e in everyone])
         self.x_out = self._xout.tensor(device).view(torch.float32).view(N, C, sh.H, W)
+        self._side, self._join = None, None
+        self.flags_tiles.set_expect(_cabi.TD_PUSH_CTAS)      # the first step's blend waits for ONE push of each sender
         self._senders = sorted({p for (_, p, _, _) in sh.halo_in()})
         self._x_senders = sorted({q for (q, _, _) in sh.x_in()})
         dist.barrier(group=group)
@@ -363,18 +397,43 @@ class StripExchange:
                                      dst_pitch, _cabi.dtype_code(dtype), _cabi.current_stream_ptr(self.device)))
 
     def push_tile_halos(self):
-        """Rows [v0, v1) of every tile of my band i -> the halo slot of band i on rank q (peer memory), then signal."""
+        """Rows [v0, v1) of every tile of my band i -> the halo slot of band i on rank q (peer memory), then signal:
+        one launch (td_push_regions)."""
         sh = self.shard
-        plane = sh.tile_h * self.tw
+        plane = sh.tile_h * self.tw * self.es
         planes = sh.cols * self.N * self.C
-        targets = set()
+        targets, regions = set(), []
         for (i, q, v0, v1) in sh.halo_out():
             src = self._own.data_ptr() + ((i - sh.band_begin[sh.rank]) * self.band_elems + v0 * self.tw) * self.es
             slot = self.peer_halo_bands[q].index(i)
             dst = self.peer_halo[q] + (slot * self.band_elems + v0 * self.tw) * self.es
-            self._copy_rows(src, dst, planes, v1 - v0, self.tw, plane, self.tw, plane, self.tw, self.dtype)
+            # rows v0..v1 of a tile are contiguous: one "row" of (v1 - v0) * tw elements per tile plane
+            regions.append((src, dst, planes, 1, (v1 - v0) * self.tw * self.es, plane, plane, plane, plane))
             targets.add(q)
-        self.flags_tiles.signal(sorted(targets))
+        if not self._aligned(regions):
+            raise ValueError("row-strip shard: tile width and halo offsets must be multiples of 16 bytes")
+        # the blend's expect counter of this set is advanced by the latent-halo push that closed the PREVIOUS step (bump_next):
+        # nothing this launch writes is read by this rank's own blend, so it may ride a side stream
+        if not _OVERLAP_PUSH:
+            self.flags_tiles.push(regions, sorted(targets), bump_own=False)
+            return
+        # side stream: this rank's blend waits (in-kernel, only in the CTAs that read a halo) for the NEIGHBOUR's push, not
+        # for this one -- the NVLink copy overlaps the blend of the interior rows; push_x_halos_and_wait joins the side
+        # stream before the step ends (the tile buffer is rewritten by the next step's denoiser)
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self._side.wait_event(fork)
+        with torch.cuda.stream(self._side):
+            self.flags_tiles.push(regions, sorted(targets), bump_own=False)
+            self._join = torch.cuda.Event()
+            self._join.record(self._side)
+
+    @staticmethod
+    def _aligned(regions) -> bool:
+        return all(v % 16 == 0 for r in regions for v in (r[0], r[1], r[4], r[5], r[6], r[7], r[8]))
 
     def band_pointer_table(self):
         """One pointer per tile row for td_blend_multidiffusion_rows: own band, halo slot, or (unused) my buffer."""
@@ -404,23 +463,33 @@ class StripExchange:
             check(lib.td_blend_multidiffusion_rows(ctypes.byref(g), self._ptr_table, sh.rows, sh.cols, self.N, self.C, _cabi.dtype_code(self.dtype),
                                                    _cabi.dtype_code(self.dtype), weights.data_ptr(),
                                                    rcp_weights.data_ptr() if rcp_weights is not None else None, self.x_out.data_ptr(), None,
-                                                   lo, hi, f if count else None, count, v if count else None, int(flags),
+                                                   lo, hi, f if count else None, count, v if count else None,
+                                                   sh.band_begin[sh.rank] if _LATE_WAIT else 0, sh.band_end[sh.rank] if _LATE_WAIT else 0, int(flags),
                                                    _cabi.current_stream_ptr(self.device)))
         return self.x_out
 
+    def join_side(self):
+        """The caller's stream waits for the side-stream tile-halo push of this step (no-op when there is none)."""
+        if self._join is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._join)
+            self._join = None
+
     def push_x_halos_and_wait(self):
-        """Rows of my strip that lower ranks scatter from -> their latent buffers; then wait for mine to arrive."""
+        """Rows of my strip that lower ranks scatter from -> their latent buffers; then wait for mine to arrive
+        (copy + signal + wait in one launch: td_push_regions)."""
         sh = self.shard
-        targets = set()
-        plane = sh.H * self.W
+        targets, regions = set(), []
+        plane = sh.H * self.W * 4
         for (p, a, b) in sh.x_out():
             off = a * self.W * 4
-            self._copy_rows(self._xout.ptr + off, self.peer_xout[p] + off, self.N * self.C, b - a, self.W, plane, self.W, plane, self.W, torch.float32)
+            regions.append((self._xout.ptr + off, self.peer_xout[p] + off, self.N * self.C, 1, (b - a) * self.W * 4, plane, plane, plane, plane))
             targets.add(p)
-        self.flags_x.signal(sorted(targets))
-        if self._x_senders:
-            first = self._x_senders[0]
-            self.flags_x.wait(first, self._x_senders[-1] - first + 1)
+        first = self._x_senders[0] if self._x_senders else 0
+        count = (self._x_senders[-1] - first + 1) if self._x_senders else 0
+        self.join_side()
+        if not self._aligned(regions):
+            raise ValueError("row-strip shard: latent width must be a multiple of 4 elements")
+        self.flags_x.push(regions, sorted(targets), first, count, bump_own=True, bump_next=self.flags_tiles.counter_ptr)
 
     def gather_latent(self, x: torch.Tensor) -> torch.Tensor:
         """All ranks' strips of `x` (any tensor laid out like the latent) -> the full latent on every rank."""

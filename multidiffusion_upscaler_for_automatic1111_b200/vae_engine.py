@@ -18,6 +18,8 @@ stop every tile at each GroupNorm, merge the tiles' statistics, continue -- is k
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -188,6 +190,9 @@ class ModuleBackend:
         copy_region(valid, result[:, :, out_bbox[2]:out_bbox[3], out_bbox[0]:out_bbox[1]])
 
 
+FOLD_UPSAMPLE = os.environ.get("TD_VAE_FOLD_UPSAMPLE", "1") != "0"     # 0: materialise the upsampled tensor (measurement only)
+
+
 class TensorCoreBackend:
     """Channels-last activations; convolutions and attention GEMMs on tcgen05, the rest on streaming kernels."""
     name = "tcgen05"
@@ -207,6 +212,14 @@ class TensorCoreBackend:
             if conv.bias is not None:
                 b[:co] = conv.bias.detach().float()
             self._w[key] = (wp, b, co, cout_rows, kh)
+        return self._w[key]
+
+    def _upconv_w(self, conv: torch.nn.Module):
+        """Folded taps of a 3x3 convolution behind a nearest-2x upsample (td_upconv2x_nhwc)."""
+        key = ("up2", id(conv))
+        if key not in self._w:
+            ci = conv.weight.shape[1]
+            self._w[key] = ops.fold_upsample_weight(conv.weight.to(self.device), self.dtype, cin_pad=ops.round_up(ci, 64))
         return self._w[key]
 
     def _affine(self, norm: torch.nn.Module):
@@ -248,6 +261,9 @@ class TensorCoreBackend:
     def conv(self, a, op: Conv, skip, post=None):
         wp, b, co, cout_rows, k = self._conv_w(op.module)
         if op.upsample_first:
+            if k == 3 and skip is None and cout_rows == co and FOLD_UPSAMPLE:
+                # ldm Upsample block: the four parity convolutions of the low-resolution tile, no 4x intermediate
+                return ops.upconv2x_nhwc(a, self._upconv_w(op.module), b, cout=cout_rows, post=post)
             a = ops.upsample2x_nhwc(a)
         _, H, W, _ = a.shape
         if op.downsample:

@@ -38,6 +38,56 @@ def pack_conv_weight(weight: torch.Tensor, dtype: torch.dtype, cin_pad: Optional
     return w.contiguous()
 
 
+def fold_upsample_weight(weight: torch.Tensor, dtype: torch.dtype, cin_pad: Optional[int] = None) -> torch.Tensor:
+    """3x3 taps of a convolution that follows a nearest-2x upsample, folded for td_upconv2x_nhwc: [Cout, Cin, 3, 3] ->
+    [16, Cout, Cin_p].  Output parity py reads low-resolution rows {i-1+py, i+py}; the hi-res rows 2i+py+ky-1 (ky = 0..2)
+    that land on the same low-resolution row share one folded tap (summed in fp32, rounded once):
+        py = 0: row i-1 <- ky 0        row i   <- ky 1 + ky 2
+        py = 1: row i   <- ky 0 + ky 1 row i+1 <- ky 2                    (columns alike)."""
+    co, ci, kh, kw = weight.shape
+    assert kh == 3 and kw == 3
+    cin_p = cin_pad or round_up(ci, 64)
+    w32 = weight.detach().float()
+    groups = (((0,), (1, 2)), ((0, 1), (2,)))        # [parity][tap] -> 3x3 indices summed
+    out = torch.zeros((16, co, cin_p), dtype=dtype, device=weight.device)
+    for py in range(2):
+        for px in range(2):
+            for ty in range(2):
+                for tx in range(2):
+                    acc = torch.zeros((co, ci), dtype=torch.float32, device=weight.device)
+                    for ky in groups[py][ty]:
+                        for kx in groups[px][tx]:
+                            acc += w32[:, :, ky, kx]
+                    out[(py * 2 + px) * 4 + ty * 2 + tx, :, :ci] = acc.to(dtype)
+    return out.contiguous()
+
+
+def upconv2x_nhwc(x: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tensor] = None, *, cout: Optional[int] = None,
+                  out: Optional[torch.Tensor] = None, post: Optional[Tuple[torch.Tensor, torch.Tensor, bool]] = None) -> torch.Tensor:
+    """Nearest-2x upsample + 3x3 / pad 1 convolution in one pass over the LOW-resolution x [N, H, W, Cin] ->
+    [N, 2H, 2W, Cout]; w16 from fold_upsample_weight."""
+    _cuda(x, "x"); _cuda(w16, "w16")
+    N, H, W, Cin = x.shape
+    taps, cout_rows, w_cin = w16.shape
+    assert taps == 16 and w_cin == Cin and x.is_contiguous() and w16.is_contiguous()
+    Cout = cout or cout_rows
+    if out is None:
+        out = torch.empty((N, 2 * H, 2 * W, Cout), dtype=x.dtype, device=x.device)
+    assert out.is_contiguous() and out.shape == (N, 2 * H, 2 * W, Cout)
+    d = TdConvDesc(N=N, H=H, W=W, Cin=Cin, Cout=Cout, kh=3, kw=3, stride=1, pad_top=1, pad_left=1, OH=2 * H, OW=2 * W,
+                   dtype=dtype_code(x.dtype), bias_per_row=0, alpha=1.0, x_pitch=x.stride(2), w_pitch=w16.stride(1), y_pitch=out.stride(2),
+                   res_pitch=0, post_scale=post[0].data_ptr() if post is not None else None,
+                   post_shift=post[1].data_ptr() if post is not None else None, post_act=int(bool(post[2])) if post is not None else 0)
+    if post is not None:
+        assert post[0].dtype == torch.float32 and post[1].dtype == torch.float32 and post[0].numel() >= Cout and post[1].numel() >= Cout
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_cuda
+    with torch.cuda.device(x.device):
+        check(lib.td_upconv2x_nhwc(ctypes.byref(d), x.data_ptr(), w16.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                   out.data_ptr(), current_stream_ptr(x.device)))
+    return out
+
+
 def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, ksize: int, stride: int = 1,
                 pad: Tuple[int, int] = (0, 0), out_hw: Optional[Tuple[int, int]] = None, residual: Optional[torch.Tensor] = None,
                 alpha: float = 1.0, cout: Optional[int] = None, out: Optional[torch.Tensor] = None,

@@ -212,3 +212,42 @@ def test_conv_with_fused_frozen_group_norm(ops, act):
     shift = (beta - mean.repeat_interleave(cpg) * scale).contiguous()
     got = ops.conv2d_nhwc(ops.nchw_to_nhwc(x, Cin), ops.pack_conv_weight(w, dtype), bias, ksize=3, pad=(1, 1), residual=res, post=(scale, shift, act))
     _check(got.permute(0, 3, 1, 2), want, dtype, f"conv + frozen GroupNorm act={act}")
+
+
+def _upconv_case(ops, dtype, N, H, W, Cin, Cout, seed):
+    x = _rand((N, Cin, H, W), dtype, seed, 0.7)
+    w = _rand((Cout, Cin, 3, 3), dtype, seed + 1, 1.0 / (Cin * 9) ** 0.5)
+    bias = _rand((Cout,), torch.float32, seed + 2, 0.3)
+    want = F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), w.float(), bias, padding=1)
+    got = ops.upconv2x_nhwc(ops.nchw_to_nhwc(x, Cin), ops.fold_upsample_weight(w, dtype), bias)
+    assert got.shape == (N, 2 * H, 2 * W, Cout)
+    # the folded taps are rounded to the activation dtype after the fp32 sum: one more rounding of the weights than the
+    # reference's own fp16 weights carry -- same order as the input rounding, inside the same bar
+    _check(got.permute(0, 3, 1, 2), want, dtype, f"upsample2x+conv {N}x{Cin}x{H}x{W}->{Cout}")
+    # and against the unfolded path on the same kernels (upsample kernel + 3x3 conv)
+    ref = ops.conv2d_nhwc(ops.upsample2x_nhwc(ops.nchw_to_nhwc(x, Cin)), ops.pack_conv_weight(w, dtype), bias, ksize=3, pad=(1, 1))
+    _check(got, ref.float(), dtype, "folded vs materialised upsample")
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 8, 64, 64), (1, 37, 45, 128, 128), (2, 19, 23, 256, 256), (1, 64, 9, 64, 512)])
+def test_upsample_folded_into_conv(ops, shape):
+    N, H, W, Cin, Cout = shape
+    _upconv_case(ops, torch.float16, N, H, W, Cin, Cout, 400 + H)
+
+
+def test_upsample_folded_into_conv_large_pair_and_bf16(ops):
+    _upconv_case(ops, torch.float16, 1, 236, 236, 512, 512, 431)     # the decoder's 236 -> 472 block: CTA pairs
+    _upconv_case(ops, torch.bfloat16, 1, 120, 130, 128, 128, 437)    # two sub-tiles per CTA
+
+
+def test_upsample_folded_with_fused_group_norm(ops):
+    dtype = torch.float16
+    N, H, W, Cin, Cout = 1, 21, 30, 128, 128
+    x = _rand((N, Cin, H, W), dtype, 450, 0.7)
+    w = _rand((Cout, Cin, 3, 3), dtype, 451, 1.0 / (Cin * 9) ** 0.5)
+    bias = _rand((Cout,), torch.float32, 452, 0.3)
+    scale, shift = _rand((Cout,), torch.float32, 453, 0.4) + 1.0, _rand((Cout,), torch.float32, 454, 0.2)
+    y = F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), w.float(), bias, padding=1)
+    want = F.silu(y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    got = ops.upconv2x_nhwc(ops.nchw_to_nhwc(x, Cin), ops.fold_upsample_weight(w, dtype), bias, post=(scale, shift, True))
+    _check(got.permute(0, 3, 1, 2), want, dtype, "upsample2x+conv + affine + SiLU")

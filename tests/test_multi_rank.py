@@ -299,8 +299,9 @@ def _gpu_worker(rank, world, port, result_dir):
                     d._exchange.close()
         # row-strip shard (default fused mode): each rank blends its own rows from own + halo tile rows; several steps
         for c in (CASE, CASE2, dict(CASE2, W=256, H=640, N=1)):
-            x = synth.latent(31, (c["N"], c["C"], c["H"], c["W"]), torch.float16)
-            plan, want = _oracle(c, x)
+            # a different latent every step: a halo left over from the previous step would not go unnoticed
+            xs = [synth.latent(31 + k, (c["N"], c["C"], c["H"], c["W"]), torch.float16) for k in range(3)]
+            wants = [_oracle(c, xk)[1] for xk in xs]
 
             def unet(x_tile, sigma, cond=None):
                 bbs = d.local_batched_bboxes[state["i"]]
@@ -319,6 +320,7 @@ def _gpu_worker(rank, world, port, result_dir):
             cond = {"c_crossattn": [torch.zeros(c["N"], 77, 8, device="cuda")], "c_concat": [torch.zeros(c["N"], 5, 1, 1, device="cuda")]}
             for step in range(3):
                 state["i"] = 0
+                x, want = xs[step], wants[step]
                 out = inner.forward(x.cuda(), torch.ones(c["N"], device="cuda"), cond=cond)
                 torch.cuda.synchronize()
                 sh = d._strip
