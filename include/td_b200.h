@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TD_ABI_VERSION 5
+#define TD_ABI_VERSION 6
 
 typedef enum td_status {
     TD_OK = 0,
@@ -364,6 +364,11 @@ typedef struct td_conv_desc {
     const float* post_scale;
     const float* post_shift;
     int32_t post_act;
+    /* optional second output (NULL: none): with y2 set, y receives the result BEFORE the post stage (what the next
+     * ResnetBlock adds back as its shortcut) and y2 [N, OH, OW, y2_pitch >= Cout] the result after it (that block's
+     * normalised + activated input): the GroupNorm pass over the activation disappears */
+    void* y2;
+    int64_t y2_pitch;
 } td_conv_desc;
 int td_conv2d_nhwc(const td_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
                    void* y, void* stream);

@@ -32,7 +32,7 @@ TD_MAX_GRID_DIM = 256
 TD_MAX_BATCH_PTRS = 128
 TD_MAX_PEERS = 16
 TD_IPC_HANDLE_BYTES = 64
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 DTYPE_CODE = {torch.float16: TD_F16, torch.bfloat16: TD_BF16, torch.float32: TD_F32}
 
@@ -83,6 +83,7 @@ class TdConvDesc(ctypes.Structure):
         ("alpha", c_float),
         ("x_pitch", c_int64), ("w_pitch", c_int64), ("y_pitch", c_int64), ("res_pitch", c_int64),
         ("post_scale", c_void_p), ("post_shift", c_void_p), ("post_act", c_int32),
+        ("y2", c_void_p), ("y2_pitch", c_int64),
     ]
 
 

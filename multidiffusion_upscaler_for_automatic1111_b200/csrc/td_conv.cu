@@ -73,6 +73,8 @@ struct ConvParams {
     int m_tiles;               // NI * tiles_y * tiles_x
     int m_groups;              // ceil(m_tiles / cluster)
     float alpha;
+    int dual;                  // 1: two outputs -- map_d receives the result BEFORE the post affine / activation (the residual source of
+                               // the next block), map_d2 the result after it (the next block's normalised input)
     int up2;                   // 1: nearest-2x upsample folded into the 3x3 convolution -- four 2x2 convolutions of the LOW-resolution
                                // image, one per output parity (py, px) = "image" index & 3; weights [16 taps, Cout, Cin]; the
                                // output map is 5-D {c, x, y, px, py} over the high-resolution tensor
@@ -245,11 +247,14 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int g, int
 template <bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_d, const __grid_constant__ ConvParams p,
+                 const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_d2,
+                 const __grid_constant__ CUtensorMap map_r, const __grid_constant__ ConvParams p,
                  const float* __restrict__ bias, const uint16_t* __restrict__ residual, const float* __restrict__ post_scale,
                  const float* __restrict__ post_shift) {
     extern __shared__ unsigned char conv_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kConvMaxStages], empty_bar[kConvMaxStages], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t res_bar[2];          // residual tile landed in the staging buffer (one per epilogue group)
+    __shared__ __align__(16) float cst[2][3][64];         // per epilogue group: bias / post scale / post shift of the current chunk
     __shared__ uint32_t tmem_base_slot;
     const uint32_t smem0 = (smem_u32(conv_smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
     const int stage_b = (p.pair ? p.BN / 2 : p.BN) * 128;                   // pair: half of the weight tile per CTA
@@ -265,10 +270,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_d);
+        if (p.dual) tma_prefetch_desc(&map_d2);
+        if (residual != nullptr) tma_prefetch_desc(&map_r);
         // a stage is free when the MMAs of EVERY CTA of the cluster have read it (peers multicast into it)
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.pair ? 1u : (uint32_t)p.cluster); }
         // pair: the leader's MMA thread waits for the epilogues of BOTH CTAs (the peer's threads arrive remotely)
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], p.pair ? 512u : 256u); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], p.pair ? 512u : 256u); mbar_init(&res_bar[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
@@ -374,7 +381,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int et = (threadIdx.x - 128) & 127;     // 0..127 inside the group
         const int bar_id = 1 + eg;
         const uint32_t sbuf = store0 + (uint32_t)eg * kConvStoreBuf;   // one staging buffer per group
+        const uint32_t sbuf2 = store0 + (uint32_t)(2 + eg) * kConvStoreBuf;   // ... and one more for the second output (dual)
         int as = 0; uint32_t aphase = 0;
+        uint32_t rphase = 0;                          // parity of this group's residual-load barrier
+        const bool has_res = residual != nullptr;
         for (int g = cid; g < num_groups; g += nclusters) {
             const TileCoord c = decode_tile(p, g, crank);
             mbar_wait(&acc_full[as], aphase);
@@ -399,14 +409,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 {
                     const int col0 = c.nb * p.BN + ch * p.chunk_cols;
                     const int ng = p.chunk_cols / 16;
-                    // residual row of this chunk (up to 128 bytes per thread): in flight before anything else waits
-                    const bool has_res = residual != nullptr && pix_ok;
-                    uint4 rres[8];
-                    if (has_res) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(residual + pix * p.res_pitch + col0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (j < 2 * ng && col0 + (j >> 1) * 16 + 16 <= p.Cout) rres[j] = __ldg(rp + j);
+                    const int sx = c.px * p.BW + mt * p.sub_dx, sy = c.py * p.BH + mt * p.sub_dy;
+                    // the group's staging buffer must have been read by its previous TMA store; then the residual tile of this
+                    // unit is fetched INTO it by TMA (same box, same swizzle as the output: every thread later reads and
+                    // overwrites only its own row) -- per-thread 128-byte global loads of a row-per-thread layout cost 32 L1
+                    // requests per instruction and were the longest stall of the residual epilogue
+                    if (et == 0) {
+                        bulk_wait_read<0>();
+                        if (has_res) {
+                            mbar_arrive_expect_tx(&res_bar[eg], (uint32_t)(kConvBM * p.chunk_cols * 2));
+                            tma_load_4d(sbuf, &map_r, col0, sx, sy, c.img, &res_bar[eg]);
+                        }
+                    }
+                    // per-channel constants of the chunk -> shared memory, once per unit instead of once per thread and group:
+                    // threads 0-15 bias, 16-31 post scale, 32-47 post shift (4 channels each; 0 / 1 / 0 where absent)
+                    if (et < 48 && (et & 15) * 4 < p.chunk_cols) {
+                        const int kind = et >> 4, c4 = (et & 15) * 4;
+                        const float* src = kind == 0 ? ((bias != nullptr && !p.bias_per_row) ? bias : nullptr) : (kind == 1 ? post_scale : post_shift);
+                        float4 val = kind == 1 ? make_float4(1.f, 1.f, 1.f, 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (src != nullptr) {
+                            const int cc = col0 + c4;
+                            if (cc + 4 <= p.Cout) val = __ldg(reinterpret_cast<const float4*>(src + cc));
+                            else {
+                                if (cc + 0 < p.Cout) val.x = __ldg(src + cc + 0);
+                                if (cc + 1 < p.Cout) val.y = __ldg(src + cc + 1);
+                                if (cc + 2 < p.Cout) val.z = __ldg(src + cc + 2);
+                            }
+                        }
+                        *reinterpret_cast<float4*>(&cst[eg][kind][c4]) = val;
                     }
                     // all TMEM loads of the chunk in flight before the single wait (up to 64 columns = 64 registers)
                     uint32_t racc[4][16];
@@ -415,9 +445,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     tc_ld16(tcol, racc[0]);
                     if (ng > 1) tc_ld16(tcol + 16u, racc[1]);
                     if (ng > 2) { tc_ld16(tcol + 32u, racc[2]); tc_ld16(tcol + 48u, racc[3]); }
-                    // the group's staging buffer must have been read by its previous TMA store
-                    if (et == 0) bulk_wait_read<0>();
-                    named_bar_sync(bar_id, 128);
+                    named_bar_sync(bar_id, 128);          // constants visible; staging buffer known free
+                    if (has_res) { mbar_wait(&res_bar[eg], rphase); rphase ^= 1u; }
                     tc_wait_ld();
 #pragma unroll
                     for (int g16 = 0; g16 < 4; ++g16) {
@@ -425,44 +454,53 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         const uint32_t (&r)[16] = racc[g16];
                         float v[16];
                         const int cb = col0 + g16 * 16;
-                        if (bias != nullptr && !p.bias_per_row && cb + 16 <= p.Cout) {      // 16 bias values: four 128-bit loads
-                            const float4* bp4 = reinterpret_cast<const float4*>(bias + cb);
+                        // shared-memory addresses of this thread's two 16-byte pieces of the group (output staging layout)
+                        uint32_t a0, a1;
+                        if (p.chunk_cols == 64) {      // 128-byte rows, 128-byte swizzle: chunk index XOR (row & 7)
+                            a0 = (uint32_t)row * 128u + ((uint32_t)((2 * g16) ^ (row & 7)) << 4);
+                            a1 = (uint32_t)row * 128u + ((uint32_t)((2 * g16 + 1) ^ (row & 7)) << 4);
+                        } else {                       // narrow outputs: dense rows of chunk_cols * 2 bytes, no swizzle
+                            a0 = (uint32_t)row * (uint32_t)(p.chunk_cols * 2) + (uint32_t)g16 * 32u;
+                            a1 = a0 + 16u;
+                        }
+                        if (p.bias_per_row) {
+                            const float bb = (bias != nullptr && pix_ok) ? __ldg(bias + pix) : 0.0f;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = __fmaf_rn(__uint_as_float(r[j]), p.alpha, bb);
+                        } else {
 #pragma unroll
                             for (int j4 = 0; j4 < 4; ++j4) {
-                                const float4 b4 = __ldg(bp4 + j4);
+                                const float4 b4 = *reinterpret_cast<const float4*>(&cst[eg][0][g16 * 16 + 4 * j4]);
                                 v[4 * j4 + 0] = __fmaf_rn(__uint_as_float(r[4 * j4 + 0]), p.alpha, b4.x);
                                 v[4 * j4 + 1] = __fmaf_rn(__uint_as_float(r[4 * j4 + 1]), p.alpha, b4.y);
                                 v[4 * j4 + 2] = __fmaf_rn(__uint_as_float(r[4 * j4 + 2]), p.alpha, b4.z);
                                 v[4 * j4 + 3] = __fmaf_rn(__uint_as_float(r[4 * j4 + 3]), p.alpha, b4.w);
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                float b = 0.0f;
-                                if (bias != nullptr) {
-                                    if (p.bias_per_row) b = pix_ok ? __ldg(bias + pix) : 0.0f;
-                                    else b = (cb + j < p.Cout) ? __ldg(bias + cb + j) : 0.0f;
-                                }
-                                v[j] = __fmaf_rn(__uint_as_float(r[j]), p.alpha, b);
-                            }
                         }
-                        if (has_res && cb + 16 <= p.Cout) {
-                            const uint4 r0 = rres[2 * g16], r1 = rres[2 * g16 + 1];
-                            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                        if (has_res) {
+                            uint32_t rw[8];
+                            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(sbuf + a0) : "memory");
+                            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7]) : "r"(sbuf + a1) : "memory");
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 v[2 * j] += unpack_lo(rw[j], p.is_bf16);
                                 v[2 * j + 1] += unpack_hi(rw[j], p.is_bf16);
                             }
                         }
-                        if (post_scale != nullptr && cb + 16 <= p.Cout) {
+                        if (p.dual) {   // the unnormalised result goes out as well (next block's shortcut / residual source)
+                            uint32_t o1[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o1[j] = pack2(v[2 * j], v[2 * j + 1], p.is_bf16);
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sbuf + a0), "r"(o1[0]), "r"(o1[1]), "r"(o1[2]), "r"(o1[3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sbuf + a1), "r"(o1[4]), "r"(o1[5]), "r"(o1[6]), "r"(o1[7]) : "memory");
+                        }
+                        if (post_scale != nullptr) {
                             // the GroupNorm (+ SiLU) that follows this convolution, statistics frozen (fast mode):
                             // y = act(v * scale[c] + shift[c]) on the fp32 accumulator, before the one rounding to fp16
-                            const float4* sc4 = reinterpret_cast<const float4*>(post_scale + cb);
-                            const float4* sh4 = reinterpret_cast<const float4*>(post_shift + cb);
 #pragma unroll
                             for (int j4 = 0; j4 < 4; ++j4) {
-                                const float4 sc = __ldg(sc4 + j4), sh = __ldg(sh4 + j4);
+                                const float4 sc = *reinterpret_cast<const float4*>(&cst[eg][1][g16 * 16 + 4 * j4]);
+                                const float4 sh = *reinterpret_cast<const float4*>(&cst[eg][2][g16 * 16 + 4 * j4]);
                                 v[4 * j4 + 0] = __fmaf_rn(v[4 * j4 + 0], sc.x, sh.x);
                                 v[4 * j4 + 1] = __fmaf_rn(v[4 * j4 + 1], sc.y, sh.y);
                                 v[4 * j4 + 2] = __fmaf_rn(v[4 * j4 + 2], sc.z, sh.z);
@@ -476,17 +514,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         uint32_t o[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) o[j] = pack2(v[2 * j], v[2 * j + 1], p.is_bf16);
-                        // 16 columns = two 16-byte chunks (2 g16, 2 g16 + 1) of this row
-                        if (p.chunk_cols == 64) {      // 128-byte rows, 128-byte swizzle: chunk index XOR (row & 7)
-                            const uint32_t rb = sbuf + (uint32_t)row * 128u;
-                            const uint32_t c0 = (uint32_t)((2 * g16) ^ (row & 7)) << 4, c1 = (uint32_t)((2 * g16 + 1) ^ (row & 7)) << 4;
-                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb + c0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb + c1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
-                        } else {                       // narrow outputs: dense rows of chunk_cols * 2 bytes, no swizzle
-                            const uint32_t rb = sbuf + (uint32_t)row * (uint32_t)(p.chunk_cols * 2) + (uint32_t)g16 * 32u;
-                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rb + 16u), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
-                        }
+                        const uint32_t sdst = p.dual ? sbuf2 : sbuf;
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sdst + a0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sdst + a1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
                     }
                     if (u == last_u) {   // this group's TMEM reads of the accumulator stage are done: hand it back
                         tc_fence_before();
@@ -497,8 +527,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     named_bar_sync(bar_id, 128);
                     if (et == 0) {
                         if (c.img < p.NI) {
-                            if (p.up2) tma_store_5d(&map_d, col0, c.px * p.BW + mt * p.sub_dx, c.py * p.BH + mt * p.sub_dy, c.img & 1, c.img >> 1, sbuf);
-                            else tma_store_4d(&map_d, col0, c.px * p.BW + mt * p.sub_dx, c.py * p.BH + mt * p.sub_dy, c.img, sbuf);
+                            if (p.up2) tma_store_5d(&map_d, col0, sx, sy, c.img & 1, c.img >> 1, sbuf);
+                            else tma_store_4d(&map_d, col0, sx, sy, c.img, sbuf);
+                            if (p.dual) {
+                                if (p.up2) tma_store_5d(&map_d2, col0, sx, sy, c.img & 1, c.img >> 1, sbuf2);
+                                else tma_store_4d(&map_d2, col0, sx, sy, c.img, sbuf2);
+                            }
                         }
                         bulk_commit();
                     }
@@ -587,7 +621,8 @@ ConvDev conv_dev() {
 
 namespace {
 // up2 = 1: `d` describes nearest-2x upsample + 3x3 / pad 1 (OH = 2 H, OW = 2 W) of ONE image; `w` holds the 16 folded taps.
-int conv_run(const td_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y, void* stream, int up2) {
+int conv_run(const td_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y, void* stream, int up2,
+             size_t y2_off = 0) {
     if (d == nullptr || x == nullptr || w == nullptr || y == nullptr) { td_set_error("td_conv2d_nhwc: null argument"); return TD_ERR_INVALID_ARG; }
     if (d->dtype != TD_F16 && d->dtype != TD_BF16) { td_set_error("td_conv2d_nhwc: dtype must be fp16 or bf16"); return TD_ERR_UNSUPPORTED; }
     if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->OH <= 0 || d->OW <= 0 || d->Cin <= 0 || d->Cout <= 0) { td_set_error("td_conv2d_nhwc: non-positive size"); return TD_ERR_INVALID_ARG; }
@@ -605,8 +640,8 @@ int conv_run(const td_conv_desc* d, const void* x, const void* w, const float* b
         td_set_error("td_conv2d_nhwc: pitches must cover the channels and be multiples of 8 elements (16 bytes)");
         return TD_ERR_INVALID_ARG;
     }
-    for (const void* ptr : {x, w, (const void*)y, residual})
-        if (ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15u) != 0) { td_set_error("td_conv2d_nhwc: tensors must be 16-byte aligned"); return TD_ERR_INVALID_ARG; }
+    for (const void* ptr : {x, w, (const void*)y, residual, (const void*)(d->bias_per_row ? nullptr : bias), (const void*)d->post_scale, (const void*)d->post_shift})
+        if (ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15u) != 0) { td_set_error("td_conv2d_nhwc: tensors (and per-channel vectors) must be 16-byte aligned"); return TD_ERR_INVALID_ARG; }
     const ConvDev dev = conv_dev();
     if (!dev.ok) { td_set_error("td_conv2d_nhwc: device query / shared-memory opt-in failed"); return TD_ERR_CUDA; }
 
@@ -670,13 +705,19 @@ int conv_run(const td_conv_desc* d, const void* x, const void* w, const float* b
     if ((d->post_scale == nullptr) != (d->post_shift == nullptr)) { td_set_error("td_conv2d_nhwc: post_scale and post_shift come together"); return TD_ERR_INVALID_ARG; }
     p.alpha = d->alpha;
     p.res_pitch = residual != nullptr ? d->res_pitch : 0;
+    p.dual = d->y2 != nullptr ? 1 : 0;
+    if (p.dual && (d->post_scale == nullptr || d->y2_pitch < d->Cout || d->y2_pitch % 8 != 0 || (reinterpret_cast<uintptr_t>(d->y2) & 15u) != 0)) {
+        td_set_error("td_conv2d_nhwc: y2 needs post_scale / post_shift, a 16-byte aligned pointer and a pitch >= Cout in multiples of 8");
+        return TD_ERR_INVALID_ARG;
+    }
+    const int n_store_bufs = p.dual ? 4 : 2;
     const int stage_bytes = p.MT * kConvStageA + (p.pair ? bn / 2 : bn) * 128;
-    const int avail = dev.smem_optin - 1024 - 2 * kConvStoreBuf;
+    const int avail = dev.smem_optin - 1024 - n_store_bufs * kConvStoreBuf;
     p.stages = std::min(kConvMaxStages, avail / stage_bytes);
     if (p.stages < 2) { td_set_error("td_conv2d_nhwc: not enough shared memory"); return TD_ERR_UNSUPPORTED; }
-    const size_t smem = (size_t)p.stages * stage_bytes + 2 * kConvStoreBuf + 1024;
+    const size_t smem = (size_t)p.stages * stage_bytes + n_store_bufs * kConvStoreBuf + 1024;
 
-    alignas(64) CUtensorMap ma, mb, md;
+    alignas(64) CUtensorMap ma, mb, md, md2;
     {
         const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
         const uint64_t str[3] = {(uint64_t)d->x_pitch * 2, (uint64_t)d->W * d->x_pitch * 2, (uint64_t)d->H * d->W * d->x_pitch * 2};
@@ -694,21 +735,36 @@ int conv_run(const td_conv_desc* d, const void* x, const void* w, const float* b
         const int rc = encode_map(&mb, w, p.is_bf16, 3, dims, str, box, es, true, "weights");
         if (rc != TD_OK) return rc;
     }
-    if (up2) {
-        // y[2 i + py, 2 j + px, c] as {c, j, i, px, py}: the tile of one parity lands on every second pixel of every second row
-        const uint64_t row = (uint64_t)d->OW * d->y_pitch * 2;
-        const uint64_t dims[5] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, 2, 2};
-        const uint64_t str[4] = {(uint64_t)d->y_pitch * 4, row * 2, (uint64_t)d->y_pitch * 2, row};
-        const uint32_t box[5] = {(uint32_t)p.chunk_cols, (uint32_t)p.BWs, (uint32_t)p.BHs, 1, 1};
-        const uint32_t es[5] = {1, 1, 1, 1, 1};
-        const int rc = encode_map(&md, y, p.is_bf16, 5, dims, str, box, es, p.chunk_cols == 64, "output (parity view)");
-        if (rc != TD_OK) return rc;
-    } else {
+    for (int which = 0; which < (p.dual ? 2 : 1); ++which) {
+        CUtensorMap* mo = which == 0 ? &md : &md2;
+        void* yo = which == 0 ? y : (up2 && d->y2 != nullptr ? (void*)((uint16_t*)d->y2 + y2_off) : d->y2);
+        const uint64_t pitch = (uint64_t)(which == 0 ? d->y_pitch : d->y2_pitch);
+        if (up2) {
+            // y[2 i + py, 2 j + px, c] as {c, j, i, px, py}: the tile of one parity lands on every second pixel of every second row
+            const uint64_t row = (uint64_t)d->OW * pitch * 2;
+            const uint64_t dims[5] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, 2, 2};
+            const uint64_t str[4] = {pitch * 4, row * 2, pitch * 2, row};
+            const uint32_t box[5] = {(uint32_t)p.chunk_cols, (uint32_t)p.BWs, (uint32_t)p.BHs, 1, 1};
+            const uint32_t es[5] = {1, 1, 1, 1, 1};
+            const int rc = encode_map(mo, yo, p.is_bf16, 5, dims, str, box, es, p.chunk_cols == 64, "output (parity view)");
+            if (rc != TD_OK) return rc;
+        } else {
+            const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->OW, (uint64_t)d->OH, (uint64_t)d->N};
+            const uint64_t str[3] = {pitch * 2, (uint64_t)d->OW * pitch * 2, (uint64_t)d->OH * d->OW * pitch * 2};
+            const uint32_t box[4] = {(uint32_t)p.chunk_cols, (uint32_t)p.BWs, (uint32_t)p.BHs, 1};
+            const uint32_t es[4] = {1, 1, 1, 1};
+            const int rc = encode_map(mo, yo, p.is_bf16, 4, dims, str, box, es, p.chunk_cols == 64, "output");
+            if (rc != TD_OK) return rc;
+        }
+    }
+    if (!p.dual) md2 = md;
+    alignas(64) CUtensorMap mr = md;
+    if (residual != nullptr) {   // the residual tile is fetched with the output's own box (zero fill outside the tensor)
         const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->OW, (uint64_t)d->OH, (uint64_t)d->N};
-        const uint64_t str[3] = {(uint64_t)d->y_pitch * 2, (uint64_t)d->OW * d->y_pitch * 2, (uint64_t)d->OH * d->OW * d->y_pitch * 2};
+        const uint64_t str[3] = {(uint64_t)d->res_pitch * 2, (uint64_t)d->OW * d->res_pitch * 2, (uint64_t)d->OH * d->OW * d->res_pitch * 2};
         const uint32_t box[4] = {(uint32_t)p.chunk_cols, (uint32_t)p.BWs, (uint32_t)p.BHs, 1};
         const uint32_t es[4] = {1, 1, 1, 1};
-        const int rc = encode_map(&md, y, p.is_bf16, 4, dims, str, box, es, p.chunk_cols == 64, "output");
+        const int rc = encode_map(&mr, residual, p.is_bf16, 4, dims, str, box, es, p.chunk_cols == 64, "residual");
         if (rc != TD_OK) return rc;
     }
     const int grid = std::max(cl, std::min(p.num_tiles * cl, dev.sms) / cl * cl);
@@ -725,8 +781,8 @@ int conv_run(const td_conv_desc* d, const void* x, const void* w, const float* b
     cfg.attrs = &attr;
     cfg.numAttrs = cl > 1 ? 1 : 0;
     const cudaError_t le = p.pair
-        ? cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, ma, mb, md, p, bias, (const uint16_t*)residual, d->post_scale, d->post_shift)
-        : cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false>, ma, mb, md, p, bias, (const uint16_t*)residual, d->post_scale, d->post_shift);
+        ? cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, ma, mb, md, md2, mr, p, bias, (const uint16_t*)residual, d->post_scale, d->post_shift)
+        : cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false>, ma, mb, md, md2, mr, p, bias, (const uint16_t*)residual, d->post_scale, d->post_shift);
     if (le != cudaSuccess) { td_set_error("td_conv2d_nhwc: launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return TD_ERR_CUDA; }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { td_set_error("td_conv2d_nhwc: launch failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
@@ -746,7 +802,7 @@ extern "C" int td_upconv2x_nhwc(const td_conv_desc* d, const void* x, const void
     for (int n = 0; n < d->N; ++n) {
         const uint16_t* xn = static_cast<const uint16_t*>(x) + (size_t)n * d->H * d->W * d->x_pitch;
         uint16_t* yn = static_cast<uint16_t*>(y) + (size_t)n * d->OH * d->OW * d->y_pitch;
-        const int rc = conv_run(&one, xn, w16, bias, nullptr, yn, stream, 1);
+        const int rc = conv_run(&one, xn, w16, bias, nullptr, yn, stream, 1, (size_t)n * d->OH * d->OW * (size_t)d->y2_pitch);
         if (rc != TD_OK) return rc;
     }
     return TD_OK;

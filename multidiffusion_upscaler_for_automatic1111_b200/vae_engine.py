@@ -191,6 +191,7 @@ class ModuleBackend:
 
 
 FOLD_UPSAMPLE = os.environ.get("TD_VAE_FOLD_UPSAMPLE", "1") != "0"     # 0: materialise the upsampled tensor (measurement only)
+DUAL_OUTPUT = os.environ.get("TD_VAE_DUAL_OUTPUT", "1") != "0"         # 0: separate GroupNorm pass at block boundaries (measurement only)
 
 
 class TensorCoreBackend:
@@ -258,18 +259,19 @@ class TensorCoreBackend:
 
     fuses_norm = True      # conv(..., post=...) applies a following frozen GroupNorm (+ SiLU) in the epilogue
 
-    def conv(self, a, op: Conv, skip, post=None):
+    def conv(self, a, op: Conv, skip, post=None, dual=False):
+        """post: the frozen GroupNorm (+ SiLU) that follows, applied in the epilogue; dual: return (raw, normalised)."""
         wp, b, co, cout_rows, k = self._conv_w(op.module)
         if op.upsample_first:
             if k == 3 and skip is None and cout_rows == co and FOLD_UPSAMPLE:
                 # ldm Upsample block: the four parity convolutions of the low-resolution tile, no 4x intermediate
-                return ops.upconv2x_nhwc(a, self._upconv_w(op.module), b, cout=cout_rows, post=post)
+                return ops.upconv2x_nhwc(a, self._upconv_w(op.module), b, cout=cout_rows, post=post, dual=dual)
             a = ops.upsample2x_nhwc(a)
         _, H, W, _ = a.shape
         if op.downsample:
             oh, ow = (H + 1 - 3) // 2 + 1, (W + 1 - 3) // 2 + 1
-            return ops.conv2d_nhwc(a, wp, b, ksize=3, stride=2, pad=(0, 0), out_hw=(oh, ow), residual=skip, cout=cout_rows, post=post)
-        return ops.conv2d_nhwc(a, wp, b, ksize=k, pad=(k // 2, k // 2), residual=skip, cout=cout_rows, post=post)
+            return ops.conv2d_nhwc(a, wp, b, ksize=3, stride=2, pad=(0, 0), out_hw=(oh, ow), residual=skip, cout=cout_rows, post=post, dual=dual)
+        return ops.conv2d_nhwc(a, wp, b, ksize=k, pad=(k // 2, k // 2), residual=skip, cout=cout_rows, post=post, dual=dual)
 
     def norm_affine(self, op: Norm, mean, var):
         """Per-channel (scale, shift, act) equivalent to custom_group_norm (+ SiLU) with these statistics:
@@ -297,7 +299,7 @@ class TensorCoreBackend:
         gamma, beta = self._affine(op.module)
         return ops.gn_apply_nhwc(a, mean, var, gamma, beta, op.act, NUM_GROUPS, GN_EPS)
 
-    def attention(self, a, op: Attention, skip):
+    def attention(self, a, op: Attention, skip, post=None, dual=False):
         """softmax(q k^T / sqrt(C)) v + proj_out (tile_utils/attn.py:49-72) as four tensor-core GEMMs and one row
         softmax; the [tokens, tokens] score matrix lives in HBM (388 MB fp16 for a 118 x 118 tile: nothing on 180 GB)."""
         m = op.module
@@ -320,8 +322,7 @@ class TensorCoreBackend:
         ops.softmax_rows(s, T, out=s)
         o = ops.gemm_nt(s, vt)         # K = Tp (a multiple of 8; the last partial 64-chunk is zero-filled by the TMA unit)
         wp, bp, *_ = self._conv_w(m.proj_out)
-        y = ops.conv2d_nhwc(o.view(1, H, W, C), wp, bp, ksize=1, residual=skip)
-        return y
+        return ops.conv2d_nhwc(o.view(1, H, W, C), wp, bp, ksize=1, residual=skip, post=post, dual=dual)
 
     def tanh(self, a):
         return torch.tanh(a)
@@ -393,6 +394,20 @@ class Executor:
                 if fz is None:
                     return op
                 st.act = self.be.norm(st.act, op, fz[0], fz[1])
+            elif fuse and DUAL_OUTPUT and isinstance(op, (Conv, Attention)) and st.pc + 2 < end and isinstance(opsq[st.pc + 1], Skip) \
+                    and isinstance(opsq[st.pc + 2], Norm) and self.frozen[opsq[st.pc + 2].site] is not None \
+                    and self._dual_ok(op, opsq[st.pc + 2]):
+                # producer -> [shortcut source] -> GroupNorm (+ SiLU) with frozen statistics (the boundary between two
+                # ResnetBlocks / attention): the producer writes BOTH tensors -- the raw one feeds the shortcut, the
+                # normalised one is the next block's input; no pass over the activation in between
+                skp, nxt = opsq[st.pc + 1], opsq[st.pc + 2]
+                if nxt.site not in self._affine_cache:
+                    self._affine_cache[nxt.site] = self.be.norm_affine(nxt, *self.frozen[nxt.site])
+                fn = self.be.conv if isinstance(op, Conv) else self.be.attention
+                raw, normed = fn(st.act, op, st.skip if op.add_skip else None, post=self._affine_cache[nxt.site], dual=True)
+                st.skip = self.be.shortcut(raw, skp)
+                st.act = normed
+                st.pc += 2
             elif fuse and isinstance(op, Conv) and st.pc + 1 < end and isinstance(opsq[st.pc + 1], Norm) \
                     and self.frozen[opsq[st.pc + 1].site] is not None:
                 # conv -> GroupNorm (+ SiLU) with frozen statistics: the norm rides in the conv's epilogue (the raw conv
@@ -408,6 +423,12 @@ class Executor:
                 self._step(st, op)
             st.pc += 1
         return None
+
+    @staticmethod
+    def _dual_ok(op, norm: Norm) -> bool:
+        """The kernel's post stage runs on whole 16-channel groups of real output channels."""
+        m = op.module if isinstance(op, Conv) else op.module.proj_out
+        return m.out_channels % 16 == 0 and m.out_channels == norm.module.num_channels
 
     def apply_barrier(self, st: TileState, op: Norm, mean, var) -> None:
         st.act = self.be.norm(st.act, op, mean, var)

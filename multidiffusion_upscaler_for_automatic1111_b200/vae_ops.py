@@ -63,9 +63,9 @@ def fold_upsample_weight(weight: torch.Tensor, dtype: torch.dtype, cin_pad: Opti
 
 
 def upconv2x_nhwc(x: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tensor] = None, *, cout: Optional[int] = None,
-                  out: Optional[torch.Tensor] = None, post: Optional[Tuple[torch.Tensor, torch.Tensor, bool]] = None) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, post: Optional[Tuple[torch.Tensor, torch.Tensor, bool]] = None, dual: bool = False):
     """Nearest-2x upsample + 3x3 / pad 1 convolution in one pass over the LOW-resolution x [N, H, W, Cin] ->
-    [N, 2H, 2W, Cout]; w16 from fold_upsample_weight."""
+    [N, 2H, 2W, Cout]; w16 from fold_upsample_weight.  dual (needs post): returns (result before post, result after post)."""
     _cuda(x, "x"); _cuda(w16, "w16")
     N, H, W, Cin = x.shape
     taps, cout_rows, w_cin = w16.shape
@@ -78,6 +78,11 @@ def upconv2x_nhwc(x: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tenso
                    dtype=dtype_code(x.dtype), bias_per_row=0, alpha=1.0, x_pitch=x.stride(2), w_pitch=w16.stride(1), y_pitch=out.stride(2),
                    res_pitch=0, post_scale=post[0].data_ptr() if post is not None else None,
                    post_shift=post[1].data_ptr() if post is not None else None, post_act=int(bool(post[2])) if post is not None else 0)
+    out2 = None
+    if dual:
+        assert post is not None, "the second output is the post stage's result"
+        out2 = torch.empty_like(out)
+        d.y2, d.y2_pitch = out2.data_ptr(), out2.stride(2)
     if post is not None:
         assert post[0].dtype == torch.float32 and post[1].dtype == torch.float32 and post[0].numel() >= Cout and post[1].numel() >= Cout
     if bias is not None:
@@ -85,16 +90,18 @@ def upconv2x_nhwc(x: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tenso
     with torch.cuda.device(x.device):
         check(lib.td_upconv2x_nhwc(ctypes.byref(d), x.data_ptr(), w16.data_ptr(), bias.data_ptr() if bias is not None else None,
                                    out.data_ptr(), current_stream_ptr(x.device)))
-    return out
+    return (out, out2) if dual else out
 
 
 def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, ksize: int, stride: int = 1,
                 pad: Tuple[int, int] = (0, 0), out_hw: Optional[Tuple[int, int]] = None, residual: Optional[torch.Tensor] = None,
                 alpha: float = 1.0, cout: Optional[int] = None, out: Optional[torch.Tensor] = None,
-                bias_per_row: bool = False, post: Optional[Tuple[torch.Tensor, torch.Tensor, bool]] = None) -> torch.Tensor:
+                bias_per_row: bool = False, post: Optional[Tuple[torch.Tensor, torch.Tensor, bool]] = None, dual: bool = False):
     """One convolution on the tensor cores.  x: [N, H, W, Cin] NHWC; w: packed [ksize*ksize, Cout_rows, Cin];
     bias: fp32 [Cout] (or [N*OH*OW] with bias_per_row); residual: [N, OH, OW, Cout] added in the epilogue.
-    pad = (top, left) zero padding; out_hw defaults to the 'same' size for stride 1."""
+    pad = (top, left) zero padding; out_hw defaults to the 'same' size for stride 1.
+    post = (scale, shift, silu): per-channel affine (+ SiLU) on the fp32 result; dual (needs post): two outputs, returns
+    (result before post, result after post)."""
     _cuda(x, "x"); _cuda(w, "w")
     N, H, W, Cin = x.shape
     taps, cout_rows, w_cin = w.shape
@@ -110,6 +117,11 @@ def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] =
                    post_scale=post[0].data_ptr() if post is not None else None, post_shift=post[1].data_ptr() if post is not None else None,
                    post_act=int(bool(post[2])) if post is not None else 0)
     assert x.stride(3) == 1 and out.stride(3) == 1 and w.stride(2) == 1
+    out2 = None
+    if dual:
+        assert post is not None, "the second output is the post stage's result"
+        out2 = torch.empty_like(out)
+        d.y2, d.y2_pitch = out2.data_ptr(), out2.stride(2)
     if post is not None:
         assert post[0].dtype == torch.float32 and post[1].dtype == torch.float32 and post[0].numel() >= Cout and post[1].numel() >= Cout
     if bias is not None:
@@ -117,7 +129,7 @@ def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] =
     with torch.cuda.device(x.device):
         check(lib.td_conv2d_nhwc(ctypes.byref(d), x.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
                                  residual.data_ptr() if residual is not None else None, out.data_ptr(), current_stream_ptr(x.device)))
-    return out
+    return (out, out2) if dual else out
 
 
 def gemm_nt(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, alpha: float = 1.0, n: Optional[int] = None,

@@ -48,7 +48,9 @@ def main():
     def conv_label(a, k, out):
         x = a[0]
         kind = "upconv" if "w16" in k or (len(a) > 1 and a[1].shape[0] == 16) else "conv"
-        return f"{kind} {tuple(x.shape[1:3])} {x.shape[3]}->{out.shape[3]} k{k.get('ksize', 3)}{' +gn' if k.get('post') else ''}{' +res' if k.get('residual') is not None else ''}"
+        o = out[0] if isinstance(out, tuple) else out
+        return (f"{kind} {tuple(x.shape[1:3])} {x.shape[3]}->{o.shape[3]} k{k.get('ksize', 3)}{' +gn' if k.get('post') else ''}"
+                f"{' +res' if k.get('residual') is not None else ''}{' dual' if k.get('dual') else ''}")
     wrap(vae_ops, "conv2d_nhwc", conv_label)
     wrap(vae_ops, "upconv2x_nhwc", conv_label)
     wrap(vae_ops, "upsample2x_nhwc", lambda a, k, o: f"upsample {tuple(a[0].shape[1:])}")

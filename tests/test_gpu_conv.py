@@ -251,3 +251,42 @@ def test_upsample_folded_with_fused_group_norm(ops):
     want = F.silu(y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
     got = ops.upconv2x_nhwc(ops.nchw_to_nhwc(x, Cin), ops.fold_upsample_weight(w, dtype), bias, post=(scale, shift, True))
     _check(got.permute(0, 3, 1, 2), want, dtype, "upsample2x+conv + affine + SiLU")
+
+
+@pytest.mark.parametrize("shape", [(1, 37, 45, 128, 128, False), (1, 130, 140, 128, 256, True), (2, 16, 24, 256, 64, True)])
+def test_conv_two_outputs_raw_and_normalised(ops, shape):
+    """One launch, two tensors: the result before the frozen-GroupNorm stage (next block's shortcut source) and after it."""
+    dtype = torch.float16
+    N, H, W, Cin, Cout, with_res = shape
+    x = _rand((N, Cin, H, W), dtype, 500, 0.7)
+    w = _rand((Cout, Cin, 3, 3), dtype, 501, 1.0 / (Cin * 9) ** 0.5)
+    bias = _rand((Cout,), torch.float32, 502, 0.3)
+    res = _rand((N, H, W, Cout), dtype, 503, 0.5) if with_res else None
+    scale, shift = _rand((Cout,), torch.float32, 504, 0.4) + 1.0, _rand((Cout,), torch.float32, 505, 0.2)
+    y = F.conv2d(x.float(), w.float(), bias, padding=1)
+    if with_res:
+        y = y + res.float().permute(0, 3, 1, 2)
+    z = F.silu(y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    raw, normed = ops.conv2d_nhwc(ops.nchw_to_nhwc(x, Cin), ops.pack_conv_weight(w, dtype), bias, ksize=3, pad=(1, 1), residual=res,
+                                  post=(scale, shift, True), dual=True)
+    _check(raw.permute(0, 3, 1, 2), y, dtype, "raw output")
+    _check(normed.permute(0, 3, 1, 2), z, dtype, "normalised output")
+    # and the single-output forms give the same bits
+    only_raw = ops.conv2d_nhwc(ops.nchw_to_nhwc(x, Cin), ops.pack_conv_weight(w, dtype), bias, ksize=3, pad=(1, 1), residual=res)
+    only_post = ops.conv2d_nhwc(ops.nchw_to_nhwc(x, Cin), ops.pack_conv_weight(w, dtype), bias, ksize=3, pad=(1, 1), residual=res,
+                                post=(scale, shift, True))
+    assert torch.equal(raw, only_raw) and torch.equal(normed, only_post)
+
+
+def test_upsample_folded_two_outputs(ops):
+    dtype = torch.float16
+    N, H, W, Cin, Cout = 1, 59, 61, 256, 256
+    x = _rand((N, Cin, H, W), dtype, 520, 0.7)
+    w = _rand((Cout, Cin, 3, 3), dtype, 521, 1.0 / (Cin * 9) ** 0.5)
+    bias = _rand((Cout,), torch.float32, 522, 0.3)
+    scale, shift = _rand((Cout,), torch.float32, 523, 0.4) + 1.0, _rand((Cout,), torch.float32, 524, 0.2)
+    y = F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), w.float(), bias, padding=1)
+    z = F.silu(y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    raw, normed = ops.upconv2x_nhwc(ops.nchw_to_nhwc(x, Cin), ops.fold_upsample_weight(w, dtype), bias, post=(scale, shift, True), dual=True)
+    _check(raw.permute(0, 3, 1, 2), y, dtype, "raw output")
+    _check(normed.permute(0, 3, 1, 2), z, dtype, "normalised output")
