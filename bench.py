@@ -1064,8 +1064,13 @@ def vae_cpu_baseline(budget_s: float):
     if budget_s <= 1.0:      # measurement runs that only want the GPU numbers
         return {"value": None, "unit": "MP/s", "cores": 0, "kind": "port", "seconds": 0.0, "sample": "skipped (--cpu-budget <= 1)"}
     from oracle import ldm_vae, vae
-    torch.set_num_threads(os.cpu_count() or 1)
     net = ldm_vae.seeded_init(ldm_vae.Decoder(), 1).eval()
+    zp = torch.randn((1, 4, 24, 24), generator=torch.Generator().manual_seed(8))
+
+    def probe():      # one small untiled decode: which thread count suits this host's convolutions
+        with torch.no_grad():
+            net(zp)
+    torch.set_num_threads(pick_cpu_threads(probe))
     z = torch.randn((1, 4, 96, 96), generator=torch.Generator().manual_seed(7))
     t0 = time.perf_counter()
     with torch.no_grad():
@@ -1233,7 +1238,6 @@ def demofusion_cpu_baseline(budget_s: float):
     from oracle import demofusion as odf
     from oracle import tiling
     c = DEMO
-    torch.set_num_threads(os.cpu_count() or 1)
     L = c["lat"]
     x = synthetic_latent(11, (c["N"], c["C"], L, L)).float()
     local, _, _ = tiling.demofusion_views(L, L, c["window"], c["overlap"])
@@ -1244,10 +1248,15 @@ def demofusion_cpu_baseline(budget_s: float):
     gb = [views[i * gtbs:(i + 1) * gtbs] for i in range(gnb)]
     cf = odf.cosine_factor(c["current_step"], c["t_enc"])
     ident = lambda t, b: t
+
+    def one():
+        with torch.no_grad():
+            odf.sample_one_step(x, lb, gb, c["scale"], True, True, c["sig"], cf, c["cs2"], c["cs3"], ident, ident)
+    torch.set_num_threads(pick_cpu_threads(one))      # the thread count at which the host runs this step fastest
     n, t0 = 0, time.perf_counter()
     with torch.no_grad():
         while True:
-            odf.sample_one_step(x, lb, gb, c["scale"], True, True, c["sig"], cf, c["cs2"], c["cs3"], ident, ident)
+            one()
             n += 1
             if time.perf_counter() - t0 > budget_s or n >= 50:
                 break
