@@ -1043,7 +1043,7 @@ def vae_arm(args, rank, world, local_rank):
         "gpu_launches": None,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (td_conv2d_nhwc, tcgen05 implicit GEMM), 128->128 3x3 on [1,944,944,128]",
                      "achieved": conv_flops / t_conv / 1e12, "peak": tf_burst, "unit": "TFLOP/s", "frac": conv_flops / t_conv / 1e12 / tf_burst,
-                     "traffic": None, "peak_source": peak_src + ", burst (kernel timed alone)", "algorithmic_flops": conv_flops,
+                     "traffic": load_traffic("conv_944_128_128"), "peak_source": peak_src + ", burst (kernel timed alone)", "algorithmic_flops": conv_flops,
                      "avg_launch_us": t_conv * 1e6,
                      "whole_decode": {"algorithmic_flops": flops, "achieved": flops / sec / 1e12, "peak": tf_sust,
                                       "frac": flops / sec / 1e12 / tf_sust, "peak_source": "sustained (inside a long step)"}},
