@@ -16,8 +16,17 @@ every launch reads cold (HBM-resident, not L2-resident) data.
 `e2e` = the same metric through the reference-facing class (MultiDiffusion.kdiff_forward, identity
 denoiser) with the step's latent copied from pinned host memory and the blended result copied back.
 
-`--impl reference` / `cpu_baseline` = the oracle port of the reference's PyTorch tile path
-(oracle/blend.py, bit-identical to the reference) on this box's host cores, identity denoiser.
+`--impl reference` / `cpu_baseline` = the UNMODIFIED reference's `sample_one_step` under the stub host where
+/root/reference exists (`kind: "reference"`), else its op-for-op restatement (oracle/blend.py, bit-identical to the
+reference; `kind: "port"`), on this box's host cores at the thread count that runs it fastest, identity denoiser.
+
+Other BASELINE configs (same JSON contract):
+    --config cfg3   Mixture of Diffusers step (td_blend_mixture heads the roofline object)
+    --config cfg4   tiled VAE decode only, z [1,4,1024,1024] -> 8192 x 8192 RGB through tilevae.VAEHook (one step = one decode;
+                    roofline.bound = "tensor": the dominant tcgen05 convolution + the whole-decode TFLOP/s); --vae-slow
+    --config cfg5   one DemoFusion.sample_one_step at the x4 phase of an SDXL 6144^2 upscale (latent [2,4,768,768])
+    --gpus N        under torchrun: row-strip tile shard for cfg2 (weak scaling by default, strong rides along, in-run
+                    parity_ok), tile round-robin for cfg4, window / view shard for cfg5
 """
 from __future__ import annotations
 
@@ -589,6 +598,13 @@ def gpu_arm(args, rank, world, local_rank):
                         "resident while this one drains; every global access still waits for completion); avg includes the "
                         "inter-kernel gap; *_no_pdl = same loop with plain stream serialisation",
             }
+            roof["mixture"]["traffic"] = load_traffic("blend_mixture")
+            if mod:      # cfg3: the step's dominant kernel is the Mixture-of-Diffusers blend -- it heads the roofline object
+                md = {k: roof[k] for k in ("kernel", "achieved", "frac", "traffic", "algorithmic_bytes", "avg_launch_us", "avg_launch_us_no_pdl")}
+                for k, v in roof["mixture"].items():
+                    roof[k] = v
+                roof["multidiffusion"] = md
+                del roof["mixture"]
             try:
                 roof["vae"] = vae_kernel_rooflines(dev, stream, peak)
             except Exception as e:   # never let the side measurement break the headline line
