@@ -642,6 +642,12 @@ int conv_run(const td_conv_desc* d, const void* x, const void* w, const float* b
     }
     for (const void* ptr : {x, w, (const void*)y, residual, (const void*)(d->bias_per_row ? nullptr : bias), (const void*)d->post_scale, (const void*)d->post_shift})
         if (ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15u) != 0) { td_set_error("td_conv2d_nhwc: tensors (and per-channel vectors) must be 16-byte aligned"); return TD_ERR_INVALID_ARG; }
+    if (d->y2 != nullptr && (d->post_scale == nullptr || d->post_shift == nullptr || d->y2_pitch < d->Cout || d->y2_pitch % 8 != 0 ||
+                             (reinterpret_cast<uintptr_t>(d->y2) & 15u) != 0)) {
+        td_set_error("td_conv2d_nhwc: y2 needs post_scale / post_shift, a 16-byte aligned pointer and a pitch >= Cout in multiples of 8");
+        return TD_ERR_INVALID_ARG;
+    }
+    if ((d->post_scale == nullptr) != (d->post_shift == nullptr)) { td_set_error("td_conv2d_nhwc: post_scale and post_shift come together"); return TD_ERR_INVALID_ARG; }
     const ConvDev dev = conv_dev();
     if (!dev.ok) { td_set_error("td_conv2d_nhwc: device query / shared-memory opt-in failed"); return TD_ERR_CUDA; }
 
@@ -702,14 +708,9 @@ int conv_run(const td_conv_desc* d, const void* x, const void* w, const float* b
     p.is_bf16 = d->dtype == TD_BF16;
     p.bias_per_row = d->bias_per_row;
     p.post_act = d->post_act;
-    if ((d->post_scale == nullptr) != (d->post_shift == nullptr)) { td_set_error("td_conv2d_nhwc: post_scale and post_shift come together"); return TD_ERR_INVALID_ARG; }
     p.alpha = d->alpha;
     p.res_pitch = residual != nullptr ? d->res_pitch : 0;
     p.dual = d->y2 != nullptr ? 1 : 0;
-    if (p.dual && (d->post_scale == nullptr || d->y2_pitch < d->Cout || d->y2_pitch % 8 != 0 || (reinterpret_cast<uintptr_t>(d->y2) & 15u) != 0)) {
-        td_set_error("td_conv2d_nhwc: y2 needs post_scale / post_shift, a 16-byte aligned pointer and a pitch >= Cout in multiples of 8");
-        return TD_ERR_INVALID_ARG;
-    }
     const int n_store_bufs = p.dual ? 4 : 2;
     const int stage_bytes = p.MT * kConvStageA + (p.pair ? bn / 2 : bn) * 128;
     const int avail = dev.smem_optin - 1024 - n_store_bufs * kConvStoreBuf;
