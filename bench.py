@@ -146,6 +146,35 @@ def cpu_reference_step_fn(method: str = "md"):
     return (lambda: blend.multidiffusion_step(x, plan.batched_bboxes, plan.weights, lambda t, bb: t)), "port"
 
 
+def eager_cuda_baseline(method: str = "md", steps: int = 20):
+    """The reference's op sequence (oracle restatement: per-tile slice copies, `x_buffer[slicer] += tile`, where / divide) in
+    stock torch EAGER on this GPU, device-resident tensors, identity denoiser -- what the unmodified reference does on a
+    CUDA device ("the kernel to beat").  Part of the cpu_baseline leg; None without a GPU."""
+    if not torch.cuda.is_available():
+        return None
+    from oracle import blend, synth, tiling
+    c = CFG
+    x = synth.latent(0, (c["N"], c["C"], c["H"], c["W"]), torch.float16).cuda()
+    plan = tiling.GridPlan(c["W"], c["H"], c["tile"], c["tile"], c["overlap"], c["tile_bs"], method == "mod")
+    if method == "mod":
+        step = lambda: blend.mixture_step(x, plan.batched_bboxes, plan.tile_weights, plan.rescale_factor, lambda t, bb: t)
+    else:
+        step = lambda: blend.multidiffusion_step(x, plan.batched_bboxes, plan.weights, lambda t, bb: t)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / steps
+    return {"ms_per_step": ms, "value": mp_per_s(ms / 1e3), "unit": "MP/s",
+            "what": "reference op sequence, stock torch eager on this GPU (device-resident, identity denoiser, host launch overhead included)"}
+
+
 def pick_cpu_threads(step) -> int:
     """Use the thread count at which the reference path is FASTEST on this host (tiny per-tile ops
     get slower with too many OpenMP threads); the count used is reported as `cores`."""
@@ -634,7 +663,8 @@ def gpu_arm(args, rank, world, local_rank):
                              "sample": f"{cpu_done} sampler steps of the same workload ("
                                        + ("unmodified reference sample_one_step" if cpu_kind == "reference" else
                                           "op-for-op restatement of the reference's sample_one_step") +
-                                       f", identity denoiser, torch CPU, {cpu_threads} threads)"},
+                                       f", identity denoiser, torch CPU, {cpu_threads} threads)",
+                             "eager_cuda": eager_cuda_baseline("mod" if mod else "md") if world == 1 and args.cpu_budget > 1.0 else None},
             "impl": "b200",
         }
         print(json.dumps(line), flush=True)

@@ -58,7 +58,7 @@ def multidiffusion_step(x_in: torch.Tensor, batched_bboxes: List[List[BBox]], we
         x_tile = scatter_tiles(x_in, bboxes)
         out = denoise(x_tile, bboxes)
         accumulate_md(x_buffer, out, bboxes, N)
-    w = torch.from_numpy(weights).view(1, 1, *weights.shape)
+    w = torch.from_numpy(weights).view(1, 1, *weights.shape).to(x_in.device)
     return normalise_md(x_buffer, w)
 
 
@@ -68,8 +68,8 @@ def mixture_step(x_in: torch.Tensor, batched_bboxes: List[List[BBox]], tile_weig
     """mixtureofdiffusers.py:61-179 (grid part).  Returns x_buffer (x_in.dtype)."""
     N = x_in.shape[0]
     x_buffer = torch.zeros_like(x_in)
-    tw = torch.from_numpy(tile_weights)
-    rf = torch.from_numpy(rescale_factor).view(1, 1, *rescale_factor.shape)
+    tw = torch.from_numpy(tile_weights).to(x_in.device)
+    rf = torch.from_numpy(rescale_factor).view(1, 1, *rescale_factor.shape).to(x_in.device)
     for bboxes in batched_bboxes:
         x_tile = scatter_tiles(x_in, bboxes)
         out = denoise(x_tile, bboxes)

@@ -34,5 +34,5 @@ def test_gpu_arm_takes_nothing_from_the_oracle():
     for m in re.finditer(r"from oracle import [^\n]+", src):
         head = src[:m.start()]
         fn = re.findall(r"\ndef (\w+)\(", head)[-1]
-        assert fn in ("cpu_reference_step_fn", "vae_cpu_baseline", "demofusion_cpu_baseline"), f"`{m.group(0)}` inside {fn}(): the GPU arm must not use the oracle"
+        assert fn in ("cpu_reference_step_fn", "eager_cuda_baseline", "vae_cpu_baseline", "demofusion_cpu_baseline"), f"`{m.group(0)}` inside {fn}(): the GPU arm must not use the oracle"
     assert "import oracle" not in src
