@@ -267,7 +267,9 @@ _OVERLAP_PUSH = os.environ.get("TD_STRIP_OVERLAP_PUSH", "0") == "1"
 
 
 class _PeerFlags:
-    """One flag array + device-side step counter per rank, mapped into every rank (see PeerExchange)."""
+    """One flag array (slot r = what rank r has published to me) + this rank's device-side expect counter, mapped into
+    every rank through CUDA IPC.  A push advances the sender's slot on each target by TD_PUSH_CTAS; a waiter compares
+    the slots of its senders with its own expect counter (td_push_regions / td_blend_multidiffusion_rows)."""
 
     def __init__(self, device, group):
         self.device, self.group = device, group
@@ -293,13 +295,6 @@ class _PeerFlags:
     @property
     def counter_ptr(self) -> int:
         return self._buf.ptr + 128
-
-    def signal(self, targets: Sequence[int]):
-        """Bump this rank's counter and publish it into slot `rank` of the flag arrays of `targets` (and its own)."""
-        tbl = [self.ptrs[r] if (r in targets or r == self.rank) else self.ptrs[self.rank] for r in range(self.world)]
-        table = (ctypes.c_void_p * self.world)(*tbl)
-        with torch.cuda.device(self.device):
-            check(lib.td_peer_signal(table, self.world, self.rank, ctypes.c_void_p(self.counter_ptr), _cabi.current_stream_ptr(self.device)))
 
     def set_expect(self, value: int):
         """Initial value of this set's expect counter (sets whose waiters are advanced through another push's bump_next)."""
@@ -330,11 +325,6 @@ class _PeerFlags:
         """(flags pointer, count, value pointer) for a wait on ranks [first, first + count)."""
         return ctypes.c_void_p(self.ptrs[self.rank] + 4 * first), count, ctypes.c_void_p(self.counter_ptr)
 
-    def wait(self, first: int, count: int):
-        f, c, v = self.wait_args(first, count)
-        with torch.cuda.device(self.device):
-            check(lib.td_peer_wait(f, c, v, _cabi.current_stream_ptr(self.device)))
-
     def close(self):
         for p in self._opened:
             lib.td_ipc_close(ctypes.c_void_p(p))
@@ -344,9 +334,10 @@ class _PeerFlags:
 
 class StripExchange:
     """Device side of the row-strip shard: the halo buffer and the blended latent of every rank are cudaMalloc'd
-    and mapped into their neighbours through CUDA IPC; halos are PUSHED (strided copies with peer destinations, over
-    NVLink), published with a release store of the step counter, and awaited inside the blend kernel / by a one-warp
-    wait kernel.  No NCCL call on the data path; every launch is replayable from a CUDA graph."""
+    and mapped into their neighbours through CUDA IPC; halos are PUSHED over NVLink and published in the same launch
+    (td_push_regions: 128-bit stores into peer memory, one release add per CTA into the target's flag slot), and awaited
+    inside the blend kernel (only by the CTAs that read a halo band) / by the latent-halo push that closes the step.
+    No NCCL call on the data path; every launch is replayable from a CUDA graph (all counters live on the device)."""
 
     def __init__(self, shard: StripShard, N: int, C: int, tile_w: int, W: int, dtype: torch.dtype, device: torch.device, group=None):
         self.shard, self.N, self.C, self.tw, self.W, self.dtype, self.device, self.group = shard, N, C, tile_w, W, dtype, device, group
@@ -391,12 +382,6 @@ class StripExchange:
         sh = self.shard
         n = len(sh.bands()) * sh.cols * self.N
         return self._own[:n * self.C * sh.tile_h * self.tw].view(n, self.C, sh.tile_h, self.tw)
-
-    def _copy_rows(self, src_ptr: int, dst_ptr: int, planes: int, rows: int, cols: int, src_plane: int, src_pitch: int, dst_plane: int,
-                   dst_pitch: int, dtype: torch.dtype):
-        with torch.cuda.device(self.device):
-            check(lib.td_copy_region(ctypes.c_void_p(src_ptr), ctypes.c_void_p(dst_ptr), planes, rows, cols, src_plane, src_pitch, dst_plane,
-                                     dst_pitch, _cabi.dtype_code(dtype), _cabi.current_stream_ptr(self.device)))
 
     def push_tile_halos(self):
         """Rows [v0, v1) of every tile of my band i -> the halo slot of band i on rank q (peer memory), then signal:
