@@ -1106,7 +1106,8 @@ def vae_arm(args, rank, world, local_rank):
 
 def vae_cpu_baseline(budget_s: float):
     """The reference's tiled VAE algorithm on the host cores (oracle restatement, fp32 torch CPU) on a bounded sample:
-    a 96 x 96 latent (768 x 768 px image), decoder tile 48, fast mode."""
+    a 48 / 64 / 96-pixel latent (384^2 .. 768^2 px image) decoded in 4 tiles, fast mode; thread count and sample size are
+    chosen from a short probe so that the leg stays within about 2.5 x --cpu-budget seconds."""
     if budget_s <= 1.0:      # measurement runs that only want the GPU numbers
         return {"value": None, "unit": "MP/s", "cores": 0, "kind": "port", "seconds": 0.0, "sample": "skipped (--cpu-budget <= 1)"}
     from oracle import ldm_vae, vae
@@ -1117,14 +1118,23 @@ def vae_cpu_baseline(budget_s: float):
         with torch.no_grad():
             net(zp)
     torch.set_num_threads(pick_cpu_threads(probe))
-    z = torch.randn((1, 4, 96, 96), generator=torch.Generator().manual_seed(7))
+    t0 = time.perf_counter()
+    probe()
+    t_probe = time.perf_counter() - t0
+    # bounded sample: the largest of three tiled decodes (4 tiles of (L/2 + 22)^2 latent pixels each + the estimator pass)
+    # whose predicted time stays within ~2.5 x the budget (default 12 s -> <= 30 s of host work)
+    L = 48
+    for cand in (64, 96):
+        if t_probe * 4 * (cand // 2 + 22) ** 2 / 24 ** 2 * 1.15 <= 2.5 * budget_s:
+            L = cand
+    z = torch.randn((1, 4, L, L), generator=torch.Generator().manual_seed(7))
     t0 = time.perf_counter()
     with torch.no_grad():
-        vae.vae_hook_call(net, z, 48, True, True, False)
+        vae.vae_hook_call(net, z, L // 2, True, True, False)
     dt = time.perf_counter() - t0
-    return {"value": (96 * 8) ** 2 / 1e6 / dt, "unit": "MP/s", "cores": torch.get_num_threads(), "kind": "port", "seconds": dt,
-            "sample": "one tiled decode of a 96x96 latent (768x768 px, decoder tile 48, fast mode), oracle restatement of "
-                      "scripts/tilevae.py on torch CPU fp32"}
+    return {"value": (L * 8) ** 2 / 1e6 / dt, "unit": "MP/s", "cores": torch.get_num_threads(), "kind": "port", "seconds": dt,
+            "sample": f"one tiled decode of a {L}x{L} latent ({L * 8}x{L * 8} px, decoder tile {L // 2}, fast mode: 4 tiles + estimator pass), "
+                      "oracle restatement of scripts/tilevae.py on torch CPU fp32"}
 
 
 def vae_reference_arm(args, rank):
